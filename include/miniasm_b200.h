@@ -1,0 +1,164 @@
+/* miniasm_b200.h -- C ABI of libminiasm_b200.so (plain pointers and sizes; no torch, no C++ types).
+ *
+ * Two levels:
+ *
+ *  1. DROP-IN level.  The reference (lh3/miniasm @ v0.3-r179) has no plugin layer; its seam is the C API
+ *     its own driver main.c:108-199 calls.  Every entry point below has the same name, argument meaning,
+ *     ownership rules and stderr/exit behaviour as the reference function it replaces, so the reference's
+ *     main.o links against this library unchanged ("link seam").  Arrays are host memory
+ *     (malloc/calloc/realloc family); each call moves its operands to the B200, runs the CUDA path and
+ *     moves the result back.  The struct layouts are ABI: main.c and the writers read fields directly.
+ *
+ *  2. FUSED level (mab_*).  One opaque device-resident context keeps hits, arcs and the graph in HBM
+ *     across stages; only counts and the final unitig graph cross PCIe.  The CLI and bench.py use this.
+ *
+ * There is no CPU fallback: without a usable CUDA device every entry point prints "[E::miniasm_b200]"
+ * and exits non-zero.
+ */
+#ifndef MINIASM_B200_H
+#define MINIASM_B200_H
+
+#include <stdio.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ ABI structs ------------------- */
+
+/* replaces sd_seq_t / sdict_t, sdict.h:6-15 */
+typedef struct { char *name; uint32_t len, aux:31, del:1; } sd_seq_t;
+typedef struct { uint32_t n_seq, m_seq; sd_seq_t *seq; void *h; } sdict_t;
+
+/* replaces asg_arc_t / asg_seq_t / asg_t, asg.h:7-23 */
+typedef struct { uint64_t ul; uint32_t v; uint32_t ol:31, del:1; } asg_arc_t;
+typedef struct { uint32_t len:31, del:1; } asg_seq_t;
+typedef struct {
+	uint32_t m_arc, n_arc:31, is_srt:1;
+	asg_arc_t *arc;
+	uint32_t m_seq, n_seq:31, is_symm:1;
+	asg_seq_t *seq;
+	uint64_t *idx;
+} asg_t;
+
+/* replaces ma_opt_t / ma_hit_t / ma_sub_t / ma_utg_t / ma_ug_t, miniasm.h:12-55 */
+typedef struct {
+	int min_span, min_match, min_dp;
+	float min_iden;
+	int max_hang, min_ovlp;
+	float int_frac;
+	int gap_fuzz, n_rounds, bub_dist, max_ext;
+	float min_ovlp_drop_ratio, max_ovlp_drop_ratio, final_ovlp_drop_ratio;
+} ma_opt_t;
+
+typedef struct {
+	uint64_t qns;
+	uint32_t qe, tn, ts, te;
+	uint32_t ml:31, rev:1;
+	uint32_t bl:31, del:1;
+} ma_hit_t;
+
+typedef struct { uint32_t s:31, del:1, e; } ma_sub_t;
+
+typedef struct {
+	uint32_t len:31, circ:1;
+	uint32_t start, end;
+	uint32_t m, n;
+	uint64_t *a;
+	char *s;
+} ma_utg_t;
+
+typedef struct { size_t n, m; ma_utg_t *a; } ma_utg_v;
+typedef struct { ma_utg_v u; asg_t *g; } ma_ug_t;
+
+/* replaces paf_file_t / paf_rec_t, paf.h:9-24 */
+#ifndef KSTRING_T
+#define KSTRING_T kstring_t
+typedef struct __kstring_t { size_t l, m; char *s; } kstring_t;
+#endif
+typedef struct { void *fp; kstring_t buf; } paf_file_t;
+typedef struct {
+	const char *qn, *tn;
+	uint32_t ql, qs, qe, tl, ts, te;
+	uint32_t ml:31, rev:1, bl;
+} paf_rec_t;
+
+extern int ma_verbose;                                   /* common.c:3 */
+
+/* ------------------------------------------------------------------ drop-in level ------------------ */
+/* host utilities (host C in the reference too): sys.c:7-46, sdict.c:8-86, paf.c:9-67, common.c:5-23 */
+double sys_cputime(void);
+double sys_realtime(void);
+void sys_init(void);
+const char *sys_timestamp(void);
+sdict_t *sd_init(void);
+void sd_destroy(sdict_t *d);
+int32_t sd_put(sdict_t *d, const char *name, uint32_t len);
+int32_t sd_get(const sdict_t *d, const char *name);
+int32_t *sd_squeeze(sdict_t *d);
+paf_file_t *paf_open(const char *fn);
+int paf_close(paf_file_t *pf);
+int paf_read(paf_file_t *pf, paf_rec_t *r);
+void ma_opt_init(ma_opt_t *opt);
+
+/* stage (i): hit.c:38-256 (miniasm.h:61-68) */
+sdict_t *ma_hit_no_cont(const char *fn, int min_span, int min_match, int max_hang, float int_frac);
+ma_hit_t *ma_hit_read(const char *fn, int min_span, int min_match, sdict_t *d, size_t *n, int bi_dir, const sdict_t *excl);
+ma_sub_t *ma_hit_sub(int min_dp, float min_iden, int end_clip, size_t n, const ma_hit_t *a, size_t n_sub);
+size_t ma_hit_cut(const ma_sub_t *reg, int min_span, size_t n, ma_hit_t *a);
+size_t ma_hit_flt(const ma_sub_t *sub, int max_hang, int min_ovlp, size_t n, ma_hit_t *a, float *cov);
+void ma_sub_merge(size_t n_sub, ma_sub_t *a, const ma_sub_t *b);
+size_t ma_hit_contained(const ma_opt_t *opt, sdict_t *d, ma_sub_t *sub, size_t n, ma_hit_t *a);
+
+/* stage (ii): asm.c:9-39, asg.c:11-193 (miniasm.h:70, asg.h:31-38) */
+asg_t *ma_sg_gen(const ma_opt_t *opt, const sdict_t *d, const ma_sub_t *sub, size_t n_hits, const ma_hit_t *hit);
+asg_t *asg_init(void);
+void asg_destroy(asg_t *g);
+void asg_seq_set(asg_t *g, int sid, int len, int del);
+void asg_arc_sort(asg_t *g);
+void asg_arc_index(asg_t *g);
+void asg_arc_rm(asg_t *g);
+void asg_cleanup(asg_t *g);
+void asg_symm(asg_t *g);
+int asg_arc_del_multi(asg_t *g);
+int asg_arc_del_asymm(asg_t *g);
+int asg_arc_del_trans(asg_t *g, int fuzz);
+
+/* stage (iii): asg.c:83-101,199-433, asm.c:41-290 (asg.h:36-42, miniasm.h:71-75) */
+int asg_arc_del_short(asg_t *g, float drop_ratio);
+int asg_cut_tip(asg_t *g, int max_ext);
+int asg_cut_internal(asg_t *g, int max_ext);
+int asg_cut_biloop(asg_t *g, int max_ext);
+int asg_pop_bubble(asg_t *g, int max_dist);
+ma_ug_t *ma_ug_gen(asg_t *g);
+int ma_ug_seq(ma_ug_t *g, const sdict_t *d, const ma_sub_t *sub, const char *fn);
+void ma_ug_print(const ma_ug_t *ug, const sdict_t *d, const ma_sub_t *sub, FILE *fp);
+void ma_sg_print(const asg_t *g, const sdict_t *d, const ma_sub_t *sub, FILE *fp);
+void ma_ug_destroy(ma_ug_t *ug);
+
+/* ------------------------------------------------------------------ fused level -------------------- */
+typedef struct mab_ctx mab_ctx_t;
+
+/* counters a run exposes (reference prints the same numbers in its [M::...] stderr lines) */
+typedef struct {
+	uint64_t n_lines, n_hits_stored, n_seq_in;          /* ma_hit_read */
+	uint64_t n_hits_final, n_seq_final;                 /* after ma_hit_contained */
+	uint64_t n_arc_sg;                                  /* ma_sg_gen */
+	uint64_t n_arc_trans_in, n_reduced, trans_inner;    /* asg_arc_del_trans: arcs in, reduced, inner-loop iterations */
+	uint64_t n_arc_final, n_utg;
+	double   ms_del_trans_kernel;                       /* CUDA-event time of the transitive-reduction kernel */
+	uint64_t n_kernel_launches, n_lib_calls;
+} mab_stats_t;
+
+mab_ctx_t *mab_create(int device);                      /* exits if the device cannot be initialised */
+void mab_destroy(mab_ctx_t *ctx);
+void mab_set_verbose(int level);                        /* 0 silences the [M::...] lines of both levels */
+const mab_stats_t *mab_stats(const mab_ctx_t *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

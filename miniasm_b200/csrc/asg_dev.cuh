@@ -1,0 +1,37 @@
+// asg_dev.cuh -- device-resident string graph (stage ii + the arc-level parts of stage iii).
+// Counterpart of the reference's asg_t container and passes (asg.h:13-42, asg.c:22-193).
+#pragma once
+#include "mab_common.cuh"
+
+struct DGraph {
+	uint32_t n_seq = 0;       // reads; vertices = 2*n_seq
+	uint32_t n_arc = 0;
+	size_t   m_arc = 0;       // capacity of arc / arc2 (elements)
+	bool is_srt = false, is_symm = false, has_idx = false;
+	uint32_t len_bits = 32;   // every arc length < 2^len_bits (lets the radix sort skip dead key bits)
+	DArc *arc = nullptr;      // canonical AoS arc array
+	DArc *arc2 = nullptr;     // ping-pong buffer for compaction / sort output
+	uint32_t *seq = nullptr;  // len:31 | del<<31 per read
+	uint64_t *idx = nullptr;  // first<<32 | count per vertex
+};
+
+void dg_reserve(MabDev &d, DGraph &g, size_t m_arc);
+void dg_set_nseq(MabDev &d, DGraph &g, uint32_t n_seq);
+void dg_free(MabDev &d, DGraph &g);
+
+// asg.c:57-70 (+ optional external deletion flags produced by dg_del_trans)
+void dg_arc_rm(MabDev &d, DGraph &g, const uint8_t *flag);
+void dg_arc_sort(MabDev &d, DGraph &g);          // asg.c:22-25
+void dg_arc_index(MabDev &d, DGraph &g);         // asg.c:27-42
+void dg_cleanup(MabDev &d, DGraph &g, const uint8_t *flag = nullptr); // asg.c:72-80
+uint32_t dg_del_multi(MabDev &d, DGraph &g);     // asg.c:104-121
+uint32_t dg_del_asymm(MabDev &d, DGraph &g);     // asg.c:124-138
+void dg_symm(MabDev &d, DGraph &g);              // asg.c:140-145
+uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz);  // asg.c:148-193
+uint32_t dg_del_short(MabDev &d, DGraph &g, float ratio);    // asg.c:83-101
+
+// statistics of the last dg_del_trans call (for the roofline arithmetic in bench.py)
+struct DelTransStats { uint64_t n_arc_in, n_vtx, inner_iters, n_reduced, n_big; float kernel_ms; };
+extern DelTransStats g_del_trans_stats;
+
+extern int mab_verbose;   // mirrors ma_verbose (common.c:3): >=3 prints the reference's [M::...] lines
