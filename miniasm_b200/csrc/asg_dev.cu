@@ -313,15 +313,17 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 			ti[i] = __ldg(idx + a.v);
 		}
 		__syncwarp();
+		bool dup = false;
 		for (uint32_t i = lane; i < nv; i += 32) {
 			uint32_t x = tv[i], h = dt_hash(x, DT_HASH - 1);
 			for (;;) {
 				uint32_t prev = atomicCAS(&hs[h], DT_EMPTY, i);
 				if (prev == DT_EMPTY) { rep[i] = (uint8_t)i; break; }
-				if (tv[prev] == x) { rep[i] = (uint8_t)prev; break; }
+				if (tv[prev] == x) { rep[i] = (uint8_t)prev; dup = true; break; }
 				h = (h + 1) & (DT_HASH - 1);
 			}
 		}
+		const bool has_dup = __any_sync(0xffffffffu, dup); // multi-arcs: several slab entries share one mark
 		__syncwarp();
 		const uint32_t L = tl[nv - 1] + fuzz;
 		for (uint32_t i = 0; i < nv; ++i) {
@@ -353,8 +355,17 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 			}
 			__syncwarp();
 		}
+		// The reference clears mark[target] right after looking at the first arc to that target
+		// (asg.c:181-184), so of several arcs to one reduced target only the lowest-index one is deleted.
+		uint32_t *fmin = reinterpret_cast<uint32_t*>(ti);
+		if (has_dup) {
+			for (uint32_t i = lane; i < nv; i += 32) fmin[i] = DT_EMPTY;
+			__syncwarp();
+			for (uint32_t i = lane; i < nv; i += 32) atomicMin(&fmin[rep[i]], i);
+			__syncwarp();
+		}
 		for (uint32_t i = lane; i < nv; i += 32) {
-			bool r = st[rep[i]] == 2;
+			bool r = st[rep[i]] == 2 && (!has_dup || fmin[rep[i]] == i);
 			flag[off + i] = r;
 			n_red += r;
 		}
@@ -368,10 +379,10 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 }
 
 // CTA per vertex, slabs of DT_MAXD < nv <= DT_BIG_MAXD.  Dynamic shared memory:
-//   tv[DT_BIG_MAXD] | hash[2*DT_BIG_MAXD] | rep (u16)[DT_BIG_MAXD] | st (u8)[DT_BIG_MAXD]
+//   tv[DT_BIG_MAXD] | hash[2*DT_BIG_MAXD] | fmin[DT_BIG_MAXD] | rep (u16)[DT_BIG_MAXD] | st (u8)[DT_BIG_MAXD]
 constexpr int DT_BIG_MAXD = 8192;
 constexpr int DT_BIG_HASH = 2 * DT_BIG_MAXD;
-constexpr size_t DT_BIG_SMEM = (size_t)DT_BIG_MAXD * 4 + (size_t)DT_BIG_HASH * 4 + (size_t)DT_BIG_MAXD * 2 + DT_BIG_MAXD;
+constexpr size_t DT_BIG_SMEM = (size_t)DT_BIG_MAXD * 4 + (size_t)DT_BIG_HASH * 4 + (size_t)DT_BIG_MAXD * 4 + (size_t)DT_BIG_MAXD * 2 + DT_BIG_MAXD;
 
 __global__ void __launch_bounds__(256)
 k_del_trans_cta(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, uint32_t fuzz, uint8_t *__restrict__ flag,
@@ -380,7 +391,8 @@ k_del_trans_cta(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, 
 	extern __shared__ __align__(16) unsigned char smem[];
 	uint32_t *tv = (uint32_t*)smem;
 	uint32_t *hs = tv + DT_BIG_MAXD;
-	uint16_t *rep = (uint16_t*)(hs + DT_BIG_HASH);
+	uint32_t *fmin = hs + DT_BIG_HASH;
+	uint16_t *rep = (uint16_t*)(fmin + DT_BIG_MAXD);
 	uint8_t *st = (uint8_t*)(rep + DT_BIG_MAXD);
 	__shared__ uint32_t s_go, s_red;
 	__shared__ unsigned long long s_inner;
@@ -396,7 +408,7 @@ k_del_trans_cta(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, 
 		}
 		if (tid == 0) s_red = 0, s_inner = 0;
 		for (uint32_t i = tid; i < DT_BIG_HASH; i += nt) hs[i] = DT_EMPTY;
-		for (uint32_t i = tid; i < nv; i += nt) tv[i] = arc[off + i].v, st[i] = 1;
+		for (uint32_t i = tid; i < nv; i += nt) tv[i] = arc[off + i].v, st[i] = 1, fmin[i] = DT_EMPTY;
 		__syncthreads();
 		for (uint32_t i = tid; i < nv; i += nt) {
 			uint32_t x = tv[i], h = dt_hash(x, DT_BIG_HASH - 1);
@@ -407,6 +419,8 @@ k_del_trans_cta(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, 
 				h = (h + 1) & (DT_BIG_HASH - 1);
 			}
 		}
+		__syncthreads();
+		for (uint32_t i = tid; i < nv; i += nt) atomicMin(&fmin[rep[i]], i); // lowest slab position per target
 		__syncthreads();
 		const uint32_t L = (uint32_t)arc[off + nv - 1].ul + fuzz;
 		for (uint32_t i = 0; i < nv; ++i) {
@@ -445,7 +459,7 @@ k_del_trans_cta(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, 
 		}
 		unsigned r_cnt = 0;
 		for (uint32_t i = tid; i < nv; i += nt) {
-			bool r = st[rep[i]] == 2;
+			bool r = st[rep[i]] == 2 && fmin[rep[i]] == i; // only the first arc to a reduced target goes (asg.c:181-184)
 			flag[off + i] = r;
 			r_cnt += r;
 		}
@@ -463,7 +477,7 @@ k_del_trans_cta(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, 
 // reference's own formulation (mark[] indexed by target vertex), the j loop spread over the CTA.
 __global__ void __launch_bounds__(1024)
 k_del_trans_huge(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, uint32_t fuzz, uint8_t *__restrict__ flag,
-                 const uint32_t *__restrict__ huge_list, uint32_t n_huge, uint8_t *mark, unsigned long long *scal)
+                 const uint32_t *__restrict__ huge_list, uint32_t n_huge, uint8_t *mark, uint32_t *first_pos, unsigned long long *scal)
 {
 	__shared__ uint32_t s_go, s_red;
 	__shared__ unsigned long long s_inner;
@@ -474,7 +488,7 @@ k_del_trans_huge(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 		const uint32_t v = huge_list[b];
 		const uint64_t iv = idx[v];
 		const uint32_t nv = (uint32_t)iv, off = (uint32_t)(iv >> 32);
-		for (uint32_t i = tid; i < nv; i += nt) mark[arc[off + i].v] = 1;
+		for (uint32_t i = tid; i < nv; i += nt) mark[arc[off + i].v] = 1, atomicMin(&first_pos[arc[off + i].v], i);
 		__syncthreads();
 		const uint32_t L = (uint32_t)arc[off + nv - 1].ul + fuzz;
 		for (uint32_t i = 0; i < nv; ++i) {
@@ -503,13 +517,13 @@ k_del_trans_huge(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 		}
 		unsigned r_cnt = 0;
 		for (uint32_t i = tid; i < nv; i += nt) {
-			bool r = mark[arc[off + i].v] == 2;
+			bool r = mark[arc[off + i].v] == 2 && first_pos[arc[off + i].v] == i;
 			flag[off + i] = r;
 			r_cnt += r;
 		}
 		if (r_cnt) atomicAdd(&s_red, r_cnt);
 		__syncthreads();
-		for (uint32_t i = tid; i < nv; i += nt) mark[arc[off + i].v] = 0;
+		for (uint32_t i = tid; i < nv; i += nt) mark[arc[off + i].v] = 0, first_pos[arc[off + i].v] = 0xffffffffu;
 		__syncthreads();
 	}
 	if (tid == 0) {
@@ -553,9 +567,11 @@ uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz)
 			uint32_t n_huge = (uint32_t)d.get_scal(SC_AUX2);
 			if (n_huge) {
 				uint8_t *mark = mab_alloc<uint8_t>(d, n_vtx);
+				uint32_t *first_pos = mab_alloc<uint32_t>(d, n_vtx);
 				MAB_CUDA(cudaMemsetAsync(mark, 0, n_vtx, d.stream));
-				MAB_LAUNCH(d, k_del_trans_huge, 1, 1024, 0, g.arc, g.idx, fuzz, flag, huge, n_huge, mark, d.d_scal);
-				d.free(mark);
+				MAB_CUDA(cudaMemsetAsync(first_pos, 0xff, (size_t)n_vtx * 4, d.stream));
+				MAB_LAUNCH(d, k_del_trans_huge, 1, 1024, 0, g.arc, g.idx, fuzz, flag, huge, n_huge, mark, first_pos, d.d_scal);
+				d.free(mark); d.free(first_pos);
 			}
 			d.free(huge);
 		}

@@ -1,0 +1,510 @@
+// hit_dev.cu -- stage (i) on the GPU: ma_hit_sort / ma_hit_sub / ma_hit_cut / ma_hit_flt / ma_sub_merge /
+// ma_hit_contained / ma_sg_gen (hit.c:19-36,109-256; asm.c:9-39).  Hits are 32-byte records moved with
+// two 128-bit accesses; the per-read interval tables (8 B/read) are gathered through L2.
+#include "hit_dev.cuh"
+#include "hit2arc.cuh"
+#include <cub/cub.cuh>
+
+extern "C" int ma_verbose;              // hit.c prints its [M::fn::timestamp] lines only when ma_verbose >= 3
+extern "C" const char *sys_timestamp(void);
+#define ma_verbose_dev ma_verbose
+
+__device__ __forceinline__ DHit ld_hit(const DHit *p)
+{
+	const uint4 *q = reinterpret_cast<const uint4*>(p);
+	uint4 a = __ldg(q), b = __ldg(q + 1);
+	DHit h;
+	h.qns = (uint64_t)a.y << 32 | a.x; h.qe = a.z; h.tn = a.w;
+	h.ts = b.x; h.te = b.y; h.ml_rev = b.z; h.bl_del = b.w;
+	return h;
+}
+__device__ __forceinline__ DHit ld_hit_rw(const DHit *p) // for kernels that also store to the array
+{
+	const uint4 *q = reinterpret_cast<const uint4*>(p);
+	uint4 a = q[0], b = q[1];
+	DHit h;
+	h.qns = (uint64_t)a.y << 32 | a.x; h.qe = a.z; h.tn = a.w;
+	h.ts = b.x; h.te = b.y; h.ml_rev = b.z; h.bl_del = b.w;
+	return h;
+}
+__device__ __forceinline__ void st_hit(DHit *p, const DHit &h)
+{
+	uint4 *q = reinterpret_cast<uint4*>(p);
+	q[0] = make_uint4((uint32_t)h.qns, (uint32_t)(h.qns >> 32), h.qe, h.tn);
+	q[1] = make_uint4(h.ts, h.te, h.ml_rev, h.bl_del);
+}
+
+static inline uint32_t bits_for(uint64_t x) { uint32_t b = 0; while (x) ++b, x >>= 1; return b ? b : 1; }
+
+void dh_reserve(MabDev &d, DHits &h, size_t m)
+{
+	if (m <= h.m) return;
+	DHit *na = mab_alloc<DHit>(d, m), *nb = mab_alloc<DHit>(d, m);
+	if (h.n) MAB_CUDA(cudaMemcpyAsync(na, h.a, h.n * sizeof(DHit), cudaMemcpyDeviceToDevice, d.stream));
+	d.free(h.a); d.free(h.a2);
+	h.a = na, h.a2 = nb, h.m = m;
+}
+
+void dh_free(MabDev &d, DHits &h)
+{
+	d.free(h.a); d.free(h.a2);
+	h = DHits();
+}
+
+// stable compaction of hits by a byte flag array; returns the number kept
+static size_t select_hits(MabDev &d, DHits &h, const uint8_t *flag)
+{
+	if (h.n == 0) return 0;
+	size_t tb = 0;
+	unsigned long long *d_n = d.d_scal + SC_NSEL;
+	cub::DeviceSelect::Flagged(nullptr, tb, h.a, flag, h.a2, d_n, (int64_t)h.n, d.stream);
+	void *tmp = d.tmp(tb);
+	cub::DeviceSelect::Flagged(tmp, tb, h.a, flag, h.a2, d_n, (int64_t)h.n, d.stream);
+	++d.n_lib;
+	size_t n = (size_t)d.get_scal(SC_NSEL);
+	DHit *t = h.a; h.a = h.a2; h.a2 = t;
+	h.n = n;
+	return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ma_hit_sort: (key = qid << lb | qs, payload = position) radix sort, then a 32-byte gather
+// ---------------------------------------------------------------------------------------------
+__global__ void k_hit_keys(const DHit *a, size_t n, uint32_t lb, uint64_t *key, uint32_t *pos)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		uint64_t q = a[i].qns;
+		key[i] = lb >= 32 ? q : ((q >> 32) << lb | (uint32_t)q);
+		pos[i] = (uint32_t)i;
+	}
+}
+__global__ void k_hit_gather(const DHit *a, const uint32_t *pos, size_t n, DHit *out)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		st_hit(out + i, ld_hit(a + pos[i]));
+}
+
+void dh_sort(MabDev &d, DHits &h, uint32_t max_len_bits)
+{
+	if (h.n < 2) return;
+	if (h.n >= (1ull << 32)) { fprintf(stderr, "[E::miniasm_b200] more than 2^32 hits on one GPU\n"); exit(73); }
+	uint32_t lb = max_len_bits > 32 ? 32 : max_len_bits;
+	int end_bit = (int)(lb + bits_for(h.n_seq ? h.n_seq - 1 : 0));
+	uint64_t *ka = mab_alloc<uint64_t>(d, h.n), *kb = mab_alloc<uint64_t>(d, h.n);
+	uint32_t *pa = mab_alloc<uint32_t>(d, h.n), *pb = mab_alloc<uint32_t>(d, h.n);
+	MAB_LAUNCH(d, k_hit_keys, mab_grid(h.n, 256), 256, 0, h.a, h.n, lb, ka, pa);
+	cub::DoubleBuffer<uint64_t> dk(ka, kb);
+	cub::DoubleBuffer<uint32_t> dp(pa, pb);
+	size_t tb = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dp, (int64_t)h.n, 0, end_bit, d.stream);
+	void *tmp = d.tmp(tb);
+	cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dp, (int64_t)h.n, 0, end_bit, d.stream);
+	++d.n_lib;
+	MAB_LAUNCH(d, k_hit_gather, mab_grid(h.n, 256), 256, 0, h.a, dp.Current(), h.n, h.a2);
+	DHit *t = h.a; h.a = h.a2; h.a2 = t;
+	d.free(ka); d.free(kb); d.free(pa); d.free(pb);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ma_hit_sub (hit.c:109-160)
+//   group = maximal run of equal query id;  per group collect (qs+clip)<<1 and (qe-clip)<<1|1 of the hits
+//   with tn != qid and ml >= bl*min_iden (float32) and qe > qs;  sort;  sweep the depth;  keep the FIRST
+//   longest stretch with depth >= min_dp;  sub = {start-clip, end+clip} or del.
+// GPU shape: every hit emits two 64-bit keys  qid<<33 | invalid<<32 | endpoint  (invalid keys sink to the
+// end of their group), one device-wide radix sort orders all groups at once, then one warp per group
+// sweeps its 2*count keys with a warp scan.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_group_bounds(const DHit *a, size_t n, uint32_t *g32)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		uint32_t q = (uint32_t)(a[i].qns >> 32);
+		if (i == 0 || (uint32_t)(a[i - 1].qns >> 32) != q) g32[2 * (size_t)q + 1] = (uint32_t)i;
+		if (i == n - 1 || (uint32_t)(a[i + 1].qns >> 32) != q) g32[2 * (size_t)q] = (uint32_t)(i + 1);
+	}
+}
+
+__global__ void k_sub_keys(const DHit *a, size_t n, float min_iden, uint32_t clip, uint64_t *key)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		DHit h = ld_hit(a + i);
+		uint32_t qid = (uint32_t)(h.qns >> 32);
+		int ml = (int)(h.ml_rev & 0x7fffffffu), bl = (int)(h.bl_del & 0x7fffffffu);
+		bool skip = h.tn == qid || (float)ml < __fmul_rn((float)bl, min_iden);
+		uint32_t qs = (uint32_t)h.qns + clip, qe = h.qe - clip;
+		uint64_t base = (uint64_t)qid << 33;
+		if (!skip && qe > qs) {
+			key[2 * i] = base | (uint32_t)(qs << 1);
+			key[2 * i + 1] = base | (uint32_t)(qe << 1 | 1);
+		} else {
+			key[2 * i] = key[2 * i + 1] = base | 1ull << 32;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256)
+k_sub_sweep(const uint64_t *key, const uint64_t *grp, uint32_t n_seq, int min_dp, uint32_t clip, DSub *sub, unsigned long long *n_remained)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+	unsigned remained = 0;
+	for (uint32_t r = wid; r < n_seq; r += nw) {
+		const uint64_t g = grp[r];
+		const uint32_t end = (uint32_t)g, first = (uint32_t)(g >> 32);
+		if (end == 0) continue;                      // read heads no group: stays {0,0,del=0}
+		const size_t k0 = 2 * (size_t)first;
+		const uint32_t nk = 2 * (end - first);
+		int depth = 0;
+		uint32_t carry_start = 0;
+		unsigned long long best = 0;                 // len<<32 | ~index  (max = longest, earliest on ties)
+		uint32_t best_end = 0;
+		for (uint32_t c = 0; c < nk; c += 32) {
+			const uint32_t i = c + lane;
+			uint64_t k = i < nk ? key[k0 + i] : (1ull << 32);
+			const bool valid = !(k >> 32 & 1);
+			const uint32_t pos = (uint32_t)k >> 1;
+			int delta = valid ? ((k & 1) ? -1 : 1) : 0, dp = delta;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, dp, o); if (lane >= o) dp += t; }
+			dp += depth;
+			const int old = dp - delta;
+			const bool up = valid && old < min_dp && dp >= min_dp;
+			const bool down = valid && old >= min_dp && dp < min_dp;
+			const unsigned upm = __ballot_sync(0xffffffffu, up);
+			const unsigned below = upm & ((1u << lane) - 1);
+			const int src = below ? 31 - __clz(below) : 0;
+			uint32_t st = __shfl_sync(0xffffffffu, pos, src);
+			if (!below) st = carry_start;
+			unsigned long long cand = 0;
+			if (down) cand = (unsigned long long)(pos - st) << 32 | (0xffffffffu - i);
+			unsigned long long m = cand;
+			#pragma unroll
+			for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+			if (m > best && (m >> 32) != 0) {
+				const unsigned who = __ballot_sync(0xffffffffu, down && cand == m);
+				best = m;
+				best_end = __shfl_sync(0xffffffffu, pos, __ffs(who) - 1);
+			}
+			if (upm) carry_start = __shfl_sync(0xffffffffu, pos, 31 - __clz(upm));
+			depth = __shfl_sync(0xffffffffu, dp, 31);
+		}
+		if (lane == 0) {
+			DSub s;
+			uint32_t len = (uint32_t)(best >> 32);
+			if (len > 0) {
+				s.s_del = ((best_end - len) - clip) & 0x7fffffffu;
+				s.e = best_end + clip;
+				++remained;
+			} else s.s_del = MAB_DEL_BIT, s.e = 0;
+			sub[r] = s;
+		}
+	}
+	if (lane == 0 && remained) atomicAdd(n_remained, (unsigned long long)remained);
+}
+
+uint64_t dh_sub(MabDev &d, const DHits &h, int min_dp, float min_iden, int end_clip, DSub *sub_out)
+{
+	const uint32_t n_seq = h.n_seq;
+	if (n_seq) MAB_CUDA(cudaMemsetAsync(sub_out, 0, (size_t)n_seq * sizeof(DSub), d.stream));
+	if (h.n == 0 || n_seq == 0) return 0;
+	if (h.n >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 hits on one GPU\n"); exit(73); }
+	uint64_t *grp = mab_alloc<uint64_t>(d, n_seq);
+	MAB_CUDA(cudaMemsetAsync(grp, 0, (size_t)n_seq * 8, d.stream));
+	MAB_LAUNCH(d, k_group_bounds, mab_grid(h.n, 256), 256, 0, h.a, h.n, (uint32_t*)grp);
+	size_t nk = 2 * h.n;
+	uint64_t *ka = mab_alloc<uint64_t>(d, nk), *kb = mab_alloc<uint64_t>(d, nk);
+	MAB_LAUNCH(d, k_sub_keys, mab_grid(h.n, 256), 256, 0, h.a, h.n, min_iden, (uint32_t)end_clip, ka);
+	cub::DoubleBuffer<uint64_t> dk(ka, kb);
+	size_t tb = 0;
+	int end_bit = 33 + (int)bits_for(n_seq - 1);
+	cub::DeviceRadixSort::SortKeys(nullptr, tb, dk, (int64_t)nk, 0, end_bit, d.stream);
+	void *tmp = d.tmp(tb);
+	cub::DeviceRadixSort::SortKeys(tmp, tb, dk, (int64_t)nk, 0, end_bit, d.stream);
+	++d.n_lib;
+	d.zero_scal(SC_COUNT);
+	MAB_LAUNCH(d, k_sub_sweep, mab_grid((size_t)n_seq * 32, 256), 256, 0, dk.Current(), grp, n_seq, min_dp, (uint32_t)end_clip, sub_out, d.d_scal + SC_COUNT);
+	uint64_t n_remained = d.get_scal(SC_COUNT);
+	d.free(ka); d.free(kb); d.free(grp);
+	if (ma_verbose_dev >= 3)
+		fprintf(stderr, "[M::%s::%s] %ld query sequences remain after sub\n", "ma_hit_sub", sys_timestamp(), (long)n_remained);
+	return n_remained;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ma_hit_cut (hit.c:162-193).  The reference computes in `int` locals from uint32 operands and compares
+// against a 31-bit field (signed after promotion) or a uint32 field (unsigned); restated with explicit types.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_cut(DHit *a, size_t n, const DSub *__restrict__ reg, int min_span, uint8_t *flag)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		DHit p = ld_hit_rw(a + i);
+		const DSub rq = reg[p.qns >> 32], rt = reg[p.tn];
+		if ((rq.s_del | rt.s_del) & MAB_DEL_BIT) { flag[i] = 0; continue; }
+		const uint32_t rqs = rq.s_del, rts = rt.s_del, rqe = rq.e, rte = rt.e; // del bits are clear here
+		const uint32_t pqs = (uint32_t)p.qns;
+		uint32_t uqs, uqe, uts, ute;
+		if (p.ml_rev >> 31) {
+			uqs = p.te < rte ? pqs : pqs + (p.te - rte);
+			uqe = p.ts > rts ? p.qe : p.qe - (rts - p.ts);
+			uts = p.qe < rqe ? p.ts : p.ts + (p.qe - rqe);
+			ute = pqs > rqs ? p.te : p.te - (rqs - pqs);
+		} else {
+			uqs = p.ts > rts ? pqs : pqs + (rts - p.ts);
+			uqe = p.te < rte ? p.qe : p.qe - (p.te - rte);
+			uts = pqs > rqs ? p.ts : p.ts + (rqs - pqs);
+			ute = p.qe < rqe ? p.te : p.te - (p.qe - rqe);
+		}
+		int qs = (int)uqs, qe = (int)uqe, ts = (int)uts, te = (int)ute;
+		qs = (qs > (int)rqs ? qs : (int)rqs) - (int)rqs;                      // signed compare (31-bit field promotes to int)
+		qe = (int)(((uint32_t)qe < rqe ? (uint32_t)qe : rqe) - rqs);          // unsigned compare (uint32 field)
+		ts = (ts > (int)rts ? ts : (int)rts) - (int)rts;
+		te = (int)(((uint32_t)te < rte ? (uint32_t)te : rte) - rts);
+		bool keep = qe - qs >= min_span && te - ts >= min_span;
+		if (keep) {
+			p.qns = (p.qns >> 32 << 32) | (uint64_t)(int64_t)qs;
+			p.qe = (uint32_t)qe, p.ts = (uint32_t)ts, p.te = (uint32_t)te;
+			st_hit(a + i, p);
+		}
+		flag[i] = keep;
+	}
+}
+
+size_t dh_cut(MabDev &d, DHits &h, const DSub *reg, int min_span)
+{
+	if (h.n) {
+		uint8_t *flag = mab_alloc<uint8_t>(d, h.n);
+		MAB_LAUNCH(d, k_cut, mab_grid(h.n, 256), 256, 0, h.a, h.n, reg, min_span, flag);
+		select_hits(d, h, flag);
+		d.free(flag);
+	}
+	if (ma_verbose_dev >= 3) fprintf(stderr, "[M::%s::%s] %ld hits remain after cut\n", "ma_hit_cut", sys_timestamp(), (long)h.n);
+	return h.n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ma_hit_flt (hit.c:195-216)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_flt(const DHit *a, size_t n, const DSub *__restrict__ sub, int max_hang, int min_ovlp, uint8_t *flag, unsigned long long *tot_dp)
+{
+	unsigned long long dp = 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		DHit h = ld_hit(a + i);
+		const DSub sq = sub[h.qns >> 32], st = sub[h.tn];
+		bool keep = false;
+		if (!((sq.s_del | st.s_del) & MAB_DEL_BIT)) {
+			DArc t;
+			const uint32_t ql = sq.e - sq.s_del, tl = st.e - st.s_del;
+			int r = mab_hit2arc(h, (int)ql, (int)tl, max_hang, .5f, min_ovlp, &t);
+			if (r >= 0 || r == MAB_HT_QCONT || r == MAB_HT_TCONT) {
+				keep = true;
+				dp += r >= 0 ? (uint32_t)r : r == MAB_HT_QCONT ? ql : tl;
+			}
+		}
+		flag[i] = keep;
+	}
+	typedef cub::BlockReduce<unsigned long long, 256> BR;
+	__shared__ typename BR::TempStorage ts;
+	unsigned long long s = BR(ts).Sum(dp);
+	if (threadIdx.x == 0 && s) atomicAdd(tot_dp, s);
+}
+
+__global__ void k_flt_len(const DHit *a, size_t n, const DSub *__restrict__ sub, unsigned long long *tot_len)
+{
+	unsigned long long len = 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		uint32_t q = (uint32_t)(a[i].qns >> 32);
+		if (i == n - 1 || (uint32_t)(a[i + 1].qns >> 32) != q) len += sub[q].e - (sub[q].s_del & 0x7fffffffu);
+	}
+	typedef cub::BlockReduce<unsigned long long, 256> BR;
+	__shared__ typename BR::TempStorage ts;
+	unsigned long long s = BR(ts).Sum(len);
+	if (threadIdx.x == 0 && s) atomicAdd(tot_len, s);
+}
+
+size_t dh_flt(MabDev &d, DHits &h, const DSub *sub, int max_hang, int min_ovlp, float *cov)
+{
+	unsigned long long tot_dp = 0, tot_len = 0;
+	if (h.n) {
+		uint8_t *flag = mab_alloc<uint8_t>(d, h.n);
+		d.zero_scal(SC_AUX, 2);
+		MAB_LAUNCH(d, k_flt, mab_grid(h.n, 256), 256, 0, h.a, h.n, sub, max_hang, min_ovlp, flag, d.d_scal + SC_AUX);
+		select_hits(d, h, flag);
+		d.free(flag);
+		if (h.n) MAB_LAUNCH(d, k_flt_len, mab_grid(h.n, 256), 256, 0, h.a, h.n, sub, d.d_scal + SC_AUX2);
+		tot_dp = d.get_scal(SC_AUX), tot_len = d.h_scal[SC_AUX2];
+	}
+	*cov = (float)((double)tot_dp / tot_len);
+	if (ma_verbose_dev >= 3)
+		fprintf(stderr, "[M::%s::%s] %ld hits remain after filtering; crude coverage after filtering: %.2f\n", "ma_hit_flt", sys_timestamp(), (long)h.n, *cov);
+	return h.n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ma_sub_merge (hit.c:218-223): a.e = a.s + b.e; a.s += b.s  (31-bit s field; del of `a` is kept, del of `b` ignored)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_sub_merge(uint32_t n, DSub *a, const DSub *b)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		DSub x = a[i], y = b[i];
+		uint32_t s = x.s_del & 0x7fffffffu, del = x.s_del & MAB_DEL_BIT;
+		x.e = s + y.e;
+		x.s_del = ((s + (y.s_del & 0x7fffffffu)) & 0x7fffffffu) | del;
+		a[i] = x;
+	}
+}
+
+void dh_sub_merge(MabDev &d, uint32_t n_sub, DSub *a, const DSub *b)
+{
+	if (n_sub) MAB_LAUNCH(d, k_sub_merge, mab_grid(n_sub, 256), 256, 0, n_sub, a, b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ma_hit_contained (hit.c:225-256)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_cont_mark(const DHit *a, size_t n, DSub *sub, HitArcParams p, uint8_t *used)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		DHit h = ld_hit(a + i);
+		const uint32_t q = (uint32_t)(h.qns >> 32), t = h.tn;
+		const DSub sq = sub[q], st = sub[t];
+		DArc tmp;
+		// lengths use the 31-bit s field only, so concurrent del-bit updates by other threads cannot change them
+		int r = mab_hit2arc(h, (int)(sq.e - (sq.s_del & 0x7fffffffu)), (int)(st.e - (st.s_del & 0x7fffffffu)), p.max_hang, p.int_frac, p.min_ovlp, &tmp);
+		if (r == MAB_HT_QCONT) atomicOr(&sub[q].s_del, MAB_DEL_BIT);
+		else if (r == MAB_HT_TCONT) atomicOr(&sub[t].s_del, MAB_DEL_BIT);
+		used[q] = 1, used[t] = 1;                   // ma_hit_mark_unused: a read is "used" if any of the n hits names it
+	}
+}
+
+__global__ void k_cont_keep(uint32_t n_seq, const DSub *sub, const uint8_t *used, const uint8_t *seq_del, uint32_t *keep)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_seq; i += gridDim.x * blockDim.x)
+		keep[i] = used[i] && !(sub[i].s_del & MAB_DEL_BIT) && !(seq_del && seq_del[i]);
+}
+
+__global__ void k_cont_map(uint32_t n_seq, const uint32_t *keep, const uint32_t *excl, int32_t *map, const DSub *sub, DSub *sub_out)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_seq; i += gridDim.x * blockDim.x) {
+		if (keep[i]) { map[i] = (int32_t)excl[i]; sub_out[excl[i]] = sub[i]; }
+		else map[i] = -1;
+	}
+}
+
+__global__ void k_cont_apply(DHit *a, size_t n, const int32_t *__restrict__ map, uint8_t *flag)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		uint64_t qns = a[i].qns;
+		int32_t qn = map[qns >> 32], tn = map[a[i].tn];
+		bool keep = qn >= 0 && tn >= 0;
+		if (keep) { a[i].qns = (uint64_t)(uint32_t)qn << 32 | (uint32_t)qns; a[i].tn = (uint32_t)tn; }
+		flag[i] = keep;
+	}
+}
+
+size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, const HitArcParams &p, int32_t *map_out)
+{
+	const uint32_t n_seq = h.n_seq;
+	uint32_t n_new = 0;
+	if (n_seq) {
+		uint8_t *used = mab_alloc<uint8_t>(d, n_seq);
+		uint32_t *keep = mab_alloc<uint32_t>(d, n_seq), *excl = mab_alloc<uint32_t>(d, (size_t)n_seq + 1);
+		DSub *sub2 = mab_alloc<DSub>(d, n_seq);
+		MAB_CUDA(cudaMemsetAsync(used, 0, n_seq, d.stream));
+		if (h.n) MAB_LAUNCH(d, k_cont_mark, mab_grid(h.n, 256), 256, 0, h.a, h.n, sub, p, used);
+		MAB_LAUNCH(d, k_cont_keep, mab_grid(n_seq, 256), 256, 0, n_seq, sub, used, seq_del, keep);
+		size_t tb = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tb, keep, excl, (int)n_seq, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceScan::ExclusiveSum(tmp, tb, keep, excl, (int)n_seq, d.stream);
+		++d.n_lib;
+		MAB_LAUNCH(d, k_cont_map, mab_grid(n_seq, 256), 256, 0, n_seq, keep, excl, map_out, sub, sub2);
+		uint32_t last_keep, last_excl;
+		MAB_CUDA(cudaMemcpyAsync(&last_keep, keep + n_seq - 1, 4, cudaMemcpyDeviceToHost, d.stream));
+		MAB_CUDA(cudaMemcpyAsync(&last_excl, excl + n_seq - 1, 4, cudaMemcpyDeviceToHost, d.stream));
+		d.sync();
+		n_new = last_keep + last_excl;
+		if (n_new) MAB_CUDA(cudaMemcpyAsync(sub, sub2, (size_t)n_new * sizeof(DSub), cudaMemcpyDeviceToDevice, d.stream));
+		if (h.n) {
+			uint8_t *flag = mab_alloc<uint8_t>(d, h.n);
+			MAB_LAUNCH(d, k_cont_apply, mab_grid(h.n, 256), 256, 0, h.a, h.n, map_out, flag);
+			select_hits(d, h, flag);
+			d.free(flag);
+		}
+		d.free(used); d.free(keep); d.free(excl); d.free(sub2);
+	}
+	h.n_seq = n_new;
+	if (ma_verbose_dev >= 3)
+		fprintf(stderr, "[M::%s::%s] %d sequences and %ld hits remain after containment removal\n", "ma_hit_contained", sys_timestamp(), n_new, (long)h.n);
+	return h.n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ma_sg_gen (asm.c:9-39)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_seq_set(uint32_t n_seq, const uint32_t *len, const uint8_t *del, uint32_t *seq, unsigned *max_len)
+{
+	unsigned mx = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_seq; i += gridDim.x * blockDim.x) {
+		uint32_t l = len[i] & 0x7fffffffu;
+		seq[i] = l | (del && del[i] ? MAB_DEL_BIT : 0);
+		mx = l > mx ? l : mx;
+	}
+	mx = __reduce_max_sync(0xffffffffu, mx);
+	if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_len, mx);
+}
+
+__global__ void k_sg_arcs(const DHit *a, size_t n, uint32_t *seq, HitArcParams p, DArc *arc, uint8_t *flag, unsigned *max_len)
+{
+	unsigned mx = 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		DHit h = ld_hit(a + i);
+		const uint32_t qn = (uint32_t)(h.qns >> 32);
+		DArc t;
+		t.ul = 0, t.v = 0, t.ol_del = 0;
+		int r = mab_hit2arc(h, (int)(seq[qn] & 0x7fffffffu), (int)(seq[h.tn] & 0x7fffffffu), p.max_hang, p.int_frac, p.min_ovlp, &t);
+		bool emit = false;
+		if (r >= 0) {
+			if (qn == h.tn) { // self match: only the palindromic artefact has an effect (asm.c:27-31)
+				if ((uint32_t)h.qns == h.ts && h.qe == h.te && (h.ml_rev >> 31)) atomicOr(&seq[qn], MAB_DEL_BIT);
+			} else emit = true;
+		} else if (r == MAB_HT_QCONT) atomicOr(&seq[qn], MAB_DEL_BIT);
+		flag[i] = emit;
+		if (emit) {
+			*reinterpret_cast<uint4*>(arc + i) = make_uint4((uint32_t)t.ul, (uint32_t)(t.ul >> 32), t.v, t.ol_del);
+			mx = (uint32_t)t.ul > mx ? (uint32_t)t.ul : mx;
+		}
+	}
+	mx = __reduce_max_sync(0xffffffffu, mx);
+	if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_len, mx);
+}
+
+void dh_sg_gen(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *del, const HitArcParams &p, DGraph &g)
+{
+	const uint32_t n_seq = h.n_seq;
+	dg_set_nseq(d, g, n_seq);
+	g.n_arc = 0, g.is_srt = false, g.is_symm = false, g.has_idx = false;
+	d.zero_scal(SC_AUX);
+	unsigned *d_max = (unsigned*)(d.d_scal + SC_AUX);
+	if (n_seq) MAB_LAUNCH(d, k_seq_set, mab_grid(n_seq, 256), 256, 0, n_seq, len, del, g.seq, d_max);
+	if (h.n) {
+		if (h.n >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 arcs on one GPU\n"); exit(73); }
+		dg_reserve(d, g, h.n);
+		uint8_t *flag = mab_alloc<uint8_t>(d, h.n);
+		// seq lengths are read while other threads may set del bits: lengths are masked, so this is benign
+		MAB_LAUNCH(d, k_sg_arcs, mab_grid(h.n, 256), 256, 0, h.a, h.n, g.seq, p, g.arc2, flag, d_max);
+		size_t tb = 0;
+		unsigned long long *d_n = d.d_scal + SC_NSEL;
+		cub::DeviceSelect::Flagged(nullptr, tb, g.arc2, flag, g.arc, d_n, (int64_t)h.n, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceSelect::Flagged(tmp, tb, g.arc2, flag, g.arc, d_n, (int64_t)h.n, d.stream);
+		++d.n_lib;
+		g.n_arc = (uint32_t)d.get_scal(SC_NSEL);
+		d.free(flag);
+	} else {
+		dg_reserve(d, g, 1);
+		d.get_scal(SC_AUX);
+	}
+	unsigned mx = (unsigned)(d.h_scal[SC_AUX] & 0xffffffffu);
+	g.len_bits = bits_for(mx);
+	dg_cleanup(d, g);
+	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", g.n_arc);
+}

@@ -1,0 +1,232 @@
+/* gfa.c -- text writers and unitig sequence filling: the I/O-bound tail of the path, host C as in the
+ * reference (asm.c:41-55 ma_sg_print, asm.c:64-116 ma_ug_destroy/ma_ug_print, asm.c:216-290 ma_ug_seq).
+ * The output format is the parity contract: byte-identical S/L/a/x lines. */
+#include <zlib.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ctype.h>
+#include "miniasm_b200.h"
+
+void ma_ug_destroy(ma_ug_t *ug)
+{
+	size_t i;
+	if (ug == 0) return;
+	for (i = 0; i < ug->u.n; ++i) free(ug->u.a[i].a), free(ug->u.a[i].s);
+	free(ug->u.a);
+	asg_destroy(ug->g);
+	free(ug);
+}
+
+void ma_sg_print(const asg_t *g, const sdict_t *d, const ma_sub_t *sub, FILE *fp)
+{
+	uint32_t i;
+	for (i = 0; i < g->n_arc; ++i) {
+		const asg_arc_t *a = &g->arc[i];
+		uint32_t u = (uint32_t)(a->ul >> 32), v = a->v;
+		const char *un = d->seq[u >> 1].name, *vn = d->seq[v >> 1].name;
+		if (sub)
+			fprintf(fp, "L\t%s:%d-%d\t%c\t%s:%d-%d\t%c\t%d:\tL1:i:%d\n", un, sub[u >> 1].s + 1, sub[u >> 1].e, "+-"[u & 1],
+					vn, sub[v >> 1].s + 1, sub[v >> 1].e, "+-"[v & 1], a->ol, (uint32_t)a->ul);
+		else
+			fprintf(fp, "L\t%s\t%c\t%s\t%c\t%d:\tL1:i:%d\n", un, "+-"[u & 1], vn, "+-"[v & 1], a->ol, (uint32_t)a->ul);
+	}
+}
+
+static void utg_name(char *buf, uint32_t i, int circ) { sprintf(buf, "utg%.6d%c", i + 1, "lc"[!!circ]); }
+
+void ma_ug_print(const ma_ug_t *ug, const sdict_t *d, const ma_sub_t *sub, FILE *fp)
+{
+	uint32_t i, j;
+	char name[32], name2[32];
+	for (i = 0; i < ug->u.n; ++i) { /* segments, circularising links, read layout */
+		const ma_utg_t *p = &ug->u.a[i];
+		uint32_t off = 0;
+		utg_name(name, i, p->circ);
+		fprintf(fp, "S\t%s\t%s\tLN:i:%d\n", name, p->s ? p->s : "*", p->len);
+		if (p->circ) {
+			fprintf(fp, "L\t%s\t+\t%s\t+\t0M\n", name, name);
+			fprintf(fp, "L\t%s\t-\t%s\t-\t0M\n", name, name);
+		}
+		for (j = 0; j < p->n; ++j) {
+			uint32_t r = (uint32_t)(p->a[j] >> 33), l = (uint32_t)p->a[j];
+			char strand = "+-"[p->a[j] >> 32 & 1];
+			if (sub) fprintf(fp, "a\t%s\t%d\t%s:%d-%d\t%c\t%d\n", name, off, d->seq[r].name, sub[r].s + 1, sub[r].e, strand, l);
+			else fprintf(fp, "a\t%s\t%d\t%s\t%c\t%d\n", name, off, d->seq[r].name, strand, l);
+			off += l;
+		}
+	}
+	for (i = 0; i < ug->g->n_arc; ++i) { /* links between unitigs */
+		const asg_arc_t *a = &ug->g->arc[i];
+		uint32_t u = (uint32_t)(a->ul >> 32), v = a->v;
+		utg_name(name, u >> 1, ug->u.a[u >> 1].circ);
+		utg_name(name2, v >> 1, ug->u.a[v >> 1].circ);
+		fprintf(fp, "L\t%s\t%c\t%s\t%c\t%dM\tSD:i:%d\n", name, "+-"[u & 1], name2, "+-"[v & 1], a->ol, (uint32_t)a->ul);
+	}
+	for (i = 0; i < ug->u.n; ++i) { /* per-unitig summary */
+		const ma_utg_t *p = &ug->u.a[i];
+		if (p->start == UINT32_MAX) {
+			fprintf(fp, "x\tutg%.6dc\t%d\t%d\n", i + 1, p->len, p->n);
+		} else {
+			uint32_t n_out0 = (uint32_t)ug->g->idx[i << 1 | 0], n_out1 = (uint32_t)ug->g->idx[i << 1 | 1];
+			uint32_t s = p->start >> 1, e = p->end >> 1;
+			if (sub)
+				fprintf(fp, "x\tutg%.6dl\t%d\t%d\t%d\t%d\t%s:%d-%d\t%c\t%s:%d-%d\t%c\n", i + 1, p->len, p->n, n_out1, n_out0,
+						d->seq[s].name, sub[s].s + 1, sub[s].e, "+-"[p->start & 1], d->seq[e].name, sub[e].s + 1, sub[e].e, "+-"[p->end & 1]);
+			else
+				fprintf(fp, "x\tutg%.6dl\t%d\t%d\t%d\t%d\t%s\t%c\t%s\t%c\n", i + 1, p->len, p->n, n_out1, n_out0,
+						d->seq[s].name, "+-"[p->start & 1], d->seq[e].name, "+-"[p->end & 1]);
+		}
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * FASTA/FASTQ streaming (gzip or plain), semantics of kseq.h:160-234 as used by asm.c:236-290:
+ * a record starts at '>' or '@'; the name ends at the first white space; sequence lines run until a
+ * line starting with '>', '@' or '+'; after '+' quality bytes are consumed until they match the
+ * sequence length.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+	gzFile fp;
+	unsigned char *buf;
+	int beg, end, eof, last; /* last: pending header character of the next record */
+	kstring_t name, seq;
+} fx_t;
+
+#define FX_CHUNK 0x10000
+
+static int fx_getc(fx_t *f)
+{
+	if (f->beg >= f->end) {
+		if (f->eof) return -1;
+		f->beg = 0;
+		f->end = gzread(f->fp, f->buf, FX_CHUNK);
+		if (f->end < FX_CHUNK) f->eof = 1;
+		if (f->end <= 0) { f->end = 0; return -1; }
+	}
+	return f->buf[f->beg++];
+}
+
+static void ks_putc(kstring_t *s, int c)
+{
+	if (s->l + 2 > s->m) { s->m = s->m ? s->m << 1 : 256; s->s = (char*)realloc(s->s, s->m); }
+	s->s[s->l++] = (char)c, s->s[s->l] = 0;
+}
+
+/* returns sequence length, or -1 at end of input */
+static long fx_read(fx_t *f)
+{
+	int c;
+	if (f->last == 0) {
+		while ((c = fx_getc(f)) != -1 && c != '>' && c != '@');
+		if (c == -1) return -1;
+		f->last = c;
+	}
+	f->name.l = f->seq.l = 0;
+	if (f->name.s) f->name.s[0] = 0;
+	while ((c = fx_getc(f)) != -1 && !isspace(c)) ks_putc(&f->name, c);
+	if (c == -1 && f->name.l == 0) return -1;
+	if (c != -1 && c != '\n') while ((c = fx_getc(f)) != -1 && c != '\n'); /* comment */
+	if (f->seq.s == 0) ks_putc(&f->seq, 0), f->seq.l = 0, f->seq.s[0] = 0;
+	while ((c = fx_getc(f)) != -1 && c != '>' && c != '+' && c != '@') {
+		if (c == '\n') continue;
+		ks_putc(&f->seq, c);
+		while ((c = fx_getc(f)) != -1 && c != '\n') ks_putc(&f->seq, c); /* rest of the line */
+		if (f->seq.l && f->seq.s[f->seq.l - 1] == '\r') f->seq.s[--f->seq.l] = 0;
+	}
+	f->last = (c == '>' || c == '@') ? c : 0;
+	if (c == '+') {
+		size_t ql = 0;
+		while ((c = fx_getc(f)) != -1 && c != '\n');         /* rest of the '+' line */
+		while (ql < f->seq.l && (c = fx_getc(f)) != -1) {     /* quality lines */
+			if (c == '\n' || c == '\r') continue;
+			++ql;
+		}
+		f->last = 0;
+	}
+	return (long)f->seq.l;
+}
+
+typedef struct { uint32_t utg:31, ori:1, start, len; } utg_slot_t;
+
+int ma_ug_seq(ma_ug_t *g, const sdict_t *d, const ma_sub_t *sub, const char *fn)
+{
+	static unsigned char comp[256];
+	static const char pairs[] = "ATCGBVDHKMRY";
+	fx_t f;
+	utg_slot_t *slot;
+	uint32_t i, j;
+	gzFile fp = fn && strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(fileno(stdin), "r");
+	if (fp == 0) return -1;
+	for (i = 0; i < 256; ++i) comp[i] = i < 128 ? (unsigned char)i : 'N';
+	for (i = 0; pairs[i]; i += 2) {
+		comp[(int)pairs[i]] = pairs[i + 1], comp[(int)pairs[i + 1]] = pairs[i];
+		comp[tolower(pairs[i])] = tolower(pairs[i + 1]), comp[tolower(pairs[i + 1])] = tolower(pairs[i]);
+	}
+	comp['U'] = 'A', comp['u'] = 'a', comp[96] = 64; /* table quirks of asm.c:224-233 */
+	memset(&f, 0, sizeof(f));
+	f.fp = fp, f.buf = (unsigned char*)malloc(FX_CHUNK);
+
+	slot = (utg_slot_t*)calloc(d->n_seq ? d->n_seq : 1, sizeof(utg_slot_t));
+	for (i = 0; i < g->u.n; ++i) {
+		ma_utg_t *u = &g->u.a[i];
+		uint32_t off = 0;
+		u->s = (char*)calloc(1, (size_t)u->len + 1);
+		memset(u->s, 'N', u->len);
+		for (j = 0; j < u->n; ++j) {
+			utg_slot_t *t = &slot[u->a[j] >> 33];
+			t->utg = i, t->ori = u->a[j] >> 32 & 1, t->start = off, t->len = (uint32_t)u->a[j];
+			off += t->len;
+		}
+	}
+	while (fx_read(&f) >= 0) {
+		int32_t id = sd_get(d, f.name.s ? f.name.s : "");
+		const utg_slot_t *t;
+		char *dst;
+		const char *src = f.seq.s;
+		size_t sl = f.seq.l;
+		if (id < 0 || slot[id].len == 0) continue;
+		t = &slot[id];
+		dst = g->u.a[t->utg].s + t->start;
+		if (sub) src += sub[id].s, sl = sub[id].e - sub[id].s;
+		if (!t->ori) memcpy(dst, src, t->len);
+		else for (i = 0; i < t->len; ++i) dst[i] = (char)comp[(unsigned char)src[sl - 1 - i]];
+	}
+	free(slot);
+	free(f.buf); free(f.name.s); free(f.seq.s);
+	gzclose(fp);
+	return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * -R prefilter: one streaming pass that names the reads clearly contained in a much longer read
+ * (hit.c:38-68).  Dictionary work on a text stream: host C, like the reference.
+ * --------------------------------------------------------------------------------------------- */
+sdict_t *ma_hit_no_cont(const char *fn, int min_span, int min_match, int max_hang, float int_frac)
+{
+	paf_file_t *fp = paf_open(fn);
+	paf_rec_t r;
+	sdict_t *d;
+	if (fp == 0) {
+		fprintf(stderr, "[E::%s] could not open PAF file %s\n", __func__, fn);
+		exit(1);
+	}
+	memset(&r, 0, sizeof(r));
+	d = sd_init();
+	while (paf_read(fp, &r) >= 0) {
+		int l5, l3;
+		if (r.qe - r.qs < (uint32_t)min_span || r.te - r.ts < (uint32_t)min_span || (int)r.ml < min_match) continue;
+		l5 = r.rev ? r.tl - r.te : r.ts;
+		l3 = r.rev ? r.ts : r.tl - r.te;
+		if (r.ql >> 1 > r.tl) { /* query at least twice as long: is the target inside it? */
+			if (l5 > max_hang >> 2 || l3 > max_hang >> 2 || r.te - r.ts < r.tl * int_frac) continue;
+			if ((int)r.qs - l5 > max_hang << 1 && (int)(r.ql - r.qe) - l3 > max_hang << 1) sd_put(d, r.tn, r.tl);
+		} else if (r.ql < r.tl >> 1) {
+			if (r.qs > (uint32_t)(max_hang >> 2) || r.ql - r.qe > (uint32_t)(max_hang >> 2) || r.qe - r.qs < r.ql * int_frac) continue;
+			if (l5 - (int)r.qs > max_hang << 1 && l3 - (int)(r.ql - r.qe) > max_hang << 1) sd_put(d, r.qn, r.ql);
+		}
+	}
+	paf_close(fp);
+	if (ma_verbose >= 3) fprintf(stderr, "[M::%s::%s] dropped %d contained reads\n", __func__, sys_timestamp(), d->n_seq);
+	return d;
+}
