@@ -14,7 +14,15 @@ pytestmark = pytest.mark.gpu
 SETS = ["tiny_exact", "jitter30", "varlen300", "bubbles800", "chaos", "chaos_small", "shuffled", "skew_small", "lowcov", "c1_ecoli_like"]
 
 
+def canon_mask(h):
+    h = h.copy()
+    h["bl_del"] &= 0x7fffffff
+    return h
+
+
 def canon_hits(h):
+    h = h.copy()
+    h["bl_del"] &= 0x7fffffff      # ma_hit_t::del is never written by the reference (uninitialised heap bit, hit.c:87-98)
     return np.sort(h, order=["qns", "tn", "qe", "ts", "te", "ml_rev", "bl_del"])
 
 
@@ -36,6 +44,9 @@ def test_stage_i_stepwise(name, pafs, ref, prod):
     def fresh():
         return Pipeline(prod, pafs[name], opt=r.opt).adopt(r)
 
+    def same_hits(x, y):
+        return x.n_hits == y.n_hits and np.array_equal(canon_mask(x.hits_np()), canon_mask(y.hits_np()))
+
     # ma_hit_sub (round 1)
     q = fresh()
     r.sub1(), q.sub1()
@@ -44,26 +55,26 @@ def test_stage_i_stepwise(name, pafs, ref, prod):
     # ma_hit_cut
     q = fresh()
     r.cut(), q.cut()
-    assert r.n_hits == q.n_hits and np.array_equal(r.hits_np(), q.hits_np())
+    assert same_hits(r, q)
     q.free()
     # ma_hit_flt
     q = fresh()
     r.flt(), q.flt()
-    assert r.n_hits == q.n_hits and np.array_equal(r.hits_np(), q.hits_np())
+    assert same_hits(r, q)
     assert r.cov.value == q.cov.value or (np.isnan(r.cov.value) and np.isnan(q.cov.value))
     q.free()
     # ma_hit_sub (round 2, end clip) + ma_hit_cut + ma_sub_merge
     q = fresh()
     r.sub2_cut_merge(), q.sub2_cut_merge()
     assert np.array_equal(r.sub_np(), q.sub_np())
-    assert r.n_hits == q.n_hits and np.array_equal(r.hits_np(), q.hits_np())
+    assert same_hits(r, q)
     q.free()
     # ma_hit_contained (+ dictionary squeeze)
     q = fresh()
     r.contained(), q.contained()
     assert r.names() == q.names()
     assert np.array_equal(r.sub_np(), q.sub_np())
-    assert r.n_hits == q.n_hits and np.array_equal(r.hits_np(), q.hits_np())
+    assert same_hits(r, q)
     q.free()
     # ma_sg_gen
     q = fresh()
