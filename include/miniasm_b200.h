@@ -157,6 +157,38 @@ void mab_destroy(mab_ctx_t *ctx);
 void mab_set_verbose(int level);                        /* 0 silences the [M::...] lines of both levels */
 const mab_stats_t *mab_stats(const mab_ctx_t *ctx);
 
+/* Step 1, main.c:117-118 / hit.c:70-107.  The PAF bytes go to HBM once (from a host buffer, or from a plain/gzip
+ * file through pinned staging buffers); parsing, the name dictionary, mirrored hits and ma_hit_sort run there. */
+int mab_load_paf_text(mab_ctx_t *ctx, const char *text, size_t len);
+int mab_load_paf_file(mab_ctx_t *ctx, const char *fn);  /* -1 if the file cannot be opened */
+int mab_ingest(mab_ctx_t *ctx, int min_span, int min_match, int bi_dir);
+/* alternative to load+ingest: hits and dictionary produced by ma_hit_read (needed for the -R exclusion list) */
+int mab_load_hits(mab_ctx_t *ctx, const ma_hit_t *a, size_t n, const sdict_t *dict);
+
+/* Steps 2-3, main.c:119-142 (ma_hit_sub/cut/flt/sub_merge/contained).  stage = the reference's -S. */
+int mab_select(mab_ctx_t *ctx, const ma_opt_t *opt, int no_first, int no_second, int stage);
+/* Step 4, main.c:155-188 (ma_sg_gen, asg_arc_del_trans, tip/bubble/short/internal/biloop passes) */
+int mab_layout(mab_ctx_t *ctx, const ma_opt_t *opt, int stage);
+/* Step 5, main.c:190-192 (ma_ug_gen) */
+int mab_unitigs(mab_ctx_t *ctx);
+
+/* Host copies in the reference's own structures (caller owns them: sd_destroy / free / asg_destroy / ma_ug_destroy) */
+sdict_t *mab_export_dict(mab_ctx_t *ctx);               /* names and lengths of the current reads, ids = graph ids */
+ma_sub_t *mab_export_sub(mab_ctx_t *ctx);               /* NULL when no read selection ran */
+ma_hit_t *mab_export_hits(mab_ctx_t *ctx, size_t *n);
+asg_t *mab_export_sg(mab_ctx_t *ctx);
+ma_ug_t *mab_export_ug(mab_ctx_t *ctx);
+float mab_coverage(const mab_ctx_t *ctx);
+
+/* timing helpers for bench.py: CUDA events on the context's stream */
+void *mab_event_create(void);
+void mab_event_record(mab_ctx_t *ctx, void *ev);
+float mab_event_elapsed_ms(void *ev_begin, void *ev_end);
+void mab_event_destroy(void *ev);
+void mab_sync(mab_ctx_t *ctx);
+void mab_last_del_trans(uint64_t *n_arc_in, uint64_t *inner, uint64_t *n_reduced, uint64_t *n_big, double *kernel_ms);
+void mab_last_clean(uint32_t *rounds, uint32_t *committed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,438 @@
+// capi_fused.cu -- fused level of the C ABI (include/miniasm_b200.h, "mab_*"): one device-resident context
+// carries the PAF text, the hits, the interval tables and the graphs through all steps of main.c:108-199;
+// only counts, the surviving read names and the final structures cross PCIe.
+#include "../../include/miniasm_b200.h"
+#include "capi_util.cuh"
+#include "hit_dev.cuh"
+#include "clean_dev.cuh"
+#include "ingest_dev.cuh"
+#include <cub/cub.cuh>
+#include <zlib.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
+
+ma_ug_t *mab_ug_download(MabDev &d, DUnitigs &du); // capi_clean.cu
+
+struct mab_ctx {
+	MabDev dev;
+	char *d_text = nullptr;
+	size_t text_len = 0, text_cap = 0;
+	DHits hits;
+	DNames names;             // original ids (as assigned by the ingest)
+	IngestStats ist;
+	uint32_t n_seq = 0;       // current number of reads (after containment removal: the squeezed count)
+	uint32_t *orig_id = nullptr; // current id -> original id; null = identity
+	DSub *sub = nullptr;      // per current read; null = no read selection ran (-1 -2)
+	DGraph sg;
+	DUnitigs ug;
+	bool have_sg = false, have_ug = false;
+	float cov = 40.0f;
+	mab_stats_t stats;
+	// pinned staging for file loads
+	char *pin[2] = {nullptr, nullptr};
+	size_t pin_bytes = 0;
+};
+
+__global__ void k_sg_len(uint32_t n, const DSub *sub, const uint32_t *slen, const uint32_t *orig, uint32_t *len, uint8_t *del)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (sub) len[i] = sub[i].e - (sub[i].s_del & 0x7fffffffu), del[i] = sub[i].s_del >> 31;
+		else len[i] = slen[orig ? orig[i] : i], del[i] = 0;
+	}
+}
+
+__global__ void k_orig_from_map(uint32_t n_old, const int32_t *map, const uint32_t *orig_old, uint32_t *orig_new)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_old; i += gridDim.x * blockDim.x)
+		if (map[i] >= 0) orig_new[map[i]] = orig_old ? orig_old[i] : i;
+}
+
+__global__ void k_name_sizes(uint32_t n, const uint32_t *orig, const uint32_t *nlen, uint32_t *out)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = nlen[orig ? orig[i] : i] + 1;
+}
+
+__global__ void k_name_pack(uint32_t n, const uint32_t *orig, const uint64_t *noff, const uint32_t *nlen, const uint32_t *slen,
+                            const char *text, const uint64_t *pos, char *out, uint32_t *out_slen)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t o = orig ? orig[i] : i, l = nlen[o];
+		const char *src = text + noff[o];
+		char *dst = out + pos[i];
+		for (uint32_t k = 0; k < l; ++k) dst[k] = src[k];
+		dst[l] = 0;
+		out_slen[i] = slen[o];
+	}
+}
+
+static void ctx_drop_graphs(mab_ctx *c)
+{
+	if (c->have_ug) dg_ug_free(c->dev, c->ug), c->have_ug = false;
+	if (c->have_sg) dg_free(c->dev, c->sg), c->have_sg = false;
+}
+
+static void ctx_reset_reads(mab_ctx *c)
+{
+	MabDev &d = c->dev;
+	ctx_drop_graphs(c);
+	d.free(c->sub), c->sub = nullptr;
+	d.free(c->orig_id), c->orig_id = nullptr;
+	names_free(d, c->names);
+	c->hits.n = 0, c->hits.n_seq = 0;
+	c->n_seq = 0;
+}
+
+extern "C" {
+
+mab_ctx_t *mab_create(int device)
+{
+	mab_ctx *c = new mab_ctx();
+	c->dev.init(device);
+	memset(&c->stats, 0, sizeof(c->stats));
+	memset(&c->ist, 0, sizeof(c->ist));
+	return c;
+}
+
+void mab_destroy(mab_ctx_t *c)
+{
+	if (!c) return;
+	MabDev &d = c->dev;
+	MAB_CUDA(cudaSetDevice(d.device));
+	ctx_reset_reads(c);
+	dh_free(d, c->hits);
+	d.free(c->d_text);
+	d.sync();
+	for (int i = 0; i < 2; ++i) if (c->pin[i]) MAB_CUDA(cudaFreeHost(c->pin[i]));
+	d.destroy();
+	delete c;
+}
+
+const mab_stats_t *mab_stats(const mab_ctx_t *c)
+{
+	mab_ctx *m = const_cast<mab_ctx*>(c);
+	m->stats.n_kernel_launches = c->dev.n_launch, m->stats.n_lib_calls = c->dev.n_lib;
+	return &c->stats;
+}
+
+static void text_reserve(mab_ctx *c, size_t len)
+{
+	if (len <= c->text_cap) return;
+	c->dev.free(c->d_text);
+	c->text_cap = len + (len >> 3) + 4096;
+	c->d_text = (char*)c->dev.alloc(c->text_cap);
+}
+
+/* PAF bytes from host memory to the GPU (one H2D copy; `text` may be pageable or pinned) */
+int mab_load_paf_text(mab_ctx_t *c, const char *text, size_t len)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	ctx_reset_reads(c);
+	text_reserve(c, len);
+	if (len) MAB_CUDA(cudaMemcpyAsync(c->d_text, text, len, cudaMemcpyHostToDevice, c->dev.stream));
+	c->text_len = len;
+	c->dev.sync();
+	return 0;
+}
+
+/* PAF file (plain or gzip, "-" = stdin) to the GPU through two pinned staging buffers: the read of chunk
+ * k+1 overlaps the H2D copy of chunk k.  Returns 0, or -1 if the file cannot be opened. */
+int mab_load_paf_file(mab_ctx_t *c, const char *fn)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	const size_t CH = 64u << 20;
+	gzFile fp = fn && strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(fileno(stdin), "r");
+	if (fp == 0) return -1;
+	gzbuffer(fp, 1 << 20);
+	ctx_reset_reads(c);
+	if (c->pin_bytes < CH) {
+		for (int i = 0; i < 2; ++i) { if (c->pin[i]) MAB_CUDA(cudaFreeHost(c->pin[i])); MAB_CUDA(cudaMallocHost(&c->pin[i], CH)); }
+		c->pin_bytes = CH;
+	}
+	struct stat sb;
+	size_t guess = 0;
+	if (fn && strcmp(fn, "-") && stat(fn, &sb) == 0) guess = (size_t)sb.st_size;
+	text_reserve(c, guess ? guess : CH);
+	cudaEvent_t ev[2];
+	for (int i = 0; i < 2; ++i) MAB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+	size_t total = 0;
+	for (int k = 0;; k ^= 1) {
+		MAB_CUDA(cudaEventSynchronize(ev[k])); // the previous copy out of this staging buffer is done
+		size_t got = 0;
+		while (got < CH) {
+			int r = gzread(fp, c->pin[k] + got, (unsigned)((CH - got) < (1u << 30) ? (CH - got) : (1u << 30)));
+			if (r <= 0) break;
+			got += (size_t)r;
+		}
+		if (got == 0) break;
+		if (total + got > c->text_cap) { // compressed input or stdin: grow the device buffer, keeping what is there
+			size_t ncap = (total + got) * 2;
+			char *nt = (char*)c->dev.alloc(ncap);
+			if (total) MAB_CUDA(cudaMemcpyAsync(nt, c->d_text, total, cudaMemcpyDeviceToDevice, c->dev.stream));
+			c->dev.free(c->d_text);
+			c->d_text = nt, c->text_cap = ncap;
+		}
+		MAB_CUDA(cudaMemcpyAsync(c->d_text + total, c->pin[k], got, cudaMemcpyHostToDevice, c->dev.stream));
+		MAB_CUDA(cudaEventRecord(ev[k], c->dev.stream));
+		total += got;
+		if (got < CH) break;
+	}
+	c->dev.sync();
+	for (int i = 0; i < 2; ++i) MAB_CUDA(cudaEventDestroy(ev[i]));
+	gzclose(fp);
+	c->text_len = total;
+	return 0;
+}
+
+/* Step 1 on the device (hit.c:70-107): parse, name dictionary, mirrored hits, sort */
+int mab_ingest(mab_ctx_t *c, int min_span, int min_match, int bi_dir)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	ctx_reset_reads(c);
+	ingest_paf(d, c->d_text, c->text_len, min_span, min_match, bi_dir, c->hits, c->names, c->ist);
+	c->n_seq = c->names.n_seq;
+	c->stats.n_lines = c->ist.n_parsed, c->stats.n_hits_stored = c->ist.n_hits, c->stats.n_seq_in = c->ist.n_seq;
+	if (ma_verbose >= 3)
+		fprintf(stderr, "[M::%s::%s] read %ld hits; stored %ld hits and %d sequences (%ld bp)\n", "ma_hit_read", sys_timestamp(),
+				(long)c->ist.n_parsed, (long)c->ist.n_hits, (int)c->ist.n_seq, (long)c->ist.tot_len);
+	return 0;
+}
+
+/* Alternative to mab_ingest: hits parsed elsewhere (e.g. ma_hit_read with an exclusion dictionary, -R) */
+int mab_load_hits(mab_ctx_t *c, const ma_hit_t *a, size_t n, const sdict_t *dict)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	ctx_reset_reads(c);
+	dh_reserve(d, c->hits, n ? n : 1);
+	c->hits.n = n, c->hits.n_seq = dict->n_seq;
+	if (n) MAB_CUDA(cudaMemcpyAsync(c->hits.a, a, n * sizeof(DHit), cudaMemcpyHostToDevice, d.stream));
+	// names live on the host in this mode: pack them into the text buffer so that the export path is the same
+	size_t bytes = 0;
+	for (uint32_t i = 0; i < dict->n_seq; ++i) bytes += strlen(dict->seq[i].name) + 1;
+	char *pack = (char*)malloc(bytes ? bytes : 1);
+	uint64_t *off = (uint64_t*)malloc((dict->n_seq ? dict->n_seq : 1) * 8);
+	uint32_t *nl = (uint32_t*)malloc((dict->n_seq ? dict->n_seq : 1) * 4), *sl = (uint32_t*)malloc((dict->n_seq ? dict->n_seq : 1) * 4);
+	bytes = 0;
+	for (uint32_t i = 0; i < dict->n_seq; ++i) {
+		size_t l = strlen(dict->seq[i].name);
+		memcpy(pack + bytes, dict->seq[i].name, l + 1);
+		off[i] = bytes, nl[i] = (uint32_t)l, sl[i] = dict->seq[i].len;
+		bytes += l + 1;
+	}
+	text_reserve(c, bytes);
+	c->text_len = bytes;
+	DNames &nm = c->names;
+	nm.n_seq = dict->n_seq;
+	nm.off = mab_alloc<uint64_t>(d, nm.n_seq); nm.nlen = mab_alloc<uint32_t>(d, nm.n_seq); nm.slen = mab_alloc<uint32_t>(d, nm.n_seq);
+	if (bytes) MAB_CUDA(cudaMemcpyAsync(c->d_text, pack, bytes, cudaMemcpyHostToDevice, d.stream));
+	if (nm.n_seq) {
+		MAB_CUDA(cudaMemcpyAsync(nm.off, off, (size_t)nm.n_seq * 8, cudaMemcpyHostToDevice, d.stream));
+		MAB_CUDA(cudaMemcpyAsync(nm.nlen, nl, (size_t)nm.n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+		MAB_CUDA(cudaMemcpyAsync(nm.slen, sl, (size_t)nm.n_seq * 4, cudaMemcpyHostToDevice, d.stream));
+	}
+	d.sync();
+	free(pack); free(off); free(nl); free(sl);
+	c->n_seq = dict->n_seq;
+	c->stats.n_hits_stored = n, c->stats.n_seq_in = dict->n_seq;
+	return 0;
+}
+
+/* Steps 2-3 (main.c:119-142): read selection.  `stage` has the meaning of the reference's -S. */
+int mab_select(mab_ctx_t *c, const ma_opt_t *opt, int no_first, int no_second, int stage)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	DHits &h = c->hits;
+	ctx_drop_graphs(c);
+	if (!no_first) {
+		if (stage >= 2) {
+			d.free(c->sub);
+			c->sub = mab_alloc<DSub>(d, c->n_seq);
+			dh_sub(d, h, opt->min_dp, opt->min_iden, 0, c->sub);
+			dh_cut(d, h, c->sub, opt->min_span);
+		}
+		if (stage >= 3 && c->sub) dh_flt(d, h, c->sub, (int)(opt->max_hang * 1.5), (int)(opt->min_ovlp * .5), &c->cov);
+	}
+	if (!no_second) {
+		if (stage >= 4) {
+			DSub *sub2 = mab_alloc<DSub>(d, c->n_seq);
+			dh_sub(d, h, opt->min_dp, opt->min_iden, opt->min_span / 2, sub2);
+			dh_cut(d, h, sub2, opt->min_span);
+			if (!no_first && c->sub) { dh_sub_merge(d, c->n_seq, c->sub, sub2); d.free(sub2); }
+			else { d.free(c->sub); c->sub = sub2; }
+		}
+		if (stage >= 5 && c->sub) {
+			const uint32_t n_old = c->n_seq;
+			int32_t *map = mab_alloc<int32_t>(d, n_old);
+			HitArcParams p = { opt->max_hang, opt->int_frac, opt->min_ovlp };
+			dh_contained(d, h, c->sub, nullptr, p, map);
+			uint32_t *orig_new = mab_alloc<uint32_t>(d, h.n_seq);
+			if (n_old) MAB_LAUNCH(d, k_orig_from_map, mab_grid(n_old, 256), 256, 0, n_old, map, c->orig_id, orig_new);
+			d.free(c->orig_id);
+			c->orig_id = orig_new;
+			c->n_seq = h.n_seq;
+			d.free(map);
+		}
+	}
+	c->stats.n_hits_final = h.n, c->stats.n_seq_final = c->n_seq;
+	d.sync();
+	return 0;
+}
+
+/* Step 4 (main.c:155-188): graph construction and cleaning.  stage as in -S (5 = raw graph ... 11 = all). */
+int mab_layout(mab_ctx_t *c, const ma_opt_t *opt, int stage)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	ctx_drop_graphs(c);
+	uint32_t *len = mab_alloc<uint32_t>(d, c->n_seq);
+	uint8_t *del = mab_alloc<uint8_t>(d, c->n_seq);
+	if (c->n_seq) MAB_LAUNCH(d, k_sg_len, mab_grid(c->n_seq, 256), 256, 0, c->n_seq, c->sub, c->names.slen, c->orig_id, len, del);
+	HitArcParams p = { opt->max_hang, opt->int_frac, opt->min_ovlp };
+	c->hits.n_seq = c->n_seq;
+	dh_sg_gen(d, c->hits, len, del, p, c->sg);
+	c->have_sg = true;
+	d.free(len); d.free(del);
+	DGraph &g = c->sg;
+	c->stats.n_arc_sg = g.n_arc;
+	if (stage >= 6) {
+		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.1: transitive reduction <===\n");
+		dg_del_trans(d, g, (uint32_t)opt->gap_fuzz);
+		c->stats.n_arc_trans_in = g_del_trans_stats.n_arc_in, c->stats.n_reduced = g_del_trans_stats.n_reduced;
+		c->stats.trans_inner = g_del_trans_stats.inner_iters, c->stats.ms_del_trans_kernel = g_del_trans_stats.kernel_ms;
+	}
+	if (stage >= 7) {
+		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.2: initial tip cutting and bubble popping <===\n");
+		dg_cut_tip(d, g, opt->max_ext);
+		dg_pop_bubble(d, g, opt->bub_dist);
+	}
+	if (stage >= 9) {
+		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.3: cutting short overlaps (%d rounds in total) <===\n", opt->n_rounds + 1);
+		for (int i = 0; i <= opt->n_rounds; ++i) {
+			float r = opt->min_ovlp_drop_ratio + (opt->max_ovlp_drop_ratio - opt->min_ovlp_drop_ratio) / opt->n_rounds * i;
+			if (dg_del_short(d, g, r) != 0) {
+				dg_cut_tip(d, g, opt->max_ext);
+				dg_pop_bubble(d, g, opt->bub_dist);
+			}
+		}
+	}
+	if (stage >= 10) {
+		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.4: removing short internal sequences and bi-loops <===\n");
+		dg_cut_internal(d, g, 1);
+		dg_cut_biloop(d, g, opt->max_ext);
+		dg_cut_tip(d, g, opt->max_ext);
+		dg_pop_bubble(d, g, opt->bub_dist);
+	}
+	if (stage >= 11) {
+		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.5: aggressively cutting short overlaps <===\n");
+		if (dg_del_short(d, g, opt->final_ovlp_drop_ratio) != 0) {
+			dg_cut_tip(d, g, opt->max_ext);
+			dg_pop_bubble(d, g, opt->bub_dist);
+		}
+	}
+	c->stats.n_arc_final = g.n_arc;
+	d.sync();
+	return 0;
+}
+
+/* Step 5 (asm.c:121-210) */
+int mab_unitigs(mab_ctx_t *c)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	if (!c->have_sg) return -1;
+	if (c->have_ug) dg_ug_free(c->dev, c->ug), c->have_ug = false;
+	dg_ug_gen(c->dev, c->sg, c->ug);
+	c->have_ug = true;
+	c->stats.n_utg = c->ug.n_utg;
+	c->dev.sync();
+	return 0;
+}
+
+/* ---- exports: reference-compatible host structures, owned by the caller -------------------------------- */
+
+sdict_t *mab_export_dict(mab_ctx_t *c)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	sdict_t *dict = sd_init();
+	const uint32_t n = c->n_seq;
+	if (n == 0) return dict;
+	uint32_t *sz = mab_alloc<uint32_t>(d, n), *d_slen = mab_alloc<uint32_t>(d, n);
+	uint64_t *pos = mab_alloc<uint64_t>(d, (size_t)n + 1);
+	MAB_LAUNCH(d, k_name_sizes, mab_grid(n, 256), 256, 0, n, c->orig_id, c->names.nlen, sz);
+	size_t tb = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tb, sz, pos, (int)n, d.stream);
+	void *tmp = d.tmp(tb);
+	cub::DeviceScan::ExclusiveSum(tmp, tb, sz, pos, (int)n, d.stream);
+	++d.n_lib;
+	uint64_t last_pos; uint32_t last_sz;
+	MAB_CUDA(cudaMemcpyAsync(&last_pos, pos + n - 1, 8, cudaMemcpyDeviceToHost, d.stream));
+	MAB_CUDA(cudaMemcpyAsync(&last_sz, sz + n - 1, 4, cudaMemcpyDeviceToHost, d.stream));
+	d.sync();
+	const size_t bytes = last_pos + last_sz;
+	char *d_pack = (char*)d.alloc(bytes), *pack = (char*)malloc(bytes);
+	uint32_t *slen = (uint32_t*)malloc((size_t)n * 4);
+	MAB_LAUNCH(d, k_name_pack, mab_grid(n, 256), 256, 0, n, c->orig_id, c->names.off, c->names.nlen, c->names.slen, c->d_text, pos, d_pack, d_slen);
+	MAB_CUDA(cudaMemcpyAsync(pack, d_pack, bytes, cudaMemcpyDeviceToHost, d.stream));
+	MAB_CUDA(cudaMemcpyAsync(slen, d_slen, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream));
+	d.sync();
+	const char *p = pack;
+	for (uint32_t i = 0; i < n; ++i) { sd_put(dict, p, slen[i]); p += strlen(p) + 1; }
+	free(pack); free(slen);
+	d.free(sz); d.free(d_slen); d.free(pos); d.free(d_pack);
+	d.sync();
+	return dict;
+}
+
+ma_sub_t *mab_export_sub(mab_ctx_t *c)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	if (!c->sub) return 0;
+	ma_sub_t *s = (ma_sub_t*)calloc(c->n_seq ? c->n_seq : 1, sizeof(ma_sub_t));
+	if (c->n_seq) MAB_CUDA(cudaMemcpyAsync(s, c->sub, (size_t)c->n_seq * sizeof(DSub), cudaMemcpyDeviceToHost, c->dev.stream));
+	c->dev.sync();
+	return s;
+}
+
+ma_hit_t *mab_export_hits(mab_ctx_t *c, size_t *n)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	ma_hit_t *a = (ma_hit_t*)malloc((c->hits.n ? c->hits.n : 1) * sizeof(ma_hit_t));
+	if (c->hits.n) MAB_CUDA(cudaMemcpyAsync(a, c->hits.a, c->hits.n * sizeof(DHit), cudaMemcpyDeviceToHost, c->dev.stream));
+	c->dev.sync();
+	*n = c->hits.n;
+	return a;
+}
+
+asg_t *mab_export_sg(mab_ctx_t *c)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	if (!c->have_sg) return 0;
+	asg_t *g = asg_init();
+	g->n_seq = c->sg.n_seq, g->m_seq = c->sg.n_seq ? c->sg.n_seq : 1;
+	g->seq = (asg_seq_t*)malloc((size_t)g->m_seq * sizeof(asg_seq_t));
+	g->m_arc = c->sg.n_arc ? c->sg.n_arc : 1;
+	g->arc = (asg_arc_t*)malloc((size_t)g->m_arc * sizeof(asg_arc_t));
+	mab_graph_download(c->dev, c->sg, g);
+	return g;
+}
+
+ma_ug_t *mab_export_ug(mab_ctx_t *c)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	if (!c->have_ug) return 0;
+	return mab_ug_download(c->dev, c->ug);
+}
+
+float mab_coverage(const mab_ctx_t *c) { return c->cov; }
+
+/* device-time probe used by bench.py: milliseconds between two points on the context's stream */
+void *mab_event_create(void) { cudaEvent_t e; MAB_CUDA(cudaEventCreate(&e)); return e; }
+void mab_event_record(mab_ctx_t *c, void *e) { MAB_CUDA(cudaEventRecord((cudaEvent_t)e, c->dev.stream)); }
+float mab_event_elapsed_ms(void *a, void *b) { float ms = 0; MAB_CUDA(cudaEventSynchronize((cudaEvent_t)b)); MAB_CUDA(cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b)); return ms; }
+void mab_event_destroy(void *e) { MAB_CUDA(cudaEventDestroy((cudaEvent_t)e)); }
+void mab_sync(mab_ctx_t *c) { c->dev.sync(); }
+
+}

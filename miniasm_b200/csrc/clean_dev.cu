@@ -874,7 +874,8 @@ void dg_ug_gen(MabDev &d, const DGraph &g, DUnitigs &ug)
 		if (consistent) {
 			uint32_t *buf[12];
 			for (int i = 0; i < 12; ++i) buf[i] = mab_alloc<uint32_t>(d, n_vtx);
-			uint64_t *ps = mab_alloc<uint64_t>(d, n_vtx), *ps2 = mab_alloc<uint64_t>(d, n_vtx);
+			uint64_t *ps_buf0 = mab_alloc<uint64_t>(d, n_vtx), *ps_buf1 = mab_alloc<uint64_t>(d, n_vtx);
+			uint64_t *ps = ps_buf0, *ps2 = ps_buf1;
 			a.jf = buf[0], a.jb = buf[1], a.mf = buf[2], a.mb = buf[3];
 			uint32_t *jf2 = buf[4], *jb2 = buf[5], *mf2 = buf[6], *mb2 = buf[7];
 			a.rk = buf[8], a.cnt = buf[9], a.seedmin = buf[10];
@@ -923,7 +924,7 @@ void dg_ug_gen(MabDev &d, const DGraph &g, DUnitigs &ug)
 			ug.items = mab_alloc<uint64_t>(d, ug.n_items);
 			if (ug.n_utg) MAB_LAUNCH(d, k_ug_emit, grid, 256, 0, gv, a, is_cyc, utg_of, first_of, ug.items, ug.meta);
 			for (int i = 0; i < 12; ++i) d.free(buf[i]);
-			d.free(ps); d.free(ps2);
+			d.free(ps_buf0); d.free(ps_buf1);
 		} else {
 			int32_t *mark = mab_alloc<int32_t>(d, n_vtx);
 			MAB_CUDA(cudaMemsetAsync(mark, 0, (size_t)n_vtx * 4, d.stream));

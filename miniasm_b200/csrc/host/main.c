@@ -1,0 +1,170 @@
+/* main.c -- the miniasm-b200 command line: same options, step order, stderr chatter and output formats as
+ * the reference driver (main.c:32-211), with every step of the hot path running on the GPU through the fused
+ * C ABI (include/miniasm_b200.h).  Usage: miniasm-b200 [options] <in.paf>
+ * Extra environment: MINIASM_B200_DEVICE=<cuda ordinal>. */
+#include <unistd.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+#include "miniasm_b200.h"
+
+#define MAB_VERSION "0.3-r179"   /* tracks the reference release whose output it reproduces */
+
+static void write_bed(const sdict_t *d, const ma_sub_t *sub) /* -p bed, main.c:13-19 */
+{
+	uint32_t i;
+	for (i = 0; i < d->n_seq; ++i)
+		if (!d->seq[i].del && sub[i].s != sub[i].e)
+			printf("%s\t%d\t%d\n", d->seq[i].name, sub[i].s, sub[i].e);
+}
+
+static void write_paf(size_t n, const ma_hit_t *h, const sdict_t *d, const ma_sub_t *sub) /* -p paf, main.c:21-30 */
+{
+	size_t i;
+	for (i = 0; i < n; ++i) {
+		uint32_t q = (uint32_t)(h[i].qns >> 32), t = h[i].tn;
+		printf("%s:%d-%d\t%d\t%d\t%d\t%c\t%s:%d-%d\t%d\t%d\t%d\t%d\t%d\t255\n", d->seq[q].name, sub[q].s + 1, sub[q].e, sub[q].e - sub[q].s,
+			   (uint32_t)h[i].qns, h[i].qe, "+-"[h[i].rev], d->seq[t].name, sub[t].s + 1, sub[t].e, sub[t].e - sub[t].s, h[i].ts, h[i].te, h[i].ml, h[i].bl);
+	}
+}
+
+static void usage(const ma_opt_t *o, const char *outfmt)
+{
+	fprintf(stderr, "Usage: miniasm-b200 [options] <in.paf>\n");
+	fprintf(stderr, "Options:\n");
+	fprintf(stderr, "  Pre-selection:\n");
+	fprintf(stderr, "    -R          prefilter clearly contained reads (2-pass required)\n");
+	fprintf(stderr, "    -m INT      min match length [%d]\n", o->min_match);
+	fprintf(stderr, "    -i FLOAT    min identity [%.2g]\n", o->min_iden);
+	fprintf(stderr, "    -s INT      min span [%d]\n", o->min_span);
+	fprintf(stderr, "    -c INT      min coverage [%d]\n", o->min_dp);
+	fprintf(stderr, "  Overlap:\n");
+	fprintf(stderr, "    -o INT      min overlap [same as -s]\n");
+	fprintf(stderr, "    -h INT      max over hang length [%d]\n", o->max_hang);
+	fprintf(stderr, "    -I FLOAT    min end-to-end match ratio [%.2g]\n", o->int_frac);
+	fprintf(stderr, "  Layout:\n");
+	fprintf(stderr, "    -g INT      max gap differences between reads for trans-reduction [%d]\n", o->gap_fuzz);
+	fprintf(stderr, "    -d INT      max distance for bubble popping [%d]\n", o->bub_dist);
+	fprintf(stderr, "    -e INT      small unitig threshold [%d]\n", o->max_ext);
+	fprintf(stderr, "    -f FILE     read sequences []\n");
+	fprintf(stderr, "    -n INT      rounds of short overlap removal [%d]\n", o->n_rounds + 1);
+	fprintf(stderr, "    -r FLOAT[,FLOAT]\n");
+	fprintf(stderr, "                max and min overlap drop ratio [%.2g,%.2g]\n", o->max_ovlp_drop_ratio, o->min_ovlp_drop_ratio);
+	fprintf(stderr, "    -F FLOAT    aggressive overlap drop ratio in the end [%.2g]\n", o->final_ovlp_drop_ratio);
+	fprintf(stderr, "  Miscellaneous:\n");
+	fprintf(stderr, "    -p STR      output information: bed, paf, sg or ug [%s]\n", outfmt);
+	fprintf(stderr, "    -b          both directions of an arc are present in input\n");
+	fprintf(stderr, "    -1          skip 1-pass read selection\n");
+	fprintf(stderr, "    -2          skip 2-pass read selection\n");
+	fprintf(stderr, "    -V          print version number\n");
+	fprintf(stderr, "\nSee miniasm.1 of the reference for a detailed description of the command-line options.\n");
+}
+
+int main(int argc, char *argv[])
+{
+	ma_opt_t opt;
+	int i, c, stage = 100, no_first = 0, no_second = 0, bi_dir = 1, o_set = 0, no_cont = 0, device = 0;
+	const char *fn_reads = 0, *outfmt = "ug", *env;
+	mab_ctx_t *ctx;
+	sdict_t *d = 0;
+	ma_sub_t *sub = 0;
+
+	ma_opt_init(&opt);
+	while ((c = getopt(argc, argv, "n:m:s:c:S:i:d:g:o:h:I:r:f:e:p:12VBRbF:")) >= 0) {
+		switch (c) {
+			case 'm': opt.min_match = atoi(optarg); break;
+			case 'i': opt.min_iden = atof(optarg); break;
+			case 's': opt.min_span = atoi(optarg); break;
+			case 'c': opt.min_dp = atoi(optarg); break;
+			case 'o': opt.min_ovlp = atoi(optarg), o_set = 1; break;
+			case 'S': stage = atoi(optarg); break;
+			case 'd': opt.bub_dist = atoi(optarg); break;
+			case 'g': opt.gap_fuzz = atoi(optarg); break;
+			case 'h': opt.max_hang = atoi(optarg); break;
+			case 'I': opt.int_frac = atof(optarg); break;
+			case 'e': opt.max_ext = atoi(optarg); break;
+			case 'f': fn_reads = optarg; break;
+			case 'p': outfmt = optarg; break;
+			case '1': no_first = 1; break;
+			case '2': no_second = 1; break;
+			case 'n': opt.n_rounds = atoi(optarg) - 1; break;
+			case 'B': bi_dir = 1; break;
+			case 'b': bi_dir = 0; break;
+			case 'R': no_cont = 1; break;
+			case 'F': opt.final_ovlp_drop_ratio = atof(optarg); break;
+			case 'V': printf("%s\n", MAB_VERSION); return 0;
+			case 'r': {
+				char *s;
+				opt.max_ovlp_drop_ratio = strtod(optarg, &s);
+				if (*s == ',') opt.min_ovlp_drop_ratio = strtod(s + 1, &s);
+				break; }
+		}
+	}
+	if (o_set == 0) opt.min_ovlp = opt.min_span;
+	if (argc == optind) { usage(&opt, outfmt); return 1; }
+
+	sys_init();
+	if ((env = getenv("MINIASM_B200_DEVICE")) != 0) device = atoi(env);
+	ctx = mab_create(device);
+
+	if (no_cont) { /* -R: the exclusion list is a host-side streaming pass; hits then come in through ma_hit_read */
+		sdict_t *excl, *d0;
+		ma_hit_t *hit;
+		size_t n_hits;
+		fprintf(stderr, "[M::%s] ===> Step 0: removing contained reads <===\n", __func__);
+		excl = ma_hit_no_cont(argv[optind], opt.min_span, opt.min_match, opt.max_hang, opt.int_frac);
+		fprintf(stderr, "[M::%s] ===> Step 1: reading read mappings <===\n", __func__);
+		d0 = sd_init();
+		hit = ma_hit_read(argv[optind], opt.min_span, opt.min_match, d0, &n_hits, bi_dir, excl);
+		mab_load_hits(ctx, hit, n_hits, d0);
+		free(hit); sd_destroy(d0); sd_destroy(excl);
+	} else {
+		fprintf(stderr, "[M::%s] ===> Step 1: reading read mappings <===\n", __func__);
+		if (mab_load_paf_file(ctx, argv[optind]) < 0) {
+			fprintf(stderr, "[E::%s] could not open PAF file %s\n", "ma_hit_read", argv[optind]);
+			exit(1);
+		}
+		mab_ingest(ctx, opt.min_span, opt.min_match, bi_dir);
+	}
+
+	if (!no_first) fprintf(stderr, "[M::%s] ===> Step 2: 1-pass (crude) read selection <===\n", __func__);
+	if (!no_second) fprintf(stderr, "[M::%s] ===> Step 3: 2-pass (fine) read selection <===\n", __func__);
+	mab_select(ctx, &opt, no_first, no_second, stage);
+
+	if (strcmp(outfmt, "bed") == 0) {
+		d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
+		if (sub) write_bed(d, sub);
+	} else if (strcmp(outfmt, "paf") == 0) {
+		size_t n_hits;
+		ma_hit_t *hit = mab_export_hits(ctx, &n_hits);
+		d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
+		if (sub) write_paf(n_hits, hit, d, sub);
+		free(hit);
+	} else if (strcmp(outfmt, "ug") == 0 || strcmp(outfmt, "sg") == 0) {
+		fprintf(stderr, "[M::%s] ===> Step 4: graph cleaning <===\n", __func__);
+		mab_layout(ctx, &opt, stage);
+		d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
+		if (strcmp(outfmt, "ug") == 0) {
+			ma_ug_t *ug;
+			fprintf(stderr, "[M::%s] ===> Step 5: generating unitigs <===\n", __func__);
+			mab_unitigs(ctx);
+			ug = mab_export_ug(ctx);
+			if (fn_reads) ma_ug_seq(ug, d, sub, fn_reads);
+			ma_ug_print(ug, d, sub, stdout);
+			ma_ug_destroy(ug);
+		} else {
+			asg_t *sg = mab_export_sg(ctx);
+			ma_sg_print(sg, d, sub, stdout);
+			asg_destroy(sg);
+		}
+	}
+	free(sub);
+	if (d) sd_destroy(d);
+	mab_destroy(ctx);
+
+	fprintf(stderr, "[M::%s] Version: %s\n", __func__, MAB_VERSION);
+	fprintf(stderr, "[M::%s] CMD:", __func__);
+	for (i = 0; i < argc; ++i) fprintf(stderr, " %s", argv[i]);
+	fprintf(stderr, "\n[M::%s] Real time: %.3f sec; CPU: %.3f sec\n", __func__, sys_realtime(), sys_cputime());
+	return 0;
+}

@@ -1,0 +1,399 @@
+// ingest_dev.cu -- GPU ingest of PAF text (the reference spends 55-60 % of its wall time here).
+//
+// Reference semantics reproduced (paf.c:34-67, kseq.h:101-149, hit.c:82-104, sdict.c:27-45):
+//   * lines end at '\n'; one trailing '\r' is dropped when the line is longer than one byte;
+//   * fields split on TAB; columns 2-4,7-11 via strtol(.,10) truncated to uint32 (ml to 31 bits);
+//     rev = first byte of column 5 is '-'; fewer than 10 fields -> line skipped; exactly 10 fields -> bl is
+//     whatever the last line with an 11th field left behind;
+//   * a line is stored iff qe-qs >= min_span && te-ts >= min_span (unsigned) && ml >= min_match;
+//   * read ids = order of first appearance among stored lines, query name before target name; the length
+//     kept for a read is the one seen at that first appearance;
+//   * every stored line yields a hit and, when bi_dir and query != target, the mirrored hit right after it;
+//   * hits sorted by (query id, query start).
+//
+// GPU shape: (1) line starts by a flagged select over the bytes, (2) one thread per line parses and hashes the
+// two names, (3) names go through an open-addressing table keyed by a 64-bit hash, value = smallest
+// occurrence number (atomicMin), every occurrence is then verified byte-for-byte against the table's
+// representative (a true hash collision triggers a re-run with another seed: ids are exact, never
+// probabilistic), (4) distinct names ranked by first occurrence = ids, (5) hits emitted at scanned offsets,
+// (6) radix sort (hit_dev.cu).
+#include "ingest_dev.cuh"
+#include <cub/cub.cuh>
+
+struct PLine {                 // one parsed PAF line, 64 bytes
+	uint32_t ql, qs, qe, tl, ts, te, ml_rev, bl;
+	uint64_t hq, ht;           // name hashes; replaced by the dictionary slots once the insert pass ran
+	uint32_t tdelta;           // target name offset from the line start
+	uint16_t qnl, tnl;         // name lengths
+	uint8_t nf, pass, pad[2];  // number of fields (capped at 11), passes the filter
+	uint32_t pad2;
+};
+#define slot_q hq
+#define slot_t ht
+static_assert(sizeof(PLine) == 64, "PLine layout");
+
+struct IsLineStart {
+	const char *text;
+	__device__ __forceinline__ bool operator()(uint64_t p) const { return p == 0 || text[p - 1] == '\n'; }
+};
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t k)
+{
+	k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+	return k;
+}
+
+// strtol(field, 0, 10) narrowed to uint32, on the byte range [p, e)
+__device__ __forceinline__ uint32_t field_to_u32(const char *p, const char *e)
+{
+	while (p < e && (*p == ' ' || (*p >= '\t' && *p <= '\r'))) ++p;
+	bool neg = false;
+	if (p < e && (*p == '-' || *p == '+')) neg = *p == '-', ++p;
+	unsigned long long v = 0;
+	bool ovf = false;
+	const unsigned long long lim = neg ? 9223372036854775808ull : 9223372036854775807ull;
+	for (; p < e && *p >= '0' && *p <= '9'; ++p) {
+		unsigned dgt = *p - '0';
+		if (!ovf && v > (lim - dgt) / 10) ovf = true;
+		if (!ovf) v = v * 10 + dgt;
+	}
+	if (ovf) v = lim;                                   // LONG_MAX / LONG_MIN clamp
+	long long s = neg ? (long long)(0ull - v) : (long long)v;
+	return (uint32_t)s;
+}
+
+__global__ void k_parse(const char *__restrict__ text, size_t len, const uint64_t *__restrict__ start, uint64_t n_lines,
+                        int min_span, int min_match, uint64_t seed, PLine *out, unsigned long long *counts)
+{
+	unsigned n_parsed = 0;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t s = start[i];
+		uint64_t eol = i + 1 < n_lines ? start[i + 1] - 1 : (text[len - 1] == '\n' ? len - 1 : len);
+		if (eol - s > 1 && text[eol - 1] == '\r') --eol;
+		const char *p = text + s, *e = text + eol, *f = p;
+		PLine r;
+		memset(&r, 0, sizeof(r));
+		int t = 0;
+		bool too_long = false;
+		for (const char *q = p;; ++q) {
+			if (q == e || *q == '\t') {
+				switch (t) {
+					case 0: {
+						uint64_t h = 1469598103934665603ULL ^ seed;
+						for (const char *c = f; c < q; ++c) h = (h ^ (uint8_t)*c) * 1099511628211ULL;
+						h = fmix64(h); r.hq = h ? h : 1; r.qnl = (uint16_t)(q - f); too_long |= (q - f) > 65535; break; }
+					case 1: r.ql = field_to_u32(f, q); break;
+					case 2: r.qs = field_to_u32(f, q); break;
+					case 3: r.qe = field_to_u32(f, q); break;
+					case 4: r.ml_rev = (f < q && *f == '-') ? 0x80000000u : 0; break;
+					case 5: {
+						uint64_t h = 1469598103934665603ULL ^ seed;
+						for (const char *c = f; c < q; ++c) h = (h ^ (uint8_t)*c) * 1099511628211ULL;
+						h = fmix64(h); r.ht = h ? h : 1; r.tnl = (uint16_t)(q - f); r.tdelta = (uint32_t)(f - p); too_long |= (q - f) > 65535; break; }
+					case 6: r.tl = field_to_u32(f, q); break;
+					case 7: r.ts = field_to_u32(f, q); break;
+					case 8: r.te = field_to_u32(f, q); break;
+					case 9: r.ml_rev |= field_to_u32(f, q) & 0x7fffffffu; break;
+					case 10: r.bl = field_to_u32(f, q); break;
+				}
+				++t;
+				f = q + 1;
+				if (q == e || t == 11) break;
+			}
+		}
+		r.nf = (uint8_t)t;
+		if (t >= 10) {
+			++n_parsed;
+			if (too_long) atomicAdd(counts + 1, 1ull); // a name beyond 65535 bytes does not fit the record: the host aborts
+		}
+		out[i] = r;
+	}
+	n_parsed = __reduce_add_sync(0xffffffffu, n_parsed);
+	if ((threadIdx.x & 31) == 0 && n_parsed) atomicAdd(counts, (unsigned long long)n_parsed);
+	(void)min_span; (void)min_match;
+}
+
+// stale bl for 10-field lines + the store filter (needs the final bl? no: the filter uses qe,qs,te,ts,ml only)
+__global__ void k_fix_filter(PLine *ln, uint64_t n_lines, int min_span, int min_match, unsigned long long *n_pass)
+{
+	unsigned cnt = 0;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+		PLine *r = ln + i;
+		bool pass = false;
+		if (r->nf >= 10) {
+			if (r->nf == 10) { // bl keeps the value of the closest earlier line that had an 11th field (paf.c:47, hit.c:73)
+				uint32_t bl = 0;
+				for (uint64_t j = i; j-- > 0;)
+					if (ln[j].nf >= 11) { bl = ln[j].bl; break; }
+				r->bl = bl;
+			}
+			pass = !(r->qe - r->qs < (uint32_t)min_span || r->te - r->ts < (uint32_t)min_span || (int)(r->ml_rev & 0x7fffffffu) < min_match);
+		}
+		r->pass = pass;
+		cnt += pass;
+	}
+	cnt = __reduce_add_sync(0xffffffffu, cnt);
+	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_pass, (unsigned long long)cnt);
+}
+
+// --------------------------------------------------------------------------------------------- dictionary
+struct NameTab {
+	unsigned long long *key;     // 64-bit name hash, 0 = empty
+	unsigned long long *first;   // smallest occurrence number (2*line + {0 query, 1 target})
+	uint32_t *id;                // read id of the slot (after ranking)
+	uint64_t mask;
+};
+
+__device__ __forceinline__ uint32_t tab_insert(const NameTab &t, uint64_t h, uint64_t occ, unsigned long long *overflow)
+{
+	uint64_t s = h & t.mask;
+	for (int probe = 0; probe < 1 << 14; ++probe, s = (s + 1) & t.mask) {
+		unsigned long long k = t.key[s];
+		if (k == 0) {
+			k = atomicCAS(&t.key[s], 0ull, (unsigned long long)h);
+			if (k == 0) k = h;
+		}
+		if (k == h) {
+			if (t.first[s] > occ) atomicMin(&t.first[s], (unsigned long long)occ); // values only decrease: the plain read filters most atomics
+			return (uint32_t)s;
+		}
+	}
+	atomicAdd(overflow, 1ull);
+	return 0xffffffffu;
+}
+
+__global__ void k_dict_insert(PLine *ln, uint64_t n_lines, NameTab t, unsigned long long *overflow)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+		if (!ln[i].pass) continue;
+		const uint64_t hq = ln[i].hq, ht = ln[i].ht;
+		ln[i].slot_q = tab_insert(t, hq, 2 * i, overflow);
+		ln[i].slot_t = tab_insert(t, ht, 2 * i + 1, overflow);
+	}
+}
+
+__device__ __forceinline__ bool same_name(const char *text, const uint64_t *start, const PLine *ln, uint64_t occ_a, uint64_t occ_b)
+{
+	const PLine &a = ln[occ_a >> 1], &b = ln[occ_b >> 1];
+	const uint32_t la = occ_a & 1 ? a.tnl : a.qnl, lb = occ_b & 1 ? b.tnl : b.qnl;
+	if (la != lb) return false;
+	const char *pa = text + start[occ_a >> 1] + (occ_a & 1 ? a.tdelta : 0), *pb = text + start[occ_b >> 1] + (occ_b & 1 ? b.tdelta : 0);
+	for (uint32_t k = 0; k < la; ++k)
+		if (pa[k] != pb[k]) return false;
+	return true;
+}
+
+// every occurrence must spell the same name as the representative (first occurrence) of its slot
+__global__ void k_dict_verify(const char *text, const uint64_t *start, const PLine *ln, uint64_t n_lines, NameTab t, unsigned long long *n_bad)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+		if (!ln[i].pass) continue;
+		uint64_t fq = t.first[ln[i].slot_q], ft = t.first[ln[i].slot_t];
+		bool ok = (fq == 2 * i || same_name(text, start, ln, 2 * i, fq)) && (ft == 2 * i + 1 || same_name(text, start, ln, 2 * i + 1, ft));
+		if (!ok) atomicAdd(n_bad, 1ull);
+	}
+}
+
+struct SlotUsed {
+	const unsigned long long *key;
+	__device__ __forceinline__ bool operator()(uint64_t s) const { return key[s] != 0; }
+};
+
+__global__ void k_dict_pairs(const uint64_t *slots, uint32_t n, NameTab t, unsigned long long *first_out)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) first_out[i] = t.first[slots[i]];
+}
+
+__global__ void k_dict_rank(const unsigned long long *first_sorted, const uint64_t *slot_sorted, uint32_t n, NameTab t,
+                            const uint64_t *start, const PLine *ln, uint64_t *noff, uint32_t *nlen, uint32_t *slen, unsigned long long *tot_len)
+{
+	unsigned long long sum = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint64_t occ = first_sorted[i];
+		const PLine &r = ln[occ >> 1];
+		t.id[slot_sorted[i]] = i;
+		noff[i] = start[occ >> 1] + (occ & 1 ? r.tdelta : 0);
+		nlen[i] = occ & 1 ? r.tnl : r.qnl;
+		slen[i] = occ & 1 ? r.tl : r.ql;
+		sum += slen[i];
+	}
+	typedef cub::BlockReduce<unsigned long long, 256> BR;
+	__shared__ typename BR::TempStorage ts;
+	unsigned long long s = BR(ts).Sum(sum);
+	if (threadIdx.x == 0 && s) atomicAdd(tot_len, s);
+}
+
+// --------------------------------------------------------------------------------------------- hits
+__global__ void k_hit_count(const PLine *ln, uint64_t n_lines, int bi_dir, uint32_t *cnt)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x)
+		cnt[i] = ln[i].pass ? (bi_dir && ln[i].slot_q != ln[i].slot_t ? 2 : 1) : 0;
+}
+
+__global__ void k_hit_emit(const PLine *ln, uint64_t n_lines, const uint32_t *cnt, const uint64_t *off, NameTab t, DHit *out, unsigned *max_qs)
+{
+	unsigned mx = 0;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t c = cnt[i];
+		if (c == 0) continue;
+		const PLine r = ln[i];
+		const uint32_t qid = t.id[r.slot_q], tid = t.id[r.slot_t];
+		DHit h;
+		h.qns = (uint64_t)qid << 32 | r.qs, h.qe = r.qe, h.tn = tid, h.ts = r.ts, h.te = r.te, h.ml_rev = r.ml_rev, h.bl_del = r.bl & 0x7fffffffu;
+		uint4 *o = reinterpret_cast<uint4*>(out + off[i]);
+		o[0] = make_uint4((uint32_t)h.qns, (uint32_t)(h.qns >> 32), h.qe, h.tn);
+		o[1] = make_uint4(h.ts, h.te, h.ml_rev, h.bl_del);
+		mx = r.qs > mx ? r.qs : mx;
+		if (c == 2) { // the same overlap seen from the target (hit.c:92-98)
+			o[2] = make_uint4(r.ts, tid, r.te, qid);
+			o[3] = make_uint4(r.qs, r.qe, h.ml_rev, h.bl_del);
+			mx = r.ts > mx ? r.ts : mx;
+		}
+	}
+	mx = __reduce_max_sync(0xffffffffu, mx);
+	if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_qs, mx);
+}
+
+void names_free(MabDev &d, DNames &n)
+{
+	d.free(n.off); d.free(n.nlen); d.free(n.slen);
+	n = DNames();
+}
+
+static inline uint32_t bits_for(uint64_t x) { uint32_t b = 0; while (x) ++b, x >>= 1; return b ? b : 1; }
+
+void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min_match, int bi_dir, DHits &h, DNames &names, IngestStats &st)
+{
+	memset(&st, 0, sizeof(st));
+	names = DNames();
+	h.n = 0, h.n_seq = 0;
+	if (len == 0) { dh_reserve(d, h, 1); return; }
+
+	// (1) line starts
+	uint64_t *start = nullptr;
+	uint64_t n_lines;
+	{
+		cub::CountingInputIterator<uint64_t> pos(0);
+		IsLineStart pred{d_text};
+		// count first (one pass over the bytes), then select into an exactly sized array
+		size_t tb = 0;
+		unsigned long long *d_n = d.d_scal + SC_NSEL;
+		cub::TransformInputIterator<int, IsLineStart, cub::CountingInputIterator<uint64_t>> ones(pos, pred);
+		cub::DeviceReduce::Sum(nullptr, tb, ones, d_n, (int64_t)len, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceReduce::Sum(tmp, tb, ones, d_n, (int64_t)len, d.stream);
+		++d.n_lib;
+		n_lines = d.get_scal(SC_NSEL);
+		start = mab_alloc<uint64_t>(d, n_lines + 1);
+		tb = 0;
+		cub::DeviceSelect::If(nullptr, tb, pos, start, d_n, (int64_t)len, pred, d.stream);
+		tmp = d.tmp(tb);
+		cub::DeviceSelect::If(tmp, tb, pos, start, d_n, (int64_t)len, pred, d.stream);
+		++d.n_lib;
+	}
+	st.n_lines = n_lines;
+
+	// (2) parse
+	PLine *ln = mab_alloc<PLine>(d, n_lines);
+	uint32_t *cnt = nullptr;
+	uint64_t *off = nullptr;
+	NameTab tab{nullptr, nullptr, nullptr, 0};
+	uint64_t n_pass = 0, cap = 0;
+	uint64_t seed = 0;
+	for (int attempt = 0;; ++attempt) {
+		d.zero_scal(SC_COUNT, 4);
+		MAB_LAUNCH(d, k_parse, mab_grid(n_lines, 128), 128, 0, d_text, len, start, n_lines, min_span, min_match, seed, ln, d.d_scal + SC_COUNT);
+		MAB_LAUNCH(d, k_fix_filter, mab_grid(n_lines, 256), 256, 0, ln, n_lines, min_span, min_match, d.d_scal + SC_AUX);
+		st.n_parsed = d.get_scal(SC_COUNT);
+		n_pass = d.h_scal[SC_AUX];
+		if (d.h_scal[SC_COUNT + 1]) { fprintf(stderr, "[E::miniasm_b200] a read name in the PAF is longer than 65535 bytes\n"); exit(78); }
+		// (3) dictionary: grow the table until every name finds a slot, re-seed the hash on a verified collision
+		if (cap == 0) { cap = 1ull << 20; while (cap < n_pass / 4) cap <<= 1; }
+		bool collided = false, overflowed = false;
+		tab.key = (unsigned long long*)mab_alloc<uint64_t>(d, cap);
+		tab.first = (unsigned long long*)mab_alloc<uint64_t>(d, cap);
+		tab.id = mab_alloc<uint32_t>(d, cap);
+		tab.mask = cap - 1;
+		MAB_CUDA(cudaMemsetAsync(tab.key, 0, cap * 8, d.stream));
+		MAB_CUDA(cudaMemsetAsync(tab.first, 0xff, cap * 8, d.stream));
+		d.zero_scal(SC_BIG, 1);
+		d.zero_scal(SC_AUX2, 1);
+		MAB_LAUNCH(d, k_dict_insert, mab_grid(n_lines, 256), 256, 0, ln, n_lines, tab, d.d_scal + SC_BIG);
+		if (d.get_scal(SC_BIG) == 0) {
+			MAB_LAUNCH(d, k_dict_verify, mab_grid(n_lines, 256), 256, 0, d_text, start, ln, n_lines, tab, d.d_scal + SC_AUX2);
+			collided = d.get_scal(SC_AUX2) != 0;
+		} else overflowed = true;
+		if (!collided && !overflowed) break;
+		d.free(tab.key); d.free(tab.first); d.free(tab.id);
+		if (overflowed) { cap <<= 2; continue; }       // table too small for the number of distinct names: parse again (the insert pass reuses the hash fields)
+		seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; // two names share a 64-bit hash: hash again with another seed
+		++st.hash_retries;
+		if (attempt > 16) { fprintf(stderr, "[E::miniasm_b200] read-name hashing keeps colliding\n"); exit(77); }
+	}
+
+	// (4) ids = rank of the first occurrence
+	uint64_t *slots = mab_alloc<uint64_t>(d, cap);
+	uint32_t n_seq;
+	{
+		cub::CountingInputIterator<uint64_t> pos(0);
+		SlotUsed used{tab.key};
+		size_t tb = 0;
+		unsigned long long *d_n = d.d_scal + SC_NSEL;
+		cub::DeviceSelect::If(nullptr, tb, pos, slots, d_n, (int64_t)cap, used, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceSelect::If(tmp, tb, pos, slots, d_n, (int64_t)cap, used, d.stream);
+		++d.n_lib;
+		uint64_t n = d.get_scal(SC_NSEL);
+		if (n >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 reads\n"); exit(73); }
+		n_seq = (uint32_t)n;
+	}
+	names.n_seq = n_seq;
+	names.off = mab_alloc<uint64_t>(d, n_seq); names.nlen = mab_alloc<uint32_t>(d, n_seq); names.slen = mab_alloc<uint32_t>(d, n_seq);
+	if (n_seq) {
+		unsigned long long *fa = (unsigned long long*)mab_alloc<uint64_t>(d, n_seq), *fb = (unsigned long long*)mab_alloc<uint64_t>(d, n_seq);
+		uint64_t *sb = mab_alloc<uint64_t>(d, n_seq);
+		MAB_LAUNCH(d, k_dict_pairs, mab_grid(n_seq, 256), 256, 0, slots, n_seq, tab, fa);
+		cub::DoubleBuffer<unsigned long long> dk(fa, fb);
+		cub::DoubleBuffer<uint64_t> dv(slots, sb);
+		size_t tb = 0;
+		int end_bit = (int)bits_for(2 * n_lines + 1);
+		cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)n_seq, 0, end_bit, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int)n_seq, 0, end_bit, d.stream);
+		++d.n_lib;
+		d.zero_scal(SC_AUX, 1);
+		MAB_LAUNCH(d, k_dict_rank, mab_grid(n_seq, 256), 256, 0, dk.Current(), dv.Current(), n_seq, tab, start, ln, names.off, names.nlen, names.slen, d.d_scal + SC_AUX);
+		st.tot_len = d.get_scal(SC_AUX);
+		d.free(fa); d.free(fb); d.free(sb);
+	}
+	d.free(slots);
+
+	// (5) hits at scanned offsets (file order, mirrored hit right after its original)
+	cnt = mab_alloc<uint32_t>(d, n_lines);
+	off = mab_alloc<uint64_t>(d, n_lines + 1);
+	MAB_LAUNCH(d, k_hit_count, mab_grid(n_lines, 256), 256, 0, ln, n_lines, bi_dir, cnt);
+	{
+		size_t tb = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, off, (int64_t)n_lines, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, off, (int64_t)n_lines, d.stream);
+		++d.n_lib;
+	}
+	uint64_t last_off;
+	uint32_t last_cnt;
+	MAB_CUDA(cudaMemcpyAsync(&last_off, off + n_lines - 1, 8, cudaMemcpyDeviceToHost, d.stream));
+	MAB_CUDA(cudaMemcpyAsync(&last_cnt, cnt + n_lines - 1, 4, cudaMemcpyDeviceToHost, d.stream));
+	d.sync();
+	const uint64_t n_hits = last_off + last_cnt;
+	dh_reserve(d, h, n_hits ? n_hits : 1);
+	h.n = n_hits, h.n_seq = n_seq;
+	d.zero_scal(SC_AUX, 1);
+	if (n_hits) MAB_LAUNCH(d, k_hit_emit, mab_grid(n_lines, 256), 256, 0, ln, n_lines, cnt, off, tab, h.a, (unsigned*)(d.d_scal + SC_AUX));
+	uint32_t max_qs = (uint32_t)(d.get_scal(SC_AUX) & 0xffffffffu);
+	st.n_hits = n_hits, st.n_seq = n_seq, st.max_qs_bits = bits_for(max_qs);
+	d.free(cnt); d.free(off); d.free(ln); d.free(start);
+	d.free(tab.key); d.free(tab.first); d.free(tab.id);
+
+	// (6) ma_hit_sort
+	dh_sort(d, h, st.max_qs_bits);
+}

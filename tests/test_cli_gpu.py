@@ -1,0 +1,129 @@
+"""The drop-in command line: `miniasm-b200 [options] in.paf` against the unmodified reference binary on the
+same input, option by option (main.c:44-74 flag surface, -S stage dumps of SURVEY.md section 4)."""
+import gzip
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from miniasm_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "miniasm_b200", "miniasm-b200")
+REF = os.path.join(ROOT, "oracle", "_ref", "miniasm_ref")
+
+
+def run(binary, args, stdin=None):
+    r = subprocess.run([binary] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, stdin=stdin)
+    return r.returncode, r.stdout, r.stderr
+
+
+@pytest.fixture(scope="module")
+def pafs(built, paf_dir):
+    return {name: synth.generate(name, f"{paf_dir}/{name}.paf") for name in ["chaos_small", "chaos", "bubbles800", "tiny_exact", "shuffled"]}
+
+
+def same(args, exact=True):
+    rc_r, out_r, _ = run(REF, args)
+    rc_c, out_c, err_c = run(CLI, args)
+    assert rc_c == rc_r, err_c.decode()[-2000:]
+    if exact:
+        assert out_c == out_r
+    else:  # outputs whose line order depends on ties of the reference's unstable radix sort
+        assert sorted(out_c.splitlines()) == sorted(out_r.splitlines())
+    return out_c
+
+
+@pytest.mark.parametrize("name", ["chaos_small", "chaos", "bubbles800", "tiny_exact", "shuffled"])
+def test_default_gfa(name, pafs):
+    out = same([pafs[name]])
+    assert out.startswith(b"S\tutg000001")
+
+
+@pytest.mark.parametrize("opts", [
+    ["-c", "2"], ["-c", "5"], ["-e", "2"], ["-e", "10"], ["-n", "1"], ["-n", "5"], ["-r", "0.8,0.4"], ["-F", "0.9"],
+    ["-h", "500"], ["-h", "3000"], ["-I", "0.6"], ["-o", "3000"], ["-m", "2500"], ["-i", "0.3"], ["-s", "1500"], ["-s", "4000"],
+    ["-g", "10"], ["-g", "100000"], ["-d", "2000"], ["-d", "500000"], ["-1"], ["-2"], ["-1", "-2"], ["-b"], ["-B"], ["-R"], ["-R", "-b"],
+])
+def test_options(opts, pafs):
+    same(opts + [pafs["chaos_small"]])
+
+
+@pytest.mark.parametrize("stage", [2, 3, 4, 5])
+def test_stage_dumps_paf(stage, pafs):
+    same(["-S", str(stage), "-p", "paf", pafs["chaos_small"]], exact=False)
+
+
+@pytest.mark.parametrize("stage", [2, 3, 4, 5, 100])
+def test_bed(stage, pafs):
+    same(["-S", str(stage), "-p", "bed", pafs["chaos_small"]])
+
+
+@pytest.mark.parametrize("stage", [1, 5, 6, 7, 9, 10, 11])
+def test_stage_dumps_sg_ug(stage, pafs):
+    same(["-S", str(stage), "-p", "sg", pafs["chaos"]], exact=False)
+    same(["-S", str(stage), "-p", "ug", pafs["chaos"]])
+
+
+def test_gzip_and_stdin(pafs, paf_dir):
+    gz = os.path.join(paf_dir, "in.paf.gz")
+    with open(pafs["chaos_small"], "rb") as f, gzip.open(gz, "wb") as g:
+        shutil.copyfileobj(f, g)
+    plain = same([pafs["chaos_small"]])
+    assert same([gz]) == plain
+    with open(pafs["chaos_small"], "rb") as f:
+        rc, out, _ = run(CLI, ["-"], stdin=f)
+    assert rc == 0 and out == plain
+
+
+def test_version_usage_and_missing_file(pafs):
+    assert run(CLI, ["-V"])[:2] == run(REF, ["-V"])[:2]
+    rc, out, err = run(CLI, [])
+    assert rc == 1 and out == b"" and b"Usage:" in err
+    rc_r, _, _ = run(REF, ["/nonexistent.paf"])
+    rc_c, _, err = run(CLI, ["/nonexistent.paf"])
+    assert rc_c == rc_r == 1 and b"could not open PAF file" in err
+
+
+def test_with_reads(pafs, paf_dir):
+    from tests.test_clean_gpu import _write_reads
+    reads = _write_reads(pafs["chaos_small"], os.path.join(paf_dir, "cli_reads.fa"))
+    out = same(["-f", reads, pafs["chaos_small"]])
+    assert b"\t*\tLN" not in out
+
+
+def test_weird_lines(paf_dir):
+    """Parser corners (paf.c:34-67): CRLF, short lines, 10-field lines (stale bl), extra tags, empty lines,
+    signs and junk in numeric fields, no trailing newline."""
+    base = synth.generate("-n 3000 -s 31 -j 200 -C 200000", os.path.join(paf_dir, "weird_base.paf"))
+    lines = open(base, "rb").read().split(b"\n")
+    out = []
+    for i, ln in enumerate(lines):
+        if not ln:
+            continue
+        f = ln.rstrip(b"\r").split(b"\t")
+        if i % 11 == 0:
+            out.append(b"\t".join(f[:10]))                    # 10 fields: bl stays stale
+        elif i % 13 == 0:
+            out.append(b"\t".join(f[:9]))                     # too short: skipped
+        elif i % 17 == 0:
+            out.append(ln + b"\ttp:A:S\tcm:i:12")             # optional tags
+        elif i % 19 == 0:
+            out.append(b"")                                   # empty line
+            out.append(ln)
+        elif i % 23 == 0:
+            f[2] = b"+" + f[2]; f[9] = f[9] + b"xyz"
+            out.append(b"\t".join(f))                         # strtol corner cases
+        elif i % 29 == 0:
+            f[1] = b" " + f[1]
+            out.append(b"\t".join(f) + b"\r")
+        else:
+            out.append(ln)
+    path = os.path.join(paf_dir, "weird.paf")
+    with open(path, "wb") as fo:
+        fo.write(b"\n".join(out))                             # no newline at the end
+    same([path])
+    same(["-S", "2", "-p", "paf", path], exact=False)
