@@ -131,8 +131,36 @@ _SIGS = {
     "ma_ug_destroy": (None, [C.POINTER(MaUg)]),
 }
 
+class MabStats(C.Structure):                                          # mab_stats_t
+    _fields_ = [(n, C.c_uint64) for n in ("n_lines", "n_hits_stored", "n_seq_in", "n_hits_final", "n_seq_final", "n_arc_sg",
+                                          "n_arc_trans_in", "n_reduced", "trans_inner", "n_arc_final", "n_utg")] + \
+               [("ms_del_trans_kernel", C.c_double), ("n_kernel_launches", C.c_uint64), ("n_lib_calls", C.c_uint64)]
+
+
 # symbols include/miniasm_b200.h declares beyond the reference seam
 _PRODUCT_ONLY = {
+    "mab_create": (C.c_void_p, [C.c_int]),
+    "mab_destroy": (None, [C.c_void_p]),
+    "mab_stats": (C.POINTER(MabStats), [C.c_void_p]),
+    "mab_load_paf_text": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mab_load_paf_file": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mab_ingest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mab_load_hits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Sdict)]),
+    "mab_select": (C.c_int, [C.c_void_p, C.POINTER(MaOpt), C.c_int, C.c_int, C.c_int]),
+    "mab_layout": (C.c_int, [C.c_void_p, C.POINTER(MaOpt), C.c_int]),
+    "mab_unitigs": (C.c_int, [C.c_void_p]),
+    "mab_export_dict": (C.POINTER(Sdict), [C.c_void_p]),
+    "mab_export_sub": (C.c_void_p, [C.c_void_p]),
+    "mab_export_hits": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "mab_export_sg": (C.POINTER(AsgT), [C.c_void_p]),
+    "mab_export_ug": (C.POINTER(MaUg), [C.c_void_p]),
+    "mab_coverage": (C.c_float, [C.c_void_p]),
+    "mab_event_create": (C.c_void_p, []),
+    "mab_event_record": (None, [C.c_void_p, C.c_void_p]),
+    "mab_event_elapsed_ms": (C.c_float, [C.c_void_p, C.c_void_p]),
+    "mab_event_destroy": (None, [C.c_void_p]),
+    "mab_sync": (None, [C.c_void_p]),
+    "mab_last_clean": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "mab_set_verbose": (None, [C.c_int]),
     "mab_last_del_trans": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),

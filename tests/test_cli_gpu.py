@@ -65,7 +65,9 @@ def test_bed(stage, pafs):
 @pytest.mark.parametrize("stage", [1, 5, 6, 7, 9, 10, 11])
 def test_stage_dumps_sg_ug(stage, pafs):
     same(["-S", str(stage), "-p", "sg", pafs["chaos"]], exact=False)
-    same(["-S", str(stage), "-p", "ug", pafs["chaos"]])
+    # before transitive reduction the raw graph has equal-key arcs; their order (unstable sort in the reference)
+    # decides the order of tied unitig links, so the early dumps are compared as multisets
+    same(["-S", str(stage), "-p", "ug", pafs["chaos"]], exact=stage >= 6)
 
 
 def test_gzip_and_stdin(pafs, paf_dir):
