@@ -315,6 +315,7 @@ def main():
             "gpu_launches": launches, "lib_calls": libcalls,
             "arcs_per_sec_del_trans": n_arc_in / (dt_ms_trans * 1e-3) if dt_ms_trans else None,
             "del_trans": {"n_arc_in": n_arc_in, "inner_iters": inner, "n_vtx": n_vtx, "kernel_ms": dt_ms_trans},
+            "phase_ms_last_step": {"ingest": st.ms_ingest, "select": st.ms_select, "layout": st.ms_layout, "unitigs": st.ms_unitigs},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_del_trans_warp",
                          "algorithmic_bytes": alg_bytes, "formula": "16*n_arc + 16*inner_iters + 1*n_arc + 12*n_vtx"},

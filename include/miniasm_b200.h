@@ -150,6 +150,7 @@ typedef struct {
 	uint64_t n_arc_final, n_utg;
 	double   ms_del_trans_kernel;                       /* CUDA-event time of the transitive-reduction kernel */
 	uint64_t n_kernel_launches, n_lib_calls;
+	double   ms_ingest, ms_select, ms_layout, ms_unitigs; /* CUDA-event time of the last call of each step */
 } mab_stats_t;
 
 mab_ctx_t *mab_create(int device);                      /* exits if the device cannot be initialised */

@@ -268,27 +268,32 @@ void dg_symm(MabDev &d, DGraph &g)
 // ---------------------------------------------------------------------------------------------
 constexpr int DT_WARPS = 8;      // warps per CTA, warp kernel
 constexpr int DT_MAXD  = 128;    // longest slab the warp kernel takes
-constexpr int DT_HASH  = 256;    // table slots per warp (load factor <= 0.5)
+constexpr int DT_HASH  = 256;    // table slots per warp (the live part is the next power of two >= 2*nv)
+constexpr int DT_EAGER = 4;      // slab positions whose neighbour index word is fetched ahead of use
 constexpr uint32_t DT_EMPTY = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t dt_hash(uint32_t x, uint32_t mask) { return (x * 2654435761u) >> 7 & mask; }
 
+// Shared memory per warp: hkey (target vertex per slot) | tl (arc length per slab entry) | ti (idx word of the first
+// DT_EAGER targets; reused as "lowest slab position per slot" when a slab holds multi-arcs) | hmark (mark per slot:
+// 1 = target of v, 2 = reduced) | slot (table slot of slab entry i).  The mark lives in the table, so arcs to the same
+// target share it exactly like mark[] indexed by vertex does in the reference.
 __global__ void __launch_bounds__(DT_WARPS * 32)
 k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, const uint32_t *__restrict__ seq,
                  uint32_t n_vtx, uint32_t fuzz, uint8_t *__restrict__ flag,
                  uint32_t *__restrict__ big_list, unsigned long long *scal)
 {
-	__shared__ uint32_t s_tv[DT_WARPS][DT_MAXD];     // target vertex of slab entry i
-	__shared__ uint32_t s_tl[DT_WARPS][DT_MAXD];     // arc length of slab entry i
-	__shared__ uint64_t s_ti[DT_WARPS][DT_MAXD];     // idx[target_i]
-	__shared__ uint32_t s_hash[DT_WARPS][DT_HASH];   // target -> first slab position
-	__shared__ uint8_t  s_st[DT_WARPS][DT_MAXD];     // mark of the target first seen at position i
-	__shared__ uint8_t  s_rep[DT_WARPS][DT_MAXD];    // slab position holding the mark of entry i
+	__shared__ uint32_t s_hkey[DT_WARPS][DT_HASH];
+	__shared__ uint32_t s_tl[DT_WARPS][DT_MAXD];
+	__shared__ uint32_t s_fmin[DT_WARPS][DT_HASH];
+	__shared__ uint64_t s_ti[DT_WARPS][DT_EAGER];
+	__shared__ uint8_t  s_hmark[DT_WARPS][DT_HASH];
+	__shared__ uint8_t  s_slot[DT_WARPS][DT_MAXD];
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	uint32_t *tv = s_tv[warp], *tl = s_tl[warp], *hs = s_hash[warp];
+	uint32_t *hkey = s_hkey[warp], *tl = s_tl[warp], *fmin = s_fmin[warp];
 	uint64_t *ti = s_ti[warp];
-	uint8_t *st = s_st[warp], *rep = s_rep[warp];
+	uint8_t *hmark = s_hmark[warp], *slot = s_slot[warp];
 	unsigned n_red = 0;
 	unsigned long long n_inner = 0;
 
@@ -305,67 +310,79 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 			if (lane == 0) big_list[atomicAdd(scal + SC_BIG, 1ull)] = v;
 			continue;
 		}
-		// stage the slab
-		for (uint32_t i = lane; i < DT_HASH; i += 32) hs[i] = DT_EMPTY;
-		for (uint32_t i = lane; i < nv; i += 32) {
-			DArc a = ld_arc_nc(arc + off + i);
-			tv[i] = a.v; tl[i] = (uint32_t)a.ul; st[i] = 1;
-			ti[i] = __ldg(idx + a.v);
-		}
+		uint32_t mask = 31;
+		while (mask + 1 < 2 * nv) mask = mask * 2 + 1;
+		for (uint32_t i = lane; i <= mask; i += 32) hkey[i] = DT_EMPTY;
 		__syncwarp();
+		// stage the slab and build the target table in one sweep
 		bool dup = false;
 		for (uint32_t i = lane; i < nv; i += 32) {
-			uint32_t x = tv[i], h = dt_hash(x, DT_HASH - 1);
+			const DArc a = ld_arc_nc(arc + off + i);
+			tl[i] = (uint32_t)a.ul;
+			if (i < DT_EAGER) ti[i] = __ldg(idx + a.v);
+			uint32_t h = dt_hash(a.v, mask);
 			for (;;) {
-				uint32_t prev = atomicCAS(&hs[h], DT_EMPTY, i);
-				if (prev == DT_EMPTY) { rep[i] = (uint8_t)i; break; }
-				if (tv[prev] == x) { rep[i] = (uint8_t)prev; dup = true; break; }
-				h = (h + 1) & (DT_HASH - 1);
+				const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a.v);
+				if (prev == DT_EMPTY) { hmark[h] = 1; break; }
+				if (prev == a.v) { dup = true; break; }
+				h = (h + 1) & mask;
 			}
+			slot[i] = (uint8_t)h;
 		}
 		const bool has_dup = __any_sync(0xffffffffu, dup); // multi-arcs: several slab entries share one mark
 		__syncwarp();
 		const uint32_t L = tl[nv - 1] + fuzz;
-		for (uint32_t i = 0; i < nv; ++i) {
-			if (st[rep[i]] != 1) continue;            // target already reduced: do not explore it (asg.c:168)
-			const uint64_t iw = ti[i];
-			const uint32_t nw = (uint32_t)iw, li = tl[i];
+		// i ascends over the slab entries whose target still carries mark 1 (asg.c:164-168); found by ballot
+		for (uint32_t i = 0;;) {
+			uint32_t nxt = nv;
+			for (uint32_t base = i & ~31u; base < nv; base += 32) {
+				const uint32_t k = base + lane;
+				const bool live = k >= i && k < nv && hmark[slot[k]] == 1;
+				const unsigned m = __ballot_sync(0xffffffffu, live);
+				if (m) { nxt = base + __ffs(m) - 1; break; }
+			}
+			if (nxt >= nv) break;
+			i = nxt;
+			const uint32_t w = hkey[slot[i]], li = tl[i];
+			const uint64_t iw = i < DT_EAGER ? ti[i] : __ldg(idx + w);
+			const uint32_t nw = (uint32_t)iw;
 			const DArc *aw = arc + (iw >> 32);
 			for (uint32_t j0 = 0; j0 < nw; j0 += 32) {
-				uint32_t j = j0 + lane, x = 0;
+				const uint32_t j = j0 + lane;
+				uint32_t x = 0;
 				bool ok = false;
 				if (j < nw) {
-					DArc a = ld_arc_nc(aw + j);
+					const DArc a = ld_arc_nc(aw + j);
 					ok = ((uint32_t)a.ul + li <= L);
 					x = a.v;
 				}
-				unsigned okm = __ballot_sync(0xffffffffu, ok);
-				unsigned pre = okm == 0xffffffffu ? okm : ((1u << (__ffs(~okm) - 1)) - 1); // lanes before the first failure
+				const unsigned okm = __ballot_sync(0xffffffffu, ok);
+				const unsigned pre = okm == 0xffffffffu ? okm : ((1u << (__ffs(~okm) - 1)) - 1); // lanes before the first failure
 				if (pre >> lane & 1) {
-					uint32_t h = dt_hash(x, DT_HASH - 1);
+					uint32_t h = dt_hash(x, mask);
 					for (;;) {
-						uint32_t p = hs[h];
-						if (p == DT_EMPTY) break;
-						if (tv[p] == x) { st[p] = 2; break; }
-						h = (h + 1) & (DT_HASH - 1);
+						const uint32_t kx = hkey[h];
+						if (kx == x) { hmark[h] = 2; break; }
+						if (kx == DT_EMPTY) break;
+						h = (h + 1) & mask;
 					}
 				}
 				if (lane == 0) n_inner += __popc(pre);
 				if (okm != 0xffffffffu) break;
 			}
 			__syncwarp();
+			++i;
 		}
 		// The reference clears mark[target] right after looking at the first arc to that target
 		// (asg.c:181-184), so of several arcs to one reduced target only the lowest-index one is deleted.
-		uint32_t *fmin = reinterpret_cast<uint32_t*>(ti);
 		if (has_dup) {
-			for (uint32_t i = lane; i < nv; i += 32) fmin[i] = DT_EMPTY;
+			for (uint32_t i = lane; i <= mask; i += 32) fmin[i] = DT_EMPTY;
 			__syncwarp();
-			for (uint32_t i = lane; i < nv; i += 32) atomicMin(&fmin[rep[i]], i);
+			for (uint32_t i = lane; i < nv; i += 32) atomicMin(&fmin[slot[i]], i);
 			__syncwarp();
 		}
 		for (uint32_t i = lane; i < nv; i += 32) {
-			bool r = st[rep[i]] == 2 && (!has_dup || fmin[rep[i]] == i);
+			const bool r = hmark[slot[i]] == 2 && (!has_dup || fmin[slot[i]] == i);
 			flag[off + i] = r;
 			n_red += r;
 		}
@@ -542,7 +559,7 @@ uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz)
 	if (g.n_arc) {
 		flag = mab_alloc<uint8_t>(d, g.n_arc);
 		uint32_t *big = mab_alloc<uint32_t>(d, n_vtx);
-		MAB_CUDA(cudaMemsetAsync(flag, 0, g.n_arc, d.stream));
+		// no memset of flag[]: every arc lies in the slab of exactly one vertex, and every vertex with arcs writes its slab's flags
 		MAB_CUDA(cudaMemsetAsync(d.d_scal, 0, 8 * sizeof(unsigned long long), d.stream));
 		cudaEvent_t e0, e1;
 		MAB_CUDA(cudaEventCreate(&e0)); MAB_CUDA(cudaEventCreate(&e1));

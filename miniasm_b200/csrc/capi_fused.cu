@@ -66,6 +66,12 @@ __global__ void k_name_pack(uint32_t n, const uint32_t *orig, const uint64_t *no
 	}
 }
 
+struct PhaseTimer { // CUDA-event stopwatch around one step of the fused API
+	MabDev &d; double *out; cudaEvent_t e0, e1;
+	PhaseTimer(MabDev &dev, double *o) : d(dev), out(o) { MAB_CUDA(cudaEventCreate(&e0)); MAB_CUDA(cudaEventCreate(&e1)); MAB_CUDA(cudaEventRecord(e0, d.stream)); }
+	~PhaseTimer() { float ms = 0; MAB_CUDA(cudaEventRecord(e1, d.stream)); MAB_CUDA(cudaEventSynchronize(e1)); MAB_CUDA(cudaEventElapsedTime(&ms, e0, e1)); *out = ms; MAB_CUDA(cudaEventDestroy(e0)); MAB_CUDA(cudaEventDestroy(e1)); }
+};
+
 static void ctx_drop_graphs(mab_ctx *c)
 {
 	if (c->have_ug) dg_ug_free(c->dev, c->ug), c->have_ug = false;
@@ -189,6 +195,7 @@ int mab_ingest(mab_ctx_t *c, int min_span, int min_match, int bi_dir)
 {
 	MAB_CUDA(cudaSetDevice(c->dev.device));
 	MabDev &d = c->dev;
+	PhaseTimer pt(d, &c->stats.ms_ingest);
 	ctx_reset_reads(c);
 	ingest_paf(d, c->d_text, c->text_len, min_span, min_match, bi_dir, c->hits, c->names, c->ist);
 	c->n_seq = c->names.n_seq;
@@ -245,6 +252,7 @@ int mab_select(mab_ctx_t *c, const ma_opt_t *opt, int no_first, int no_second, i
 	MAB_CUDA(cudaSetDevice(c->dev.device));
 	MabDev &d = c->dev;
 	DHits &h = c->hits;
+	PhaseTimer pt(d, &c->stats.ms_select);
 	ctx_drop_graphs(c);
 	if (!no_first) {
 		if (stage >= 2) {
@@ -286,6 +294,7 @@ int mab_layout(mab_ctx_t *c, const ma_opt_t *opt, int stage)
 {
 	MAB_CUDA(cudaSetDevice(c->dev.device));
 	MabDev &d = c->dev;
+	PhaseTimer pt(d, &c->stats.ms_layout);
 	ctx_drop_graphs(c);
 	uint32_t *len = mab_alloc<uint32_t>(d, c->n_seq);
 	uint8_t *del = mab_alloc<uint8_t>(d, c->n_seq);
@@ -342,6 +351,7 @@ int mab_unitigs(mab_ctx_t *c)
 {
 	MAB_CUDA(cudaSetDevice(c->dev.device));
 	if (!c->have_sg) return -1;
+	PhaseTimer pt(c->dev, &c->stats.ms_unitigs);
 	if (c->have_ug) dg_ug_free(c->dev, c->ug), c->have_ug = false;
 	dg_ug_gen(c->dev, c->sg, c->ug);
 	c->have_ug = true;
