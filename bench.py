@@ -319,7 +319,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_del_trans_warp",
                          "algorithmic_bytes": alg_bytes, "formula": "16*n_arc + 16*inner_iters + 1*n_arc + 12*n_vtx"},
-            "cpu_baseline": cpu, "clocks": clocks, "wall_s_timed_region": wall_dev,
+            "cpu_baseline": cpu, "clocks": clocks, "wall_s_timed_region": wall_dev, "wall_ms_per_step": wall_dev / a.steps * 1e3,
         }))
     lib.mab_event_destroy(e0), lib.mab_event_destroy(e1)
     lib.mab_destroy(ctx)

@@ -66,10 +66,14 @@ __global__ void k_name_pack(uint32_t n, const uint32_t *orig, const uint64_t *no
 	}
 }
 
-struct PhaseTimer { // CUDA-event stopwatch around one step of the fused API
-	MabDev &d; double *out; cudaEvent_t e0, e1;
-	PhaseTimer(MabDev &dev, double *o) : d(dev), out(o) { MAB_CUDA(cudaEventCreate(&e0)); MAB_CUDA(cudaEventCreate(&e1)); MAB_CUDA(cudaEventRecord(e0, d.stream)); }
-	~PhaseTimer() { float ms = 0; MAB_CUDA(cudaEventRecord(e1, d.stream)); MAB_CUDA(cudaEventSynchronize(e1)); MAB_CUDA(cudaEventElapsedTime(&ms, e0, e1)); *out = ms; MAB_CUDA(cudaEventDestroy(e0)); MAB_CUDA(cudaEventDestroy(e1)); }
+struct PhaseTimer { // CUDA-event stopwatch around one step of the fused API (+ host wall clock when MAB_TRACE is set)
+	MabDev &d; double *out; cudaEvent_t e0, e1; double w0; const char *name;
+	PhaseTimer(MabDev &dev, double *o, const char *nm) : d(dev), out(o), name(nm) { w0 = sys_realtime(); MAB_CUDA(cudaEventCreate(&e0)); MAB_CUDA(cudaEventCreate(&e1)); MAB_CUDA(cudaEventRecord(e0, d.stream)); }
+	~PhaseTimer() {
+		float ms = 0; MAB_CUDA(cudaEventRecord(e1, d.stream)); MAB_CUDA(cudaEventSynchronize(e1)); MAB_CUDA(cudaEventElapsedTime(&ms, e0, e1)); *out = ms;
+		MAB_CUDA(cudaEventDestroy(e0)); MAB_CUDA(cudaEventDestroy(e1));
+		if (getenv("MAB_TRACE")) fprintf(stderr, "[T::%s] device %.3f ms, host wall %.3f ms\n", name, ms, (sys_realtime() - w0) * 1e3);
+	}
 };
 
 static void ctx_drop_graphs(mab_ctx *c)
@@ -195,7 +199,7 @@ int mab_ingest(mab_ctx_t *c, int min_span, int min_match, int bi_dir)
 {
 	MAB_CUDA(cudaSetDevice(c->dev.device));
 	MabDev &d = c->dev;
-	PhaseTimer pt(d, &c->stats.ms_ingest);
+	PhaseTimer pt(d, &c->stats.ms_ingest, "mab_ingest");
 	ctx_reset_reads(c);
 	ingest_paf(d, c->d_text, c->text_len, min_span, min_match, bi_dir, c->hits, c->names, c->ist);
 	c->n_seq = c->names.n_seq;
@@ -252,22 +256,28 @@ int mab_select(mab_ctx_t *c, const ma_opt_t *opt, int no_first, int no_second, i
 	MAB_CUDA(cudaSetDevice(c->dev.device));
 	MabDev &d = c->dev;
 	DHits &h = c->hits;
-	PhaseTimer pt(d, &c->stats.ms_select);
+	PhaseTimer pt(d, &c->stats.ms_select, "mab_select");
 	ctx_drop_graphs(c);
 	if (!no_first) {
 		if (stage >= 2) {
 			d.free(c->sub);
 			c->sub = mab_alloc<DSub>(d, c->n_seq);
+			d.trace("select:begin");
 			dh_sub(d, h, opt->min_dp, opt->min_iden, 0, c->sub);
+			d.trace("select:sub1");
 			dh_cut(d, h, c->sub, opt->min_span);
+			d.trace("select:cut1");
 		}
 		if (stage >= 3 && c->sub) dh_flt(d, h, c->sub, (int)(opt->max_hang * 1.5), (int)(opt->min_ovlp * .5), &c->cov);
 	}
 	if (!no_second) {
 		if (stage >= 4) {
 			DSub *sub2 = mab_alloc<DSub>(d, c->n_seq);
+			d.trace("select:flt");
 			dh_sub(d, h, opt->min_dp, opt->min_iden, opt->min_span / 2, sub2);
+			d.trace("select:sub2");
 			dh_cut(d, h, sub2, opt->min_span);
+			d.trace("select:cut2");
 			if (!no_first && c->sub) { dh_sub_merge(d, c->n_seq, c->sub, sub2); d.free(sub2); }
 			else { d.free(c->sub); c->sub = sub2; }
 		}
@@ -282,6 +292,7 @@ int mab_select(mab_ctx_t *c, const ma_opt_t *opt, int no_first, int no_second, i
 			c->orig_id = orig_new;
 			c->n_seq = h.n_seq;
 			d.free(map);
+			d.trace("select:contained");
 		}
 	}
 	c->stats.n_hits_final = h.n, c->stats.n_seq_final = c->n_seq;
@@ -294,14 +305,16 @@ int mab_layout(mab_ctx_t *c, const ma_opt_t *opt, int stage)
 {
 	MAB_CUDA(cudaSetDevice(c->dev.device));
 	MabDev &d = c->dev;
-	PhaseTimer pt(d, &c->stats.ms_layout);
+	PhaseTimer pt(d, &c->stats.ms_layout, "mab_layout");
 	ctx_drop_graphs(c);
 	uint32_t *len = mab_alloc<uint32_t>(d, c->n_seq);
 	uint8_t *del = mab_alloc<uint8_t>(d, c->n_seq);
 	if (c->n_seq) MAB_LAUNCH(d, k_sg_len, mab_grid(c->n_seq, 256), 256, 0, c->n_seq, c->sub, c->names.slen, c->orig_id, len, del);
 	HitArcParams p = { opt->max_hang, opt->int_frac, opt->min_ovlp };
 	c->hits.n_seq = c->n_seq;
+	d.trace("layout:begin");
 	dh_sg_gen(d, c->hits, len, del, p, c->sg);
+	d.trace("layout:sg_gen");
 	c->have_sg = true;
 	d.free(len); d.free(del);
 	DGraph &g = c->sg;
@@ -311,6 +324,7 @@ int mab_layout(mab_ctx_t *c, const ma_opt_t *opt, int stage)
 		dg_del_trans(d, g, (uint32_t)opt->gap_fuzz);
 		c->stats.n_arc_trans_in = g_del_trans_stats.n_arc_in, c->stats.n_reduced = g_del_trans_stats.n_reduced;
 		c->stats.trans_inner = g_del_trans_stats.inner_iters, c->stats.ms_del_trans_kernel = g_del_trans_stats.kernel_ms;
+		d.trace("layout:del_trans+cleanup+symm");
 	}
 	if (stage >= 7) {
 		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.2: initial tip cutting and bubble popping <===\n");
@@ -343,6 +357,7 @@ int mab_layout(mab_ctx_t *c, const ma_opt_t *opt, int stage)
 	}
 	c->stats.n_arc_final = g.n_arc;
 	d.sync();
+	d.trace("layout:cleaning passes");
 	return 0;
 }
 
@@ -351,7 +366,7 @@ int mab_unitigs(mab_ctx_t *c)
 {
 	MAB_CUDA(cudaSetDevice(c->dev.device));
 	if (!c->have_sg) return -1;
-	PhaseTimer pt(c->dev, &c->stats.ms_unitigs);
+	PhaseTimer pt(c->dev, &c->stats.ms_unitigs, "mab_unitigs");
 	if (c->have_ug) dg_ug_free(c->dev, c->ug), c->have_ug = false;
 	dg_ug_gen(c->dev, c->sg, c->ug);
 	c->have_ug = true;

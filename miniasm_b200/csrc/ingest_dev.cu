@@ -269,6 +269,7 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 	h.n = 0, h.n_seq = 0;
 	if (len == 0) { dh_reserve(d, h, 1); return; }
 
+	d.trace("ingest:begin");
 	// (1) line starts
 	uint64_t *start = nullptr;
 	uint64_t n_lines;
@@ -292,6 +293,7 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 		++d.n_lib;
 	}
 	st.n_lines = n_lines;
+	d.trace("ingest:line_starts");
 
 	// (2) parse
 	PLine *ln = mab_alloc<PLine>(d, n_lines);
@@ -306,6 +308,7 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 		MAB_LAUNCH(d, k_fix_filter, mab_grid(n_lines, 256), 256, 0, ln, n_lines, min_span, min_match, d.d_scal + SC_AUX);
 		st.n_parsed = d.get_scal(SC_COUNT);
 		n_pass = d.h_scal[SC_AUX];
+		d.trace("ingest:parse+filter");
 		if (d.h_scal[SC_COUNT + 1]) { fprintf(stderr, "[E::miniasm_b200] a read name in the PAF is longer than 65535 bytes\n"); exit(78); }
 		// (3) dictionary: grow the table until every name finds a slot, re-seed the hash on a verified collision
 		if (cap == 0) { cap = 1ull << 20; while (cap < n_pass / 4) cap <<= 1; }
@@ -331,6 +334,7 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 		if (attempt > 16) { fprintf(stderr, "[E::miniasm_b200] read-name hashing keeps colliding\n"); exit(77); }
 	}
 
+	d.trace("ingest:dictionary");
 	// (4) ids = rank of the first occurrence
 	uint64_t *slots = mab_alloc<uint64_t>(d, cap);
 	uint32_t n_seq;
@@ -368,6 +372,7 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 	}
 	d.free(slots);
 
+	d.trace("ingest:rank_ids");
 	// (5) hits at scanned offsets (file order, mirrored hit right after its original)
 	cnt = mab_alloc<uint32_t>(d, n_lines);
 	off = mab_alloc<uint64_t>(d, n_lines + 1);
@@ -394,6 +399,8 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 	d.free(cnt); d.free(off); d.free(ln); d.free(start);
 	d.free(tab.key); d.free(tab.first); d.free(tab.id);
 
+	d.trace("ingest:emit_hits");
 	// (6) ma_hit_sort
 	dh_sort(d, h, st.max_qs_bits);
+	d.trace("ingest:sort_hits");
 }

@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <vector>
 
 #define MAB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
 	fprintf(stderr, "[E::miniasm_b200] %s failed at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); \
@@ -45,8 +47,25 @@ static_assert(sizeof(DArc) == 16, "asg_arc_t layout");
 // Per-GPU runtime: one stream, a stream-ordered allocator, a scratch area for CUB and a pinned
 // mailbox for the few scalars (element counts) the host must see between passes.
 // ---------------------------------------------------------------------------------------------
+// Device memory arena: a few large cudaMalloc'd segments carved by a host-side first-fit free list with
+// coalescing.  All work of a context runs on ONE stream, so a block can be handed out again as soon as it is
+// freed on the host: any kernel that still uses it was launched earlier on the same stream.  After the first
+// pass over a workload no driver allocation happens any more (cudaMallocAsync showed 100s of ms of jitter on
+// multi-GB requests, see DESIGN.md "memory").
+struct MabArena {
+	struct Seg { char *base; size_t size; };
+	std::vector<Seg> segs;
+	std::map<char*, size_t> free_blk;    // start -> size, coalesced
+	std::map<char*, size_t> live;        // start -> size
+	size_t reserved = 0, in_use = 0, peak = 0;
+	void *alloc(size_t bytes);
+	void free(void *p);
+	void release_all();
+};
+
 struct MabDev {
 	int device = 0;
+	MabArena arena;
 	cudaStream_t stream = nullptr;
 	void *cub_tmp = nullptr;
 	size_t cub_tmp_bytes = 0;
@@ -65,6 +84,9 @@ struct MabDev {
 	void zero_scal(int i, int n = 1);
 	unsigned long long get_scal(int i);     // synchronises the stream
 	void sync();
+	void trace(const char *label);          // MAB_TRACE=1: synchronise and print the wall time since the previous trace point
+	int trace_on = -1;
+	double trace_t = 0;
 };
 
 template <typename T> static inline T *mab_alloc(MabDev &d, size_t n) { return (T*)d.alloc((n ? n : 1) * sizeof(T)); }
