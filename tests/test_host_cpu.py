@@ -1,0 +1,106 @@
+"""CPU tier: the host C side of the product (sdict.c, paf.c, gfa.c) -- no GPU involved."""
+import ctypes as C
+import gzip
+import os
+
+import pytest
+
+from miniasm_b200 import capi, synth
+from miniasm_b200.pipeline import Pipeline
+
+
+class PafRec(C.Structure):                                   # paf_rec_t, paf.h:20-24
+    _fields_ = [("qn", C.c_char_p), ("tn", C.c_char_p), ("ql", C.c_uint32), ("qs", C.c_uint32), ("qe", C.c_uint32),
+                ("tl", C.c_uint32), ("ts", C.c_uint32), ("te", C.c_uint32), ("ml_rev", C.c_uint32), ("bl", C.c_uint32)]
+
+
+def paf_records(lib, path):
+    lib.dll.paf_open.restype = C.c_void_p
+    lib.dll.paf_open.argtypes = [C.c_char_p]
+    lib.dll.paf_read.argtypes = [C.c_void_p, C.POINTER(PafRec)]
+    lib.dll.paf_close.argtypes = [C.c_void_p]
+    fp = lib.dll.paf_open(path.encode())
+    assert fp
+    r, out = PafRec(), []
+    while lib.dll.paf_read(fp, C.byref(r)) >= 0:
+        out.append((r.qn, r.ql, r.qs, r.qe, r.ml_rev >> 31, r.tn, r.tl, r.ts, r.te, r.ml_rev & 0x7fffffff, r.bl))
+    lib.dll.paf_close(fp)
+    return out
+
+
+WEIRD = (b"q1\t1000\t10\t900\t+\tt1\t2000\t5\t800\t700\t890\t255\n"
+         b"q2\t1000\t+10\t 900\t-\tt1\t2000\t5\t800\t700abc\t890\t255\ttp:A:S\r\n"
+         b"\n"
+         b"short\tline\n"
+         b"q3\t1000\t0\t1000\t-\tt2\t3000\t0\t1000\t999\n"                 # 10 fields: bl stays 890
+         b"q4\t99999999999999999999\t-5\t77\t*\tt3\t1\t2\t3\t4\t5\t6\t7\t8\n"
+         b"q5\t1\t2\t3\t-\tt5\t6\t7\t8\t9\t10")                            # no trailing newline
+
+
+def test_paf_reader_corner_cases(built, tmp_path):
+    prod = capi.load_product()
+    p = tmp_path / "weird.paf"
+    p.write_bytes(WEIRD)
+    got = paf_records(prod, str(p))
+    assert got == [
+        (b"q1", 1000, 10, 900, 0, b"t1", 2000, 5, 800, 700, 890),
+        (b"q2", 1000, 10, 900, 1, b"t1", 2000, 5, 800, 700, 890),
+        (b"q3", 1000, 0, 1000, 1, b"t2", 3000, 0, 1000, 999, 890),
+        (b"q4", 0xffffffff, 0xfffffffb, 77, 0, b"t3", 1, 2, 3, 4, 5),
+        (b"q5", 1, 2, 3, 1, b"t5", 6, 7, 8, 9, 10),
+    ]
+    if os.path.exists(capi.REFERENCE_SO):
+        assert paf_records(capi.load_reference(), str(p)) == got
+    gz = tmp_path / "weird.paf.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(WEIRD)
+    assert paf_records(prod, str(gz)) == got
+
+
+def test_sdict(built):
+    prod = capi.load_product()
+    d = prod.sd_init()
+    names = [f"read/{i}".encode() for i in range(5000)]
+    for i, n in enumerate(names):
+        assert prod.sd_put(d, n, 100 + i) == i
+    assert prod.sd_put(d, names[17], 1) == 17 and d.contents.seq[17].len == 117      # first length wins
+    assert prod.sd_get(d, b"nope") == -1 and prod.sd_get(d, names[4999]) == 4999
+    for i in range(0, 5000, 3):
+        d.contents.seq[i].aux_del |= 0x80000000
+    m = capi.np_from_ptr(prod.sd_squeeze(d), 5000, "<i4")
+    assert d.contents.n_seq == 5000 - len(range(0, 5000, 3))
+    assert m[0] == -1 and m[1] == 0 and m[2] == 1 and m[4] == 2
+    assert prod.sd_get(d, names[3]) == -1 and prod.sd_get(d, names[4]) == 2
+    prod.sd_destroy(d)
+
+
+@pytest.mark.skipif(not os.path.exists(capi.REFERENCE_SO), reason="oracle/_ref not built")
+def test_writers_and_ug_seq_against_reference(built, ref, paf_dir):
+    from tests.test_clean_gpu import _write_reads
+    prod = capi.load_product()
+    paf = synth.generate("chaos_small", f"{paf_dir}/hc.paf")
+    for fmt in ("fa", "fq.gz"):
+        reads = _write_reads(paf, os.path.join(paf_dir, f"hc_reads.{fmt}"), gz=fmt.endswith("gz"), fastq=fmt.startswith("fq"))
+        a = Pipeline(ref, paf).read().select().sg_gen().clean().ug_gen()
+        want = a.gfa(reads)
+        b = Pipeline(ref, paf).read().select().sg_gen().clean().ug_gen()
+        d2 = prod.sd_init()                                                           # sdict_t::h is private to each library: rebuild the dictionary on our side
+        for i, nm in enumerate(b.names()):
+            assert prod.sd_put(d2, nm, b.d.contents.seq[i].len) == i
+        prod.ma_ug_seq(b.ug, d2, b.sub, reads.encode())                               # our ma_ug_seq fills the reference's unitig structs
+        assert prod.print_to_string("ma_ug_print", b.ug, d2, b.sub) == want
+        prod.sd_destroy(d2)
+        assert prod.print_to_string("ma_sg_print", b.sg, b.d, b.sub) == a.sg_text()
+        assert prod.print_to_string("ma_sg_print", b.sg, b.d, None) == ref.print_to_string("ma_sg_print", a.sg, a.d, None)
+        a.free(), b.free()
+
+
+@pytest.mark.skipif(not os.path.exists(capi.REFERENCE_SO), reason="oracle/_ref not built")
+def test_no_cont_prefilter_against_reference(built, ref, paf_dir):
+    prod = capi.load_product()
+    paf = synth.generate("-n 4000 -l 2000 -L 30000 -c 30 -j 100 -s 41", f"{paf_dir}/nocont.paf")
+    a = ref.ma_hit_no_cont(paf.encode(), 2000, 100, 1000, 0.8)
+    b = prod.ma_hit_no_cont(paf.encode(), 2000, 100, 1000, 0.8)
+    na = [a.contents.seq[i].name for i in range(a.contents.n_seq)]
+    nb = [b.contents.seq[i].name for i in range(b.contents.n_seq)]
+    assert na == nb and len(na) > 10

@@ -1,0 +1,65 @@
+"""CPU tier: the oracle port step by step against the unmodified reference (oracle/_ref/libminiasm_ref.so) --
+this is what pins the restatement, since the reference has no tests of its own."""
+import os
+
+import numpy as np
+import pytest
+
+from miniasm_b200 import capi, synth
+from miniasm_b200.pipeline import Pipeline, canon_arcs
+
+pytestmark = pytest.mark.skipif(not os.path.exists(capi.REFERENCE_SO), reason="oracle/_ref not built (needs /root/reference)")
+SETS = ["tiny_exact", "chaos_small", "chaos", "bubbles800", "shuffled", "lowcov", "varlen300", "skew_small", "c1_ecoli_like"]
+
+
+@pytest.fixture(scope="module")
+def port(built):
+    return capi.load_oracle_port()
+
+
+def mask(h):
+    h = h.copy()
+    h["bl_del"] &= 0x7fffffff
+    return h
+
+
+@pytest.mark.parametrize("name", SETS)
+def test_port_matches_reference_stepwise(name, ref, port, paf_dir):
+    paf = synth.generate(name, f"{paf_dir}/{name}.paf")
+    r, p = Pipeline(ref, paf).read(), Pipeline(port, paf).read()
+    assert r.names() == p.names()
+    assert np.array_equal(np.sort(mask(r.hits_np()), order=list(capi.HIT_DT.names)), np.sort(mask(p.hits_np()), order=list(capi.HIT_DT.names)))
+    p.free()
+    p = Pipeline(port, paf, opt=r.opt).adopt(r)      # continue from the reference's own (tie-ordered) hit array
+    for step in ("sub1", "cut", "flt", "sub2_cut_merge", "contained"):
+        getattr(r, step)(), getattr(p, step)()
+        assert r.n_hits == p.n_hits and np.array_equal(mask(r.hits_np()), mask(p.hits_np())), step
+        assert np.array_equal(r.sub_np(), p.sub_np()), step
+    assert r.names() == p.names()
+    r.sg_gen(), p.sg_gen()
+    (ar, sr, ir, _, _), (ap, sp, ip, _, _) = r.graph_np(), p.graph_np()
+    assert np.array_equal(canon_arcs(ar), canon_arcs(ap)) and np.array_equal(sr, sp) and np.array_equal(ir, ip)
+    o = r.opt
+    for fn, args in [("asg_arc_del_trans", (o.gap_fuzz,)), ("asg_cut_tip", (o.max_ext,)), ("asg_pop_bubble", (o.bub_dist,)),
+                     ("asg_arc_del_short", (0.5,)), ("asg_cut_tip", (o.max_ext,)), ("asg_pop_bubble", (o.bub_dist,)),
+                     ("asg_arc_del_short", (0.7,)), ("asg_cut_internal", (1,)), ("asg_cut_biloop", (o.max_ext,)),
+                     ("asg_cut_tip", (o.max_ext,)), ("asg_pop_bubble", (o.bub_dist,)), ("asg_arc_del_short", (0.8,))]:
+        g2 = port.clone_graph(r.sg)                  # same pre-state for both
+        a = getattr(ref, fn)(r.sg, *args)
+        b = getattr(port, fn)(g2, *args)
+        assert a == b, fn
+        x, y = ref.read_graph(r.sg), port.read_graph(g2)
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[3:] == y[3:], fn
+        port.asg_destroy(g2)
+    ur, up = ref.ma_ug_gen(r.sg), port.ma_ug_gen(r.sg)
+    assert ref.print_to_string("ma_ug_print", ur, r.d, r.sub) == ref.print_to_string("ma_ug_print", up, r.d, r.sub)
+    ref.ma_ug_destroy(ur), port.ma_ug_destroy(up)
+    r.free(), p.free()
+
+
+def test_tie_order_audit(ref, port, paf_dir):
+    """the reference's radix sort is unstable, ours (port and CUDA) are stable.  On data with
+    thousands of tied sort keys the final GFA must not depend on it."""
+    for name in ("jitter30", "chaos"):
+        paf = synth.generate(name, f"{paf_dir}/{name}.paf")
+        assert Pipeline(ref, paf).run_all() == Pipeline(port, paf).run_all()
