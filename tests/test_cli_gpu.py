@@ -129,3 +129,20 @@ def test_weird_lines(paf_dir):
         fo.write(b"\n".join(out))                             # no newline at the end
     same([path])
     same(["-S", "2", "-p", "paf", path], exact=False)
+
+
+SEAM = os.path.join(ROOT, "oracle", "_ref", "miniasm_seam")
+
+
+@pytest.mark.skipif(not os.path.exists(SEAM), reason="oracle/_ref/miniasm_seam not built")
+@pytest.mark.parametrize("opts", [[], ["-p", "sg"], ["-R"], ["-c", "2", "-e", "2"]])
+def test_link_seam(opts, pafs):
+    """The reference's own main.o (compiled from its main.c, untouched) linked against libminiasm_b200.so:
+    every library call of main.c:108-199 lands in the CUDA path, the GFA must be the reference's."""
+    rc_r, out_r, _ = run(REF, opts + [pafs["chaos_small"]])
+    rc_s, out_s, err = run(SEAM, opts + [pafs["chaos_small"]])
+    assert rc_s == rc_r == 0, err.decode()[-2000:]
+    if "sg" in opts:
+        assert sorted(out_s.splitlines()) == sorted(out_r.splitlines())
+    else:
+        assert out_s == out_r
