@@ -162,6 +162,7 @@ _PRODUCT_ONLY = {
     "mab_event_destroy": (None, [C.c_void_p]),
     "mab_sync": (None, [C.c_void_p]),
     "mab_last_clean": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "mab_count_del_trans_inner": (None, [C.c_int]),
     "mab_set_verbose": (None, [C.c_int]),
     "mab_last_del_trans": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),

@@ -15,6 +15,7 @@
 #include <cub/cub.cuh>
 
 int mab_verbose = 3;
+int mab_del_trans_count_inner = 0;
 DelTransStats g_del_trans_stats;
 
 // ---------------------------------------------------------------------------------------------
@@ -33,6 +34,15 @@ __device__ __forceinline__ DArc ld_arc_nc(const DArc *p)
 	DArc a;
 	a.ul = (uint64_t)t.y << 32 | t.x; a.v = t.z; a.ol_del = t.w;
 	return a;
+}
+
+// one LDG.128 through the read-only path, kept as a single instruction even when only some words are used
+// (two 32-bit loads of a 16-byte record cost twice the L1 wavefronts: ncu on k_del_trans_warp v2)
+__device__ __forceinline__ uint4 ld_arc4(const DArc *p)
+{
+	uint4 t;
+	asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+	return t;
 }
 
 static inline uint32_t bits_for(uint64_t x) { uint32_t b = 0; while (x) ++b, x >>= 1; return b ? b : 1; }
@@ -278,12 +288,13 @@ __device__ __forceinline__ uint32_t dt_hash(uint32_t x, uint32_t mask) { return 
 // DT_EAGER targets; reused as "lowest slab position per slot" when a slab holds multi-arcs) | hmark (mark per slot:
 // 1 = target of v, 2 = reduced) | slot (table slot of slab entry i).  The mark lives in the table, so arcs to the same
 // target share it exactly like mark[] indexed by vertex does in the reference.
+template <bool STATS>
 __global__ void __launch_bounds__(DT_WARPS * 32)
 k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, const uint32_t *__restrict__ seq,
                  uint32_t n_vtx, uint32_t fuzz, uint8_t *__restrict__ flag,
                  uint32_t *__restrict__ big_list, unsigned long long *scal)
 {
-	__shared__ uint32_t s_hkey[DT_WARPS][DT_HASH];
+	__shared__ __align__(16) uint32_t s_hkey[DT_WARPS][DT_HASH];
 	__shared__ uint32_t s_tl[DT_WARPS][DT_MAXD];
 	__shared__ uint32_t s_fmin[DT_WARPS][DT_HASH];
 	__shared__ uint64_t s_ti[DT_WARPS][DT_EAGER];
@@ -310,21 +321,22 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 			if (lane == 0) big_list[atomicAdd(scal + SC_BIG, 1ull)] = v;
 			continue;
 		}
-		uint32_t mask = 31;
-		while (mask + 1 < 2 * nv) mask = mask * 2 + 1;
-		for (uint32_t i = lane; i <= mask; i += 32) hkey[i] = DT_EMPTY;
+		const uint32_t mask = nv <= 16 ? 31u : (0xffffffffu >> __clz(2 * nv - 1)); // table = next power of two >= 2*nv, at least 32 slots
+		if (mask == 31) hkey[lane] = DT_EMPTY;
+		else for (uint32_t i = lane * 4; i <= mask; i += 128) *reinterpret_cast<uint4*>(hkey + i) = make_uint4(DT_EMPTY, DT_EMPTY, DT_EMPTY, DT_EMPTY);
 		__syncwarp();
 		// stage the slab and build the target table in one sweep
 		bool dup = false;
-		for (uint32_t i = lane; i < nv; i += 32) {
-			const DArc a = ld_arc_nc(arc + off + i);
-			tl[i] = (uint32_t)a.ul;
-			if (i < DT_EAGER) ti[i] = __ldg(idx + a.v);
-			uint32_t h = dt_hash(a.v, mask);
+		const DArc *pv = arc + off + lane;
+		for (uint32_t i = lane; i < nv; i += 32, pv += 32) {
+			const uint4 a = ld_arc4(pv);       // x = len, z = target
+			tl[i] = a.x;
+			if (i < DT_EAGER) ti[i] = __ldg(idx + a.z);
+			uint32_t h = dt_hash(a.z, mask);
 			for (;;) {
-				const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a.v);
+				const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a.z);
 				if (prev == DT_EMPTY) { hmark[h] = 1; break; }
-				if (prev == a.v) { dup = true; break; }
+				if (prev == a.z) { dup = true; break; }
 				h = (h + 1) & mask;
 			}
 			slot[i] = (uint8_t)h;
@@ -346,15 +358,14 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 			const uint32_t w = hkey[slot[i]], li = tl[i];
 			const uint64_t iw = i < DT_EAGER ? ti[i] : __ldg(idx + w);
 			const uint32_t nw = (uint32_t)iw;
-			const DArc *aw = arc + (iw >> 32);
-			for (uint32_t j0 = 0; j0 < nw; j0 += 32) {
-				const uint32_t j = j0 + lane;
+			const DArc *pw = arc + (iw >> 32) + lane;
+			for (uint32_t j0 = 0; j0 < nw; j0 += 32, pw += 32) {
 				uint32_t x = 0;
 				bool ok = false;
-				if (j < nw) {
-					const DArc a = ld_arc_nc(aw + j);
-					ok = ((uint32_t)a.ul + li <= L);
-					x = a.v;
+				if (j0 + lane < nw) {
+					const uint4 a = ld_arc4(pw);
+					ok = (a.x + li <= L);
+					x = a.z;
 				}
 				const unsigned okm = __ballot_sync(0xffffffffu, ok);
 				const unsigned pre = okm == 0xffffffffu ? okm : ((1u << (__ffs(~okm) - 1)) - 1); // lanes before the first failure
@@ -367,7 +378,7 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 						h = (h + 1) & mask;
 					}
 				}
-				if (lane == 0) n_inner += __popc(pre);
+				if (STATS && lane == 0) n_inner += __popc(pre);
 				if (okm != 0xffffffffu) break;
 			}
 			__syncwarp();
@@ -566,7 +577,9 @@ uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz)
 		MAB_CUDA(cudaEventRecord(e0, d.stream));
 		unsigned grid = (n_vtx + DT_WARPS - 1) / DT_WARPS;
 		if (grid > 148u * 64u) grid = 148u * 64u;
-		MAB_LAUNCH(d, k_del_trans_warp, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal);
+		// the inner-iteration counter (for the roofline arithmetic) costs issue slots: only counted when asked for
+		if (mab_del_trans_count_inner) MAB_LAUNCH(d, k_del_trans_warp<true>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal);
+		else MAB_LAUNCH(d, k_del_trans_warp<false>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal);
 		MAB_CUDA(cudaEventRecord(e1, d.stream));
 		uint32_t n_big = (uint32_t)d.get_scal(SC_BIG);
 		float ms = 0;

@@ -34,4 +34,5 @@ uint32_t dg_del_short(MabDev &d, DGraph &g, float ratio);    // asg.c:83-101
 struct DelTransStats { uint64_t n_arc_in, n_vtx, inner_iters, n_reduced, n_big; float kernel_ms; };
 extern DelTransStats g_del_trans_stats;
 
+extern int mab_del_trans_count_inner; // 1: asg_arc_del_trans also counts its inner-loop iterations (slower kernel variant)
 extern int mab_verbose;   // mirrors ma_verbose (common.c:3): >=3 prints the reference's [M::...] lines

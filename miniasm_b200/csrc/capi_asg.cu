@@ -91,6 +91,7 @@ int asg_arc_del_trans(asg_t *g, int fuzz) { int r; WITH_GRAPH(g, r = (int)dg_del
 int asg_arc_del_short(asg_t *g, float drop_ratio) { int r; WITH_GRAPH(g, r = (int)dg_del_short(d, dg, drop_ratio)); return r; }
 
 void mab_set_verbose(int level) { mab_verbose = level; ma_verbose = level; }
+void mab_count_del_trans_inner(int on) { mab_del_trans_count_inner = on; }
 
 /* last asg_arc_del_trans kernel statistics, for tests and bench (drop-in level has no context object) */
 void mab_last_del_trans(uint64_t *n_arc_in, uint64_t *inner, uint64_t *n_reduced, uint64_t *n_big, double *kernel_ms)

@@ -13,6 +13,7 @@
 #include <sys/stat.h>
 
 ma_ug_t *mab_ug_download(MabDev &d, DUnitigs &du); // capi_clean.cu
+extern "C" sdict_t *sd_from_packed(char *block, size_t block_size, uint32_t n, const uint32_t *len); // host/sdict.c
 
 struct mab_ctx {
 	MabDev dev;
@@ -265,10 +266,10 @@ int mab_select(mab_ctx_t *c, const ma_opt_t *opt, int no_first, int no_second, i
 			d.trace("select:begin");
 			dh_sub(d, h, opt->min_dp, opt->min_iden, 0, c->sub);
 			d.trace("select:sub1");
-			dh_cut(d, h, c->sub, opt->min_span);
-			d.trace("select:cut1");
+			if (stage >= 3) dh_cut_flt(d, h, c->sub, opt->min_span, (int)(opt->max_hang * 1.5), (int)(opt->min_ovlp * .5), &c->cov);
+			else dh_cut(d, h, c->sub, opt->min_span);
+			d.trace("select:cut1(+flt)");
 		}
-		if (stage >= 3 && c->sub) dh_flt(d, h, c->sub, (int)(opt->max_hang * 1.5), (int)(opt->min_ovlp * .5), &c->cov);
 	}
 	if (!no_second) {
 		if (stage >= 4) {
@@ -276,11 +277,27 @@ int mab_select(mab_ctx_t *c, const ma_opt_t *opt, int no_first, int no_second, i
 			d.trace("select:flt");
 			dh_sub(d, h, opt->min_dp, opt->min_iden, opt->min_span / 2, sub2);
 			d.trace("select:sub2");
-			dh_cut(d, h, sub2, opt->min_span);
-			d.trace("select:cut2");
+			DSub *cut2 = nullptr; // round-2 table kept aside when its ma_hit_cut is fused into the containment pass
+			if (stage >= 5) {
+				cut2 = mab_alloc<DSub>(d, c->n_seq);
+				if (c->n_seq) MAB_CUDA(cudaMemcpyAsync(cut2, sub2, (size_t)c->n_seq * sizeof(DSub), cudaMemcpyDeviceToDevice, d.stream));
+			} else dh_cut(d, h, sub2, opt->min_span);
 			if (!no_first && c->sub) { dh_sub_merge(d, c->n_seq, c->sub, sub2); d.free(sub2); }
 			else { d.free(c->sub); c->sub = sub2; }
-		}
+			if (cut2) {
+				const uint32_t n_old = c->n_seq;
+				int32_t *map = mab_alloc<int32_t>(d, n_old);
+				HitArcParams p = { opt->max_hang, opt->int_frac, opt->min_ovlp };
+				dh_contained(d, h, c->sub, nullptr, p, map, cut2, opt->min_span);
+				uint32_t *orig_new = mab_alloc<uint32_t>(d, h.n_seq);
+				if (n_old) MAB_LAUNCH(d, k_orig_from_map, mab_grid(n_old, 256), 256, 0, n_old, map, c->orig_id, orig_new);
+				d.free(c->orig_id);
+				c->orig_id = orig_new;
+				c->n_seq = h.n_seq;
+				d.free(map); d.free(cut2);
+				d.trace("select:cut2+contained");
+			}
+		} else
 		if (stage >= 5 && c->sub) {
 			const uint32_t n_old = c->n_seq;
 			int32_t *map = mab_alloc<int32_t>(d, n_old);
@@ -403,9 +420,9 @@ sdict_t *mab_export_dict(mab_ctx_t *c)
 	MAB_CUDA(cudaMemcpyAsync(pack, d_pack, bytes, cudaMemcpyDeviceToHost, d.stream));
 	MAB_CUDA(cudaMemcpyAsync(slen, d_slen, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream));
 	d.sync();
-	const char *p = pack;
-	for (uint32_t i = 0; i < n; ++i) { sd_put(dict, p, slen[i]); p += strlen(p) + 1; }
-	free(pack); free(slen);
+	sd_destroy(dict);
+	dict = sd_from_packed(pack, bytes, n, slen); // takes `pack`; the hash index is built only if a name is looked up
+	free(slen);
 	d.free(sz); d.free(d_slen); d.free(pos); d.free(d_pack);
 	d.sync();
 	return dict;

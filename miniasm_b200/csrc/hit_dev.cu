@@ -201,6 +201,162 @@ k_sub_sweep(const uint64_t *key, const uint64_t *grp, uint32_t n_seq, int min_dp
 	if (lane == 0 && remained) atomicAdd(n_remained, (unsigned long long)remained);
 }
 
+// ---- shared-memory variant: one warp (<= SUBW_HITS hits) or one CTA (<= SUBC_HITS hits) per read ------------
+// The endpoints of one read never leave the SM: load the group's hits (two 128-bit loads each), emit the keys into
+// shared memory, bitonic-sort them there, sweep the depth with the same warp scan as k_sub_sweep.  Only reads
+// with more hits than a CTA can hold go through the device-wide sort above.
+constexpr int SUBW_WARPS = 8;
+constexpr int SUBW_HITS = 256;               // per warp: 512 keys = 2 KB
+constexpr int SUBC_HITS = 12288;             // per CTA: 24576 keys = 96 KB of dynamic shared memory
+
+// depth sweep over n sorted keys in shared memory by one warp; returns the interval through *out (lane 0 writes)
+__device__ __forceinline__ bool sub_sweep_smem(const uint32_t *key, uint32_t n, int min_dp, uint32_t clip, DSub *out, int lane)
+{
+	int depth = 0;
+	uint32_t carry_start = 0, best_end = 0;
+	unsigned long long best = 0;
+	for (uint32_t c = 0; c < n; c += 32) {
+		const uint32_t i = c + lane;
+		const bool valid = i < n;
+		const uint32_t k = valid ? key[i] : 0, pos = k >> 1;
+		int delta = valid ? ((k & 1) ? -1 : 1) : 0, dp = delta;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, dp, o); if (lane >= o) dp += t; }
+		dp += depth;
+		const int old = dp - delta;
+		const bool up = valid && old < min_dp && dp >= min_dp;
+		const bool down = valid && old >= min_dp && dp < min_dp;
+		const unsigned upm = __ballot_sync(0xffffffffu, up);
+		const unsigned below = upm & ((1u << lane) - 1);
+		const int src = below ? 31 - __clz(below) : 0;
+		uint32_t st = __shfl_sync(0xffffffffu, pos, src);
+		if (!below) st = carry_start;
+		unsigned long long cand = 0;
+		if (down) cand = (unsigned long long)(pos - st) << 32 | (0xffffffffu - i);
+		unsigned long long m = cand;
+		#pragma unroll
+		for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+		if (m > best && (m >> 32) != 0) {
+			const unsigned who = __ballot_sync(0xffffffffu, down && cand == m);
+			best = m;
+			best_end = __shfl_sync(0xffffffffu, pos, __ffs(who) - 1);
+		}
+		if (upm) carry_start = __shfl_sync(0xffffffffu, pos, 31 - __clz(upm));
+		depth = __shfl_sync(0xffffffffu, dp, 31);
+	}
+	const uint32_t len = (uint32_t)(best >> 32);
+	if (lane == 0) {
+		DSub s;
+		if (len > 0) s.s_del = ((best_end - len) - clip) & 0x7fffffffu, s.e = best_end + clip;
+		else s.s_del = MAB_DEL_BIT, s.e = 0;
+		*out = s;
+	}
+	return len > 0;
+}
+
+__device__ __forceinline__ bool sub_hit_keys(const DHit &h, uint32_t qid, float min_iden, uint32_t clip, uint32_t *ks, uint32_t *ke)
+{
+	const int ml = (int)(h.ml_rev & 0x7fffffffu), bl = (int)(h.bl_del & 0x7fffffffu);
+	if (h.tn == qid || (float)ml < __fmul_rn((float)bl, min_iden)) return false;
+	const uint32_t qs = (uint32_t)h.qns + clip, qe = h.qe - clip;
+	if (!(qe > qs)) return false;
+	*ks = qs << 1, *ke = qe << 1 | 1;
+	return true;
+}
+
+__global__ void __launch_bounds__(SUBW_WARPS * 32)
+k_sub_warp(const DHit *__restrict__ a, const uint64_t *__restrict__ grp, uint32_t n_seq, int min_dp, float min_iden, uint32_t clip,
+           DSub *sub, uint32_t *big_list, unsigned long long *scal)
+{
+	__shared__ uint32_t s_key[SUBW_WARPS][2 * SUBW_HITS];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t *key = s_key[warp];
+	unsigned remained = 0;
+	for (uint32_t r = blockIdx.x * SUBW_WARPS + warp; r < n_seq; r += gridDim.x * SUBW_WARPS) {
+		const uint64_t g = grp[r];
+		const uint32_t end = (uint32_t)g, first = (uint32_t)(g >> 32);
+		if (end == 0) continue;
+		const uint32_t cnt = end - first;
+		if (cnt > SUBW_HITS) { if (lane == 0) big_list[atomicAdd(scal + SC_BIG, 1ull)] = r; continue; }
+		uint32_t n = 0; // keys emitted so far (uniform)
+		for (uint32_t c = 0; c < cnt; c += 32) {
+			uint32_t ks = 0, ke = 0;
+			bool ok = false;
+			if (c + lane < cnt) ok = sub_hit_keys(ld_hit(a + first + c + lane), r, min_iden, clip, &ks, &ke);
+			const unsigned m = __ballot_sync(0xffffffffu, ok);
+			if (ok) { const uint32_t p = n + 2 * __popc(m & ((1u << lane) - 1)); key[p] = ks, key[p + 1] = ke; }
+			n += 2 * __popc(m);
+		}
+		uint32_t np = 32; while (np < n) np <<= 1;
+		for (uint32_t i = n + lane; i < np; i += 32) key[i] = 0xffffffffu;
+		__syncwarp();
+		for (uint32_t k = 2; k <= np; k <<= 1)
+			for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+				for (uint32_t t = lane; t < np / 2; t += 32) {
+					const uint32_t lo = (t / j) * 2 * j + (t % j), hi = lo + j;
+					const uint32_t x = key[lo], y = key[hi];
+					const bool asc = (lo & k) == 0;
+					if ((x > y) == asc) key[lo] = y, key[hi] = x;
+				}
+				__syncwarp();
+			}
+		remained += sub_sweep_smem(key, n, min_dp, clip, sub + r, lane);
+		__syncwarp();
+	}
+	if (lane == 0 && remained) atomicAdd(scal + SC_COUNT, (unsigned long long)remained);
+}
+
+__global__ void __launch_bounds__(512)
+k_sub_cta(const DHit *__restrict__ a, const uint64_t *__restrict__ grp, const uint32_t *__restrict__ big_list, uint32_t n_big,
+          int min_dp, float min_iden, uint32_t clip, DSub *sub, uint32_t *huge_list, unsigned long long *scal)
+{
+	extern __shared__ uint32_t c_key[];
+	__shared__ uint32_t s_n;
+	const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+	for (uint32_t b = blockIdx.x; b < n_big; b += gridDim.x) {
+		const uint32_t r = big_list[b];
+		const uint64_t g = grp[r];
+		const uint32_t first = (uint32_t)(g >> 32), cnt = (uint32_t)g - first;
+		if (cnt > SUBC_HITS) { if (tid == 0) huge_list[atomicAdd(scal + SC_AUX2, 1ull)] = r; continue; }
+		if (tid == 0) s_n = 0;
+		__syncthreads();
+		for (uint32_t c = tid; c < cnt; c += nt) {
+			uint32_t ks, ke;
+			if (sub_hit_keys(ld_hit(a + first + c), r, min_iden, clip, &ks, &ke)) { const uint32_t p = atomicAdd(&s_n, 2u); c_key[p] = ks, c_key[p + 1] = ke; }
+		}
+		__syncthreads();
+		const uint32_t n = s_n;
+		uint32_t np = 32; while (np < n) np <<= 1;
+		for (uint32_t i = n + tid; i < np; i += nt) c_key[i] = 0xffffffffu;
+		__syncthreads();
+		for (uint32_t k = 2; k <= np; k <<= 1)
+			for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+				for (uint32_t t = tid; t < np / 2; t += nt) {
+					const uint32_t lo = (t / j) * 2 * j + (t % j), hi = lo + j;
+					const uint32_t x = c_key[lo], y = c_key[hi];
+					const bool asc = (lo & k) == 0;
+					if ((x > y) == asc) c_key[lo] = y, c_key[hi] = x;
+				}
+				__syncthreads();
+			}
+		if (tid < 32) {
+			const bool kept = sub_sweep_smem(c_key, n, min_dp, clip, sub + r, lane);
+			if (lane == 0 && kept) atomicAdd(scal + SC_COUNT, 1ull);
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void k_sub_copy_listed(const uint32_t *list, uint32_t n, const DSub *from, DSub *to, unsigned long long *n_remained)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		to[list[i]] = from[list[i]];
+		if (!(from[list[i]].s_del & MAB_DEL_BIT)) atomicAdd(n_remained, 1ull);
+	}
+}
+
+static uint64_t dh_sub_global(MabDev &d, const DHits &h, int min_dp, float min_iden, int end_clip, DSub *sub_out, const uint64_t *grp);
+
 uint64_t dh_sub(MabDev &d, const DHits &h, int min_dp, float min_iden, int end_clip, DSub *sub_out)
 {
 	const uint32_t n_seq = h.n_seq;
@@ -208,8 +364,45 @@ uint64_t dh_sub(MabDev &d, const DHits &h, int min_dp, float min_iden, int end_c
 	if (h.n == 0 || n_seq == 0) return 0;
 	if (h.n >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 hits on one GPU\n"); exit(73); }
 	uint64_t *grp = mab_alloc<uint64_t>(d, n_seq);
+	uint32_t *big = mab_alloc<uint32_t>(d, n_seq);
 	MAB_CUDA(cudaMemsetAsync(grp, 0, (size_t)n_seq * 8, d.stream));
+	MAB_CUDA(cudaMemsetAsync(d.d_scal, 0, 8 * sizeof(unsigned long long), d.stream));
 	MAB_LAUNCH(d, k_group_bounds, mab_grid(h.n, 256), 256, 0, h.a, h.n, (uint32_t*)grp);
+	unsigned grid = (n_seq + SUBW_WARPS - 1) / SUBW_WARPS;
+	if (grid > 148u * 32u) grid = 148u * 32u;
+	MAB_LAUNCH(d, k_sub_warp, grid, SUBW_WARPS * 32, 0, h.a, grp, n_seq, min_dp, min_iden, (uint32_t)end_clip, sub_out, big, d.d_scal);
+	uint32_t n_big = (uint32_t)d.get_scal(SC_BIG);
+	if (n_big) {
+		static bool attr_set = false;
+		const size_t smem = (size_t)SUBC_HITS * 2 * 4;
+		if (!attr_set) { MAB_CUDA(cudaFuncSetAttribute(k_sub_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+		uint32_t *huge = mab_alloc<uint32_t>(d, n_big);
+		MAB_LAUNCH(d, k_sub_cta, n_big < 148u * 2 ? n_big : 148u * 2, 512, smem, h.a, grp, big, n_big, min_dp, min_iden, (uint32_t)end_clip, sub_out, huge, d.d_scal);
+		uint32_t n_huge = (uint32_t)d.get_scal(SC_AUX2);
+		if (n_huge) { // reads with more hits than a CTA can sort: device-wide sort of everything, keep only their rows
+			DSub *tmp = mab_alloc<DSub>(d, n_seq);
+			unsigned long long saved = d.get_scal(SC_COUNT);
+			dh_sub_global(d, h, min_dp, min_iden, end_clip, tmp, grp);
+			MAB_CUDA(cudaMemcpyAsync(d.d_scal + SC_COUNT, &saved, 8, cudaMemcpyHostToDevice, d.stream));
+			MAB_LAUNCH(d, k_sub_copy_listed, mab_grid(n_huge, 128), 128, 0, huge, n_huge, tmp, sub_out, d.d_scal + SC_COUNT);
+			d.sync();
+			d.free(tmp);
+		}
+		d.free(huge);
+	}
+	uint64_t n_remained = d.get_scal(SC_COUNT);
+	d.free(grp); d.free(big);
+	if (ma_verbose_dev >= 3)
+		fprintf(stderr, "[M::%s::%s] %ld query sequences remain after sub\n", "ma_hit_sub", sys_timestamp(), (long)n_remained);
+	return n_remained;
+}
+
+static uint64_t dh_sub_global(MabDev &d, const DHits &h, int min_dp, float min_iden, int end_clip, DSub *sub_out, const uint64_t *grp)
+{
+	const uint32_t n_seq = h.n_seq;
+	if (n_seq) MAB_CUDA(cudaMemsetAsync(sub_out, 0, (size_t)n_seq * sizeof(DSub), d.stream));
+	if (h.n == 0 || n_seq == 0) return 0;
+	if (h.n >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 hits on one GPU\n"); exit(73); }
 	size_t nk = 2 * h.n;
 	uint64_t *ka = mab_alloc<uint64_t>(d, nk), *kb = mab_alloc<uint64_t>(d, nk);
 	MAB_LAUNCH(d, k_sub_keys, mab_grid(h.n, 256), 256, 0, h.a, h.n, min_iden, (uint32_t)end_clip, ka);
@@ -223,9 +416,7 @@ uint64_t dh_sub(MabDev &d, const DHits &h, int min_dp, float min_iden, int end_c
 	d.zero_scal(SC_COUNT);
 	MAB_LAUNCH(d, k_sub_sweep, mab_grid((size_t)n_seq * 32, 256), 256, 0, dk.Current(), grp, n_seq, min_dp, (uint32_t)end_clip, sub_out, d.d_scal + SC_COUNT);
 	uint64_t n_remained = d.get_scal(SC_COUNT);
-	d.free(ka); d.free(kb); d.free(grp);
-	if (ma_verbose_dev >= 3)
-		fprintf(stderr, "[M::%s::%s] %ld query sequences remain after sub\n", "ma_hit_sub", sys_timestamp(), (long)n_remained);
+	d.free(ka); d.free(kb);
 	return n_remained;
 }
 
@@ -233,12 +424,11 @@ uint64_t dh_sub(MabDev &d, const DHits &h, int min_dp, float min_iden, int end_c
 // ma_hit_cut (hit.c:162-193).  The reference computes in `int` locals from uint32 operands and compares
 // against a 31-bit field (signed after promotion) or a uint32 field (unsigned); restated with explicit types.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_cut(DHit *a, size_t n, const DSub *__restrict__ reg, int min_span, uint8_t *flag)
+// clips hit p to the kept intervals rq (query read) / rt (target read); true if both spans stay >= min_span
+__device__ __forceinline__ bool cut_hit(DHit &p, const DSub rq, const DSub rt, int min_span)
 {
-	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-		DHit p = ld_hit_rw(a + i);
-		const DSub rq = reg[p.qns >> 32], rt = reg[p.tn];
-		if ((rq.s_del | rt.s_del) & MAB_DEL_BIT) { flag[i] = 0; continue; }
+	{
+		if ((rq.s_del | rt.s_del) & MAB_DEL_BIT) return false;
 		const uint32_t rqs = rq.s_del, rts = rt.s_del, rqe = rq.e, rte = rt.e; // del bits are clear here
 		const uint32_t pqs = (uint32_t)p.qns;
 		uint32_t uqs, uqe, uts, ute;
@@ -262,10 +452,110 @@ __global__ void k_cut(DHit *a, size_t n, const DSub *__restrict__ reg, int min_s
 		if (keep) {
 			p.qns = (p.qns >> 32 << 32) | (uint64_t)(int64_t)qs;
 			p.qe = (uint32_t)qe, p.ts = (uint32_t)ts, p.te = (uint32_t)te;
-			st_hit(a + i, p);
+		}
+		return keep;
+	}
+}
+
+__global__ void k_cut(DHit *a, size_t n, const DSub *__restrict__ reg, int min_span, uint8_t *flag)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		DHit p = ld_hit_rw(a + i);
+		const bool keep = cut_hit(p, reg[p.qns >> 32], reg[p.tn], min_span);
+		if (keep) st_hit(a + i, p);
+		flag[i] = keep;
+	}
+}
+
+// ma_hit_cut followed by ma_hit_flt on the same interval table (main.c:123-125) in one sweep and one compaction
+__global__ void k_cut_flt(DHit *a, size_t n, const DSub *__restrict__ sub, int min_span, int max_hang, int min_ovlp, uint8_t *flag,
+                          unsigned long long *n_cut, unsigned long long *tot_dp)
+{
+	unsigned long long dp = 0;
+	unsigned cut = 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		DHit p = ld_hit_rw(a + i);
+		const DSub sq = sub[p.qns >> 32], st = sub[p.tn];
+		bool keep = cut_hit(p, sq, st, min_span);
+		if (keep) {
+			++cut;
+			DArc t;
+			const uint32_t ql = sq.e - sq.s_del, tl = st.e - st.s_del;
+			const int r = mab_hit2arc(p, (int)ql, (int)tl, max_hang, .5f, min_ovlp, &t);
+			keep = r >= 0 || r == MAB_HT_QCONT || r == MAB_HT_TCONT;
+			if (keep) { dp += r >= 0 ? (uint32_t)r : r == MAB_HT_QCONT ? ql : tl; st_hit(a + i, p); }
 		}
 		flag[i] = keep;
 	}
+	typedef cub::BlockReduce<unsigned long long, 256> BR;
+	__shared__ typename BR::TempStorage ts;
+	unsigned long long s = BR(ts).Sum(dp);
+	__syncthreads();
+	unsigned long long c = BR(ts).Sum((unsigned long long)cut);
+	if (threadIdx.x == 0) { if (s) atomicAdd(tot_dp, s); if (c) atomicAdd(n_cut, c); }
+}
+
+// second-round ma_hit_cut fused with pass 1 of ma_hit_contained (hit.c:231-236): clip, then classify the clipped hit
+// against the merged interval table (its lengths equal those of the round-2 table) and raise containment flags
+__global__ void k_cut_cont_mark(DHit *a, size_t n, const DSub *__restrict__ sub2, DSub *sub, int min_span, HitArcParams hp,
+                                uint8_t *used, uint8_t *flag, unsigned long long *n_cut)
+{
+	unsigned cut = 0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		DHit p = ld_hit_rw(a + i);
+		const uint32_t q = (uint32_t)(p.qns >> 32), t = p.tn;
+		const DSub rq = sub2[q], rt = sub2[t];
+		const bool keep = cut_hit(p, rq, rt, min_span);
+		if (keep) {
+			++cut;
+			st_hit(a + i, p);
+			DArc tmp;
+			const int r = mab_hit2arc(p, (int)(rq.e - rq.s_del), (int)(rt.e - rt.s_del), hp.max_hang, hp.int_frac, hp.min_ovlp, &tmp);
+			if (r == MAB_HT_QCONT) atomicOr(&sub[q].s_del, MAB_DEL_BIT);
+			else if (r == MAB_HT_TCONT) atomicOr(&sub[t].s_del, MAB_DEL_BIT);
+			used[q] = 1, used[t] = 1;
+		}
+		flag[i] = keep;
+	}
+	cut = __reduce_add_sync(0xffffffffu, cut);
+	if ((threadIdx.x & 31) == 0 && cut) atomicAdd(n_cut, (unsigned long long)cut);
+}
+
+__global__ void k_cont_apply2(DHit *a, size_t n, const int32_t *__restrict__ map, uint8_t *flag)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		bool keep = flag[i];
+		if (keep) {
+			uint64_t qns = a[i].qns;
+			int32_t qn = map[qns >> 32], tn = map[a[i].tn];
+			keep = qn >= 0 && tn >= 0;
+			if (keep) { a[i].qns = (uint64_t)(uint32_t)qn << 32 | (uint32_t)qns; a[i].tn = (uint32_t)tn; }
+		}
+		flag[i] = keep;
+	}
+}
+
+__global__ void k_flt_len(const DHit *a, size_t n, const DSub *__restrict__ sub, unsigned long long *tot_len);
+
+size_t dh_cut_flt(MabDev &d, DHits &h, const DSub *sub, int min_span, int max_hang, int min_ovlp, float *cov)
+{
+	unsigned long long tot_dp = 0, tot_len = 0, n_cut = 0;
+	if (h.n) {
+		uint8_t *flag = mab_alloc<uint8_t>(d, h.n);
+		d.zero_scal(SC_AUX, 2);
+		d.zero_scal(SC_COUNT, 1);
+		MAB_LAUNCH(d, k_cut_flt, mab_grid(h.n, 256), 256, 0, h.a, h.n, sub, min_span, max_hang, min_ovlp, flag, d.d_scal + SC_COUNT, d.d_scal + SC_AUX);
+		select_hits(d, h, flag);
+		d.free(flag);
+		if (h.n) MAB_LAUNCH(d, k_flt_len, mab_grid(h.n, 256), 256, 0, h.a, h.n, sub, d.d_scal + SC_AUX2);
+		tot_dp = d.get_scal(SC_AUX), tot_len = d.h_scal[SC_AUX2], n_cut = d.h_scal[SC_COUNT];
+	}
+	*cov = (float)((double)tot_dp / tot_len);
+	if (ma_verbose_dev >= 3) {
+		fprintf(stderr, "[M::%s::%s] %ld hits remain after cut\n", "ma_hit_cut", sys_timestamp(), (long)n_cut);
+		fprintf(stderr, "[M::%s::%s] %ld hits remain after filtering; crude coverage after filtering: %.2f\n", "ma_hit_flt", sys_timestamp(), (long)h.n, *cov);
+	}
+	return h.n;
 }
 
 size_t dh_cut(MabDev &d, DHits &h, const DSub *reg, int min_span)
@@ -400,15 +690,22 @@ __global__ void k_cont_apply(DHit *a, size_t n, const int32_t *__restrict__ map,
 	}
 }
 
-size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, const HitArcParams &p, int32_t *map_out)
+size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, const HitArcParams &p, int32_t *map_out, const DSub *cut_reg, int min_span)
 {
 	const uint32_t n_seq = h.n_seq;
 	uint32_t n_new = 0;
+	unsigned long long n_cut = 0;
+	uint8_t *cut_flag = nullptr;
 	if (n_seq) {
 		uint8_t *used = mab_alloc<uint8_t>(d, n_seq);
 		uint32_t *keep = mab_alloc<uint32_t>(d, n_seq), *excl = mab_alloc<uint32_t>(d, (size_t)n_seq + 1);
 		DSub *sub2 = mab_alloc<DSub>(d, n_seq);
 		MAB_CUDA(cudaMemsetAsync(used, 0, n_seq, d.stream));
+		if (cut_reg && h.n) { // fused with the preceding ma_hit_cut: one sweep clips and classifies, one compaction at the end
+			cut_flag = mab_alloc<uint8_t>(d, h.n);
+			d.zero_scal(SC_COUNT, 1);
+			MAB_LAUNCH(d, k_cut_cont_mark, mab_grid(h.n, 256), 256, 0, h.a, h.n, cut_reg, sub, min_span, p, used, cut_flag, d.d_scal + SC_COUNT);
+		} else
 		if (h.n) MAB_LAUNCH(d, k_cont_mark, mab_grid(h.n, 256), 256, 0, h.a, h.n, sub, p, used);
 		MAB_LAUNCH(d, k_cont_keep, mab_grid(n_seq, 256), 256, 0, n_seq, sub, used, seq_del, keep);
 		size_t tb = 0;
@@ -423,7 +720,12 @@ size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, cons
 		d.sync();
 		n_new = last_keep + last_excl;
 		if (n_new) MAB_CUDA(cudaMemcpyAsync(sub, sub2, (size_t)n_new * sizeof(DSub), cudaMemcpyDeviceToDevice, d.stream));
-		if (h.n) {
+		if (cut_flag) {
+			n_cut = d.get_scal(SC_COUNT);
+			MAB_LAUNCH(d, k_cont_apply2, mab_grid(h.n, 256), 256, 0, h.a, h.n, map_out, cut_flag);
+			select_hits(d, h, cut_flag);
+			d.free(cut_flag);
+		} else if (h.n) {
 			uint8_t *flag = mab_alloc<uint8_t>(d, h.n);
 			MAB_LAUNCH(d, k_cont_apply, mab_grid(h.n, 256), 256, 0, h.a, h.n, map_out, flag);
 			select_hits(d, h, flag);
@@ -432,6 +734,7 @@ size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, cons
 		d.free(used); d.free(keep); d.free(excl); d.free(sub2);
 	}
 	h.n_seq = n_new;
+	if (cut_reg && ma_verbose_dev >= 3) fprintf(stderr, "[M::%s::%s] %ld hits remain after cut\n", "ma_hit_cut", sys_timestamp(), (long)n_cut);
 	if (ma_verbose_dev >= 3)
 		fprintf(stderr, "[M::%s::%s] %d sequences and %ld hits remain after containment removal\n", "ma_hit_contained", sys_timestamp(), n_new, (long)h.n);
 	return h.n;

@@ -35,7 +35,11 @@ void dh_sub_merge(MabDev &d, uint32_t n_sub, DSub *a, const DSub *b);
 // (sdict.c:69-86).  seq_del: per-read deletion flags of the dictionary on entry (may be null = none).
 // On return sub is compacted in place, hits renumbered/compacted, map_out[old] = new id or -1, and
 // h.n_seq is the surviving read count.  Returns the new hit count.
-size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, const HitArcParams &p, int32_t *map_out);
+// With cut_reg != null the call first applies ma_hit_cut(cut_reg, min_span) to the hits (fused sweep, one compaction).
+size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, const HitArcParams &p, int32_t *map_out,
+                    const DSub *cut_reg = nullptr, int min_span = 0);
+// ma_hit_cut immediately followed by ma_hit_flt on the same table (main.c:123-125), fused
+size_t dh_cut_flt(MabDev &d, DHits &h, const DSub *sub, int min_span, int max_hang, int min_ovlp, float *cov);
 
 // ma_sg_gen (asm.c:9-39): lens/del per read -> graph with arcs emitted in hit order, then asg_cleanup.
 void dh_sg_gen(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *del, const HitArcParams &p, DGraph &g);

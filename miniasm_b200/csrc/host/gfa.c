@@ -33,51 +33,95 @@ void ma_sg_print(const asg_t *g, const sdict_t *d, const ma_sub_t *sub, FILE *fp
 	}
 }
 
-static void utg_name(char *buf, uint32_t i, int circ) { sprintf(buf, "utg%.6d%c", i + 1, "lc"[!!circ]); }
+/* A small append buffer with hand-rolled integer formatting: the `a` lines are one per read, i.e. millions of
+ * lines on real inputs, and fprintf dominated the host tail of the end-to-end path.  Output bytes are those of
+ * the reference's fprintf formats (asm.c:77-116): "%d" of the 32-bit value, "utg%.6d" zero-padded to 6 digits. */
+typedef struct { char *s; size_t l, m; FILE *fp; } obuf_t;
+
+static inline void ob_room(obuf_t *b, size_t k)
+{
+	if (b->l + k <= b->m) return;
+	if (b->l) fwrite(b->s, 1, b->l, b->fp), b->l = 0;
+	if (k > b->m) { b->m = k + (1 << 20); b->s = (char*)realloc(b->s, b->m); }
+}
+static inline void ob_c(obuf_t *b, char c) { b->s[b->l++] = c; }
+static inline void ob_str(obuf_t *b, const char *s) { size_t n = strlen(s); ob_room(b, n + 64); memcpy(b->s + b->l, s, n); b->l += n; }
+static inline void ob_int(obuf_t *b, int32_t v) /* "%d" */
+{
+	char t[12]; int n = 0;
+	uint32_t x = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+	if (v < 0) ob_c(b, '-');
+	do t[n++] = '0' + x % 10, x /= 10; while (x);
+	while (n) ob_c(b, t[--n]);
+}
+static inline void ob_utg(obuf_t *b, uint32_t i, int circ) /* "utg%.6d%c" of i+1 */
+{
+	char t[12]; int n = 0;
+	uint32_t x = i + 1;
+	do t[n++] = '0' + x % 10, x /= 10; while (x);
+	ob_c(b, 'u'); ob_c(b, 't'); ob_c(b, 'g');
+	for (x = n; x < 6; ++x) ob_c(b, '0');
+	while (n) ob_c(b, t[--n]);
+	ob_c(b, "lc"[!!circ]);
+}
+static inline void ob_read(obuf_t *b, const sdict_t *d, const ma_sub_t *sub, uint32_t r) /* name or name:s+1-e */
+{
+	ob_str(b, d->seq[r].name);
+	if (sub) { ob_c(b, ':'); ob_int(b, (int32_t)(sub[r].s + 1)); ob_c(b, '-'); ob_int(b, (int32_t)sub[r].e); }
+}
 
 void ma_ug_print(const ma_ug_t *ug, const sdict_t *d, const ma_sub_t *sub, FILE *fp)
 {
 	uint32_t i, j;
-	char name[32], name2[32];
+	obuf_t b = {0, 0, 0, fp};
+	ob_room(&b, 1 << 22);
 	for (i = 0; i < ug->u.n; ++i) { /* segments, circularising links, read layout */
 		const ma_utg_t *p = &ug->u.a[i];
 		uint32_t off = 0;
-		utg_name(name, i, p->circ);
-		fprintf(fp, "S\t%s\t%s\tLN:i:%d\n", name, p->s ? p->s : "*", p->len);
+		ob_room(&b, 256);
+		ob_c(&b, 'S'); ob_c(&b, '\t'); ob_utg(&b, i, p->circ); ob_c(&b, '\t');
+		if (p->s) { size_t n = strlen(p->s); ob_room(&b, n + 256); memcpy(b.s + b.l, p->s, n); b.l += n; }
+		else ob_c(&b, '*');
+		memcpy(b.s + b.l, "\tLN:i:", 6), b.l += 6; ob_int(&b, (int32_t)p->len); ob_c(&b, '\n');
 		if (p->circ) {
-			fprintf(fp, "L\t%s\t+\t%s\t+\t0M\n", name, name);
-			fprintf(fp, "L\t%s\t-\t%s\t-\t0M\n", name, name);
+			int k;
+			for (k = 0; k < 2; ++k) {
+				ob_c(&b, 'L'); ob_c(&b, '\t'); ob_utg(&b, i, 1); ob_c(&b, '\t'); ob_c(&b, "+-"[k]); ob_c(&b, '\t');
+				ob_utg(&b, i, 1); ob_c(&b, '\t'); ob_c(&b, "+-"[k]); ob_c(&b, '\t'); ob_c(&b, '0'); ob_c(&b, 'M'); ob_c(&b, '\n');
+			}
 		}
 		for (j = 0; j < p->n; ++j) {
-			uint32_t r = (uint32_t)(p->a[j] >> 33), l = (uint32_t)p->a[j];
-			char strand = "+-"[p->a[j] >> 32 & 1];
-			if (sub) fprintf(fp, "a\t%s\t%d\t%s:%d-%d\t%c\t%d\n", name, off, d->seq[r].name, sub[r].s + 1, sub[r].e, strand, l);
-			else fprintf(fp, "a\t%s\t%d\t%s\t%c\t%d\n", name, off, d->seq[r].name, strand, l);
+			const uint32_t r = (uint32_t)(p->a[j] >> 33), l = (uint32_t)p->a[j];
+			ob_room(&b, 256);
+			ob_c(&b, 'a'); ob_c(&b, '\t'); ob_utg(&b, i, p->circ); ob_c(&b, '\t'); ob_int(&b, (int32_t)off); ob_c(&b, '\t');
+			ob_read(&b, d, sub, r);
+			ob_c(&b, '\t'); ob_c(&b, "+-"[p->a[j] >> 32 & 1]); ob_c(&b, '\t'); ob_int(&b, (int32_t)l); ob_c(&b, '\n');
 			off += l;
 		}
 	}
 	for (i = 0; i < ug->g->n_arc; ++i) { /* links between unitigs */
 		const asg_arc_t *a = &ug->g->arc[i];
-		uint32_t u = (uint32_t)(a->ul >> 32), v = a->v;
-		utg_name(name, u >> 1, ug->u.a[u >> 1].circ);
-		utg_name(name2, v >> 1, ug->u.a[v >> 1].circ);
-		fprintf(fp, "L\t%s\t%c\t%s\t%c\t%dM\tSD:i:%d\n", name, "+-"[u & 1], name2, "+-"[v & 1], a->ol, (uint32_t)a->ul);
+		const uint32_t u = (uint32_t)(a->ul >> 32), v = a->v;
+		ob_room(&b, 256);
+		ob_c(&b, 'L'); ob_c(&b, '\t'); ob_utg(&b, u >> 1, ug->u.a[u >> 1].circ); ob_c(&b, '\t'); ob_c(&b, "+-"[u & 1]); ob_c(&b, '\t');
+		ob_utg(&b, v >> 1, ug->u.a[v >> 1].circ); ob_c(&b, '\t'); ob_c(&b, "+-"[v & 1]); ob_c(&b, '\t');
+		ob_int(&b, (int32_t)a->ol); ob_c(&b, 'M'); memcpy(b.s + b.l, "\tSD:i:", 6), b.l += 6; ob_int(&b, (int32_t)(uint32_t)a->ul); ob_c(&b, '\n');
 	}
 	for (i = 0; i < ug->u.n; ++i) { /* per-unitig summary */
 		const ma_utg_t *p = &ug->u.a[i];
+		ob_room(&b, 512);
+		ob_c(&b, 'x'); ob_c(&b, '\t');
 		if (p->start == UINT32_MAX) {
-			fprintf(fp, "x\tutg%.6dc\t%d\t%d\n", i + 1, p->len, p->n);
+			ob_utg(&b, i, 1); ob_c(&b, '\t'); ob_int(&b, (int32_t)p->len); ob_c(&b, '\t'); ob_int(&b, (int32_t)p->n); ob_c(&b, '\n');
 		} else {
-			uint32_t n_out0 = (uint32_t)ug->g->idx[i << 1 | 0], n_out1 = (uint32_t)ug->g->idx[i << 1 | 1];
-			uint32_t s = p->start >> 1, e = p->end >> 1;
-			if (sub)
-				fprintf(fp, "x\tutg%.6dl\t%d\t%d\t%d\t%d\t%s:%d-%d\t%c\t%s:%d-%d\t%c\n", i + 1, p->len, p->n, n_out1, n_out0,
-						d->seq[s].name, sub[s].s + 1, sub[s].e, "+-"[p->start & 1], d->seq[e].name, sub[e].s + 1, sub[e].e, "+-"[p->end & 1]);
-			else
-				fprintf(fp, "x\tutg%.6dl\t%d\t%d\t%d\t%d\t%s\t%c\t%s\t%c\n", i + 1, p->len, p->n, n_out1, n_out0,
-						d->seq[s].name, "+-"[p->start & 1], d->seq[e].name, "+-"[p->end & 1]);
+			ob_utg(&b, i, 0); ob_c(&b, '\t'); ob_int(&b, (int32_t)p->len); ob_c(&b, '\t'); ob_int(&b, (int32_t)p->n); ob_c(&b, '\t');
+			ob_int(&b, (int32_t)(uint32_t)ug->g->idx[i << 1 | 1]); ob_c(&b, '\t'); ob_int(&b, (int32_t)(uint32_t)ug->g->idx[i << 1 | 0]); ob_c(&b, '\t');
+			ob_read(&b, d, sub, p->start >> 1); ob_c(&b, '\t'); ob_c(&b, "+-"[p->start & 1]); ob_c(&b, '\t');
+			ob_read(&b, d, sub, p->end >> 1); ob_c(&b, '\t'); ob_c(&b, "+-"[p->end & 1]); ob_c(&b, '\n');
 		}
 	}
+	if (b.l) fwrite(b.s, 1, b.l, fp);
+	free(b.s);
 }
 
 /* ---------------------------------------------------------------------------------------------

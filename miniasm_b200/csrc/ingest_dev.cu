@@ -32,6 +32,64 @@ struct PLine {                 // one parsed PAF line, 64 bytes
 #define slot_t ht
 static_assert(sizeof(PLine) == 64, "PLine layout");
 
+// ---- line starts -----------------------------------------------------------------------------------------
+// A line starts at byte 0 and after every '\n' that is not the last byte.  Tiles of NL_TILE bytes, one CTA each,
+// 128-bit loads laid out so that a warp reads 512 contiguous bytes per instruction.
+constexpr int NL_THREADS = 256;
+constexpr int NL_PER_THREAD = 4;                      // uint4 words per thread
+constexpr uint64_t NL_TILE = (uint64_t)NL_THREADS * NL_PER_THREAD * 16;
+
+__device__ __forceinline__ uint32_t nl_mask4(uint32_t w) { return __vcmpeq4(w, 0x0a0a0a0au); } // 0xff in every byte equal to '\n'
+
+// newline bytes of the 16-byte word at `off` that are followed by another byte of the text; bit k = byte k
+__device__ __forceinline__ uint32_t nl_bits16(const char *text, size_t len, uint64_t off)
+{
+	if (off >= len) return 0;
+	uint32_t bits = 0;
+	if (off + 16 <= len) {
+		const uint4 w = __ldg(reinterpret_cast<const uint4*>(text + off));
+		const uint32_t m[4] = { nl_mask4(w.x), nl_mask4(w.y), nl_mask4(w.z), nl_mask4(w.w) };
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) bits |= ((m[k] & 1) | (m[k] >> 7 & 2) | (m[k] >> 14 & 4) | (m[k] >> 21 & 8)) << (4 * k);
+	} else for (uint64_t k = 0; off + k < len; ++k) bits |= (uint32_t)(text[off + k] == '\n') << k;
+	if (off + 16 >= len && len - 1 - off < 16) bits &= ~(1u << (len - 1 - off)); // a newline ending the file starts no line
+	return bits;
+}
+
+__global__ void __launch_bounds__(NL_THREADS) k_nl_count(const char *__restrict__ text, size_t len, uint64_t n_tile, uint64_t *cnt)
+{
+	typedef cub::BlockReduce<uint32_t, NL_THREADS> BR;
+	__shared__ typename BR::TempStorage ts;
+	for (uint64_t t = blockIdx.x; t < n_tile; t += gridDim.x) {
+		uint32_t c = 0;
+		#pragma unroll
+		for (int k = 0; k < NL_PER_THREAD; ++k) c += __popc(nl_bits16(text, len, t * NL_TILE + ((uint64_t)k * NL_THREADS + threadIdx.x) * 16));
+		c = BR(ts).Sum(c);
+		if (threadIdx.x == 0) cnt[t] = c;
+		__syncthreads();
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) cnt[n_tile] = 0;
+}
+
+__global__ void __launch_bounds__(NL_THREADS) k_nl_write(const char *__restrict__ text, size_t len, uint64_t n_tile, const uint64_t *__restrict__ base, uint64_t *out)
+{
+	typedef cub::BlockScan<uint32_t, NL_THREADS> BS;
+	__shared__ typename BS::TempStorage ts;
+	for (uint64_t t = blockIdx.x; t < n_tile; t += gridDim.x) {
+		uint64_t at = base[t];
+		#pragma unroll
+		for (int k = 0; k < NL_PER_THREAD; ++k) {
+			const uint64_t off = t * NL_TILE + ((uint64_t)k * NL_THREADS + threadIdx.x) * 16;
+			uint32_t bits = nl_bits16(text, len, off), rank, total;
+			BS(ts).ExclusiveSum((uint32_t)__popc(bits), rank, total);
+			uint64_t *o = out + at + rank;
+			while (bits) { const int b = __ffs(bits) - 1; *o++ = off + b + 1; bits &= bits - 1; }
+			at += total;
+			__syncthreads();
+		}
+	}
+}
+
 struct IsLineStart {
 	const char *text;
 	__device__ __forceinline__ bool operator()(uint64_t p) const { return p == 0 || text[p - 1] == '\n'; }
@@ -62,55 +120,85 @@ __device__ __forceinline__ uint32_t field_to_u32(const char *p, const char *e)
 	return (uint32_t)s;
 }
 
-__global__ void k_parse(const char *__restrict__ text, size_t len, const uint64_t *__restrict__ start, uint64_t n_lines,
-                        int min_span, int min_match, uint64_t seed, PLine *out, unsigned long long *counts)
+// parse one line [p, e) (no terminator, '\r' already dropped); names are hashed with FNV-1a + fmix64
+__device__ __forceinline__ void parse_line(const char *p, const char *e, uint64_t seed, PLine &r, bool &too_long)
 {
-	unsigned n_parsed = 0;
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
-		const uint64_t s = start[i];
-		uint64_t eol = i + 1 < n_lines ? start[i + 1] - 1 : (text[len - 1] == '\n' ? len - 1 : len);
-		if (eol - s > 1 && text[eol - 1] == '\r') --eol;
-		const char *p = text + s, *e = text + eol, *f = p;
-		PLine r;
-		memset(&r, 0, sizeof(r));
-		int t = 0;
-		bool too_long = false;
-		for (const char *q = p;; ++q) {
-			if (q == e || *q == '\t') {
-				switch (t) {
-					case 0: {
-						uint64_t h = 1469598103934665603ULL ^ seed;
-						for (const char *c = f; c < q; ++c) h = (h ^ (uint8_t)*c) * 1099511628211ULL;
-						h = fmix64(h); r.hq = h ? h : 1; r.qnl = (uint16_t)(q - f); too_long |= (q - f) > 65535; break; }
-					case 1: r.ql = field_to_u32(f, q); break;
-					case 2: r.qs = field_to_u32(f, q); break;
-					case 3: r.qe = field_to_u32(f, q); break;
-					case 4: r.ml_rev = (f < q && *f == '-') ? 0x80000000u : 0; break;
-					case 5: {
-						uint64_t h = 1469598103934665603ULL ^ seed;
-						for (const char *c = f; c < q; ++c) h = (h ^ (uint8_t)*c) * 1099511628211ULL;
-						h = fmix64(h); r.ht = h ? h : 1; r.tnl = (uint16_t)(q - f); r.tdelta = (uint32_t)(f - p); too_long |= (q - f) > 65535; break; }
-					case 6: r.tl = field_to_u32(f, q); break;
-					case 7: r.ts = field_to_u32(f, q); break;
-					case 8: r.te = field_to_u32(f, q); break;
-					case 9: r.ml_rev |= field_to_u32(f, q) & 0x7fffffffu; break;
-					case 10: r.bl = field_to_u32(f, q); break;
-				}
-				++t;
-				f = q + 1;
-				if (q == e || t == 11) break;
+	const char *f = p;
+	int t = 0;
+	memset(&r, 0, sizeof(r));
+	for (const char *q = p;; ++q) {
+		if (q == e || *q == '\t') {
+			switch (t) {
+				case 0: {
+					uint64_t h = 1469598103934665603ULL ^ seed;
+					for (const char *c = f; c < q; ++c) h = (h ^ (uint8_t)*c) * 1099511628211ULL;
+					h = fmix64(h); r.hq = h ? h : 1; r.qnl = (uint16_t)(q - f); too_long |= (q - f) > 65535; break; }
+				case 1: r.ql = field_to_u32(f, q); break;
+				case 2: r.qs = field_to_u32(f, q); break;
+				case 3: r.qe = field_to_u32(f, q); break;
+				case 4: r.ml_rev = (f < q && *f == '-') ? 0x80000000u : 0; break;
+				case 5: {
+					uint64_t h = 1469598103934665603ULL ^ seed;
+					for (const char *c = f; c < q; ++c) h = (h ^ (uint8_t)*c) * 1099511628211ULL;
+					h = fmix64(h); r.ht = h ? h : 1; r.tnl = (uint16_t)(q - f); r.tdelta = (uint32_t)(f - p); too_long |= (q - f) > 65535; break; }
+				case 6: r.tl = field_to_u32(f, q); break;
+				case 7: r.ts = field_to_u32(f, q); break;
+				case 8: r.te = field_to_u32(f, q); break;
+				case 9: r.ml_rev |= field_to_u32(f, q) & 0x7fffffffu; break;
+				case 10: r.bl = field_to_u32(f, q); break;
 			}
+			++t;
+			f = q + 1;
+			if (q == e || t == 11) break;
 		}
-		r.nf = (uint8_t)t;
-		if (t >= 10) {
-			++n_parsed;
-			if (too_long) atomicAdd(counts + 1, 1ull); // a name beyond 65535 bytes does not fit the record: the host aborts
+	}
+	r.nf = (uint8_t)t;
+}
+
+// One CTA parses PARSE_LINES consecutive lines.  Their bytes are contiguous in the file, so the CTA first copies
+// the whole range into shared memory with coalesced 128-bit loads and the threads then walk their own line there:
+// byte-wise walking of global memory made every warp-level load touch ~16 cache lines (ncu: L1 wavefront bound).
+// A range that does not fit (very long lines) is parsed straight from global memory.
+constexpr int PARSE_LINES = 128;
+constexpr int PARSE_SMEM = 24 * 1024;
+
+__global__ void __launch_bounds__(PARSE_LINES)
+k_parse(const char *__restrict__ text, size_t len, const uint64_t *__restrict__ start, uint64_t n_lines,
+        uint64_t seed, PLine *out, unsigned long long *counts)
+{
+	__shared__ __align__(16) char s_text[PARSE_SMEM];
+	unsigned n_parsed = 0;
+	const uint64_t n_blk = (n_lines + PARSE_LINES - 1) / PARSE_LINES;
+	for (uint64_t b = blockIdx.x; b < n_blk; b += gridDim.x) {
+		const uint64_t l0 = b * PARSE_LINES, l1 = l0 + PARSE_LINES < n_lines ? l0 + PARSE_LINES : n_lines;
+		const uint64_t s0 = start[l0], s1 = l1 < n_lines ? start[l1] : len;
+		const uint64_t a0 = s0 & ~(uint64_t)15;
+		const bool staged = s1 - a0 <= PARSE_SMEM;
+		__syncthreads(); // the previous range is no longer needed
+		if (staged) {
+			const uint64_t n16 = (s1 - a0 + 15) >> 4; // whole 16-byte words; the tail word may reach past `len` but stays inside the (padded) allocation
+			for (uint64_t k = threadIdx.x; k < n16; k += PARSE_LINES)
+				reinterpret_cast<uint4*>(s_text)[k] = __ldg(reinterpret_cast<const uint4*>(text + a0) + k);
 		}
-		out[i] = r;
+		__syncthreads();
+		const uint64_t i = l0 + threadIdx.x;
+		if (i < l1) {
+			const uint64_t s = start[i];
+			uint64_t eol = i + 1 < n_lines ? start[i + 1] - 1 : (text[len - 1] == '\n' ? len - 1 : len);
+			const char *base = staged ? s_text - a0 : text; // base + file offset = address of that byte
+			if (eol - s > 1 && base[eol - 1] == '\r') --eol;
+			PLine r;
+			bool too_long = false;
+			parse_line(base + s, base + eol, seed, r, too_long);
+			if (r.nf >= 10) {
+				++n_parsed;
+				if (too_long) atomicAdd(counts + 1, 1ull); // a name beyond 65535 bytes does not fit the record: the host aborts
+			}
+			out[i] = r;
+		}
 	}
 	n_parsed = __reduce_add_sync(0xffffffffu, n_parsed);
 	if ((threadIdx.x & 31) == 0 && n_parsed) atomicAdd(counts, (unsigned long long)n_parsed);
-	(void)min_span; (void)min_match;
 }
 
 // stale bl for 10-field lines + the store filter (needs the final bl? no: the filter uses qe,qs,te,ts,ml only)
@@ -270,27 +358,27 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 	if (len == 0) { dh_reserve(d, h, 1); return; }
 
 	d.trace("ingest:begin");
-	// (1) line starts
+	// (1) line starts: count newlines per 16 KB tile, scan the tile counts, write the positions
 	uint64_t *start = nullptr;
 	uint64_t n_lines;
 	{
-		cub::CountingInputIterator<uint64_t> pos(0);
-		IsLineStart pred{d_text};
-		// count first (one pass over the bytes), then select into an exactly sized array
+		const uint64_t n_tile = (len + NL_TILE - 1) / NL_TILE;
+		uint64_t *cnt = mab_alloc<uint64_t>(d, n_tile + 1);
+		uint64_t *base = mab_alloc<uint64_t>(d, n_tile + 1);
+		MAB_LAUNCH(d, k_nl_count, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, cnt);
 		size_t tb = 0;
-		unsigned long long *d_n = d.d_scal + SC_NSEL;
-		cub::TransformInputIterator<int, IsLineStart, cub::CountingInputIterator<uint64_t>> ones(pos, pred);
-		cub::DeviceReduce::Sum(nullptr, tb, ones, d_n, (int64_t)len, d.stream);
+		cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, base, (int64_t)(n_tile + 1), d.stream);
 		void *tmp = d.tmp(tb);
-		cub::DeviceReduce::Sum(tmp, tb, ones, d_n, (int64_t)len, d.stream);
+		cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, base, (int64_t)(n_tile + 1), d.stream);
 		++d.n_lib;
-		n_lines = d.get_scal(SC_NSEL);
+		uint64_t n_nl;
+		MAB_CUDA(cudaMemcpyAsync(&n_nl, base + n_tile, 8, cudaMemcpyDeviceToHost, d.stream));
+		d.sync();
+		n_lines = n_nl + 1; // newlines that are followed by at least one byte, plus the first line
 		start = mab_alloc<uint64_t>(d, n_lines + 1);
-		tb = 0;
-		cub::DeviceSelect::If(nullptr, tb, pos, start, d_n, (int64_t)len, pred, d.stream);
-		tmp = d.tmp(tb);
-		cub::DeviceSelect::If(tmp, tb, pos, start, d_n, (int64_t)len, pred, d.stream);
-		++d.n_lib;
+		MAB_CUDA(cudaMemsetAsync(start, 0, 8, d.stream));
+		MAB_LAUNCH(d, k_nl_write, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, base, start + 1);
+		d.free(cnt); d.free(base);
 	}
 	st.n_lines = n_lines;
 	d.trace("ingest:line_starts");
@@ -304,7 +392,7 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 	uint64_t seed = 0;
 	for (int attempt = 0;; ++attempt) {
 		d.zero_scal(SC_COUNT, 4);
-		MAB_LAUNCH(d, k_parse, mab_grid(n_lines, 128), 128, 0, d_text, len, start, n_lines, min_span, min_match, seed, ln, d.d_scal + SC_COUNT);
+		MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, n_lines, seed, ln, d.d_scal + SC_COUNT);
 		MAB_LAUNCH(d, k_fix_filter, mab_grid(n_lines, 256), 256, 0, ln, n_lines, min_span, min_match, d.d_scal + SC_AUX);
 		st.n_parsed = d.get_scal(SC_COUNT);
 		n_pass = d.h_scal[SC_AUX];

@@ -124,3 +124,26 @@ def test_empty_inputs(prod):
     assert not capi.np_from_ptr(s, 4, SUB_DT)["e"].any()
     assert prod.ma_hit_cut(s, 2000, 0, z) == 0
     capi.c_free(s), capi.c_free(z)
+
+
+def test_sub_group_sizes(ref, prod):
+    """Groups beyond the warp kernel (256 hits), beyond the CTA kernel (12288 hits) and tiny ones, in one array:
+    the shared-memory paths and the device-wide-sort fallback of ma_hit_sub must agree with the reference."""
+    rng = np.random.default_rng(9)
+    rows = []
+    sizes = {0: 3, 1: 40, 2: 256, 3: 257, 4: 700, 5: 5000, 6: 12288, 7: 12289, 8: 20000, 9: 1}
+    for q, n in sizes.items():
+        qs = rng.integers(0, 30000, size=n)
+        ln = rng.integers(500, 20000, size=n)
+        for k in range(n):
+            lowid = rng.random() < 0.05
+            rows.append(((q << 32) | int(qs[k]), int(qs[k] + ln[k]), int(100 + rng.integers(0, 50)) if rng.random() > 0.02 else q,
+                         0, int(ln[k]), 10 if lowid else 1000, 1000))
+    a = np.array(rows, dtype=HIT_DT)
+    a = a[np.argsort(a["qns"], kind="stable")]
+    for dp, clip in ((3, 0), (3, 1000), (1, 0), (50, 300)):
+        pa = capi.c_malloc_copy(a)
+        sr = ref.ma_hit_sub(dp, 0.05, clip, len(a), pa, 200)
+        sp = prod.ma_hit_sub(dp, 0.05, clip, len(a), pa, 200)
+        assert np.array_equal(capi.np_from_ptr(sr, 200, SUB_DT), capi.np_from_ptr(sp, 200, SUB_DT)), (dp, clip)
+        capi.c_free(sr), capi.c_free(sp), capi.c_free(pa)
