@@ -86,11 +86,24 @@ struct ArcKeep {
 	}
 };
 
+__global__ void k_arc_count_dead(ArcKeep keep, uint32_t n, unsigned long long *n_dead)
+{
+	unsigned dead = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dead += !keep(i);
+	dead = __reduce_add_sync(0xffffffffu, dead);
+	if ((threadIdx.x & 31) == 0 && dead) atomicAdd(n_dead, (unsigned long long)dead);
+}
+
 void dg_arc_rm(MabDev &d, DGraph &g, const uint8_t *flag)
 {
 	if (g.n_arc == 0) return;
 	cub::CountingInputIterator<uint32_t> cnt(0);
 	ArcKeep keep{g.arc, g.seq, flag};
+	if (!flag && g.n_arc > (1u << 20)) { // a read-only sweep is half the traffic of a compaction: skip the copy when nothing dies
+		d.zero_scal(SC_NSEL);
+		MAB_LAUNCH(d, k_arc_count_dead, mab_grid(g.n_arc, 256), 256, 0, keep, g.n_arc, d.d_scal + SC_NSEL);
+		if (d.get_scal(SC_NSEL) == 0) return;
+	}
 	cub::TransformInputIterator<bool, ArcKeep, cub::CountingInputIterator<uint32_t>> flags(cnt, keep);
 	size_t tb = 0;
 	unsigned long long *d_n = d.d_scal + SC_NSEL;
@@ -148,6 +161,25 @@ void dg_arc_sort(MabDev &d, DGraph &g)
 		d.free(ka); d.free(kb); d.free(va); d.free(vb);
 	}
 	g.is_srt = true;
+}
+
+// Builds the sorted AoS arc array from unsorted (key, value) columns; keys equal to `sentinel` (placed past every
+// real key) are padding and end up behind the n_real arcs.  Used by ma_sg_gen, which emits the columns directly.
+void dg_build_sorted(MabDev &d, DGraph &g, uint64_t *key, uint64_t *val, uint64_t *key2, uint64_t *val2, uint32_t n_in, uint32_t n_real, uint32_t lb, bool has_sentinel)
+{
+	dg_reserve(d, g, n_real ? n_real : 1);
+	g.len_bits = lb;
+	if (n_in > 1) {
+		uint32_t end_bit = lb + bits_for((uint64_t)g.n_seq * 2 - 1) + (has_sentinel ? 1 : 0);
+		cub::DoubleBuffer<uint64_t> dk(key, key2), dv(val, val2);
+		size_t tb = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)n_in, 0, (int)end_bit, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int)n_in, 0, (int)end_bit, d.stream);
+		++d.n_lib;
+		if (n_real) MAB_LAUNCH(d, k_arc_merge, mab_grid(n_real, 256), 256, 0, dk.Current(), dv.Current(), n_real, lb, g.arc);
+	} else if (n_real) MAB_LAUNCH(d, k_arc_merge, 1, 32, 0, key, val, n_real, lb, g.arc);
+	g.n_arc = n_real, g.is_srt = true, g.has_idx = false;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -289,7 +321,7 @@ __device__ __forceinline__ uint32_t dt_hash(uint32_t x, uint32_t mask) { return 
 // 1 = target of v, 2 = reduced) | slot (table slot of slab entry i).  The mark lives in the table, so arcs to the same
 // target share it exactly like mark[] indexed by vertex does in the reference.
 template <bool STATS>
-__global__ void __launch_bounds__(DT_WARPS * 32)
+__global__ void __launch_bounds__(DT_WARPS * 32, 6)
 k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, const uint32_t *__restrict__ seq,
                  uint32_t n_vtx, uint32_t fuzz, uint8_t *__restrict__ flag,
                  uint32_t *__restrict__ big_list, unsigned long long *scal)
@@ -325,21 +357,38 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 		if (mask == 31) hkey[lane] = DT_EMPTY;
 		else for (uint32_t i = lane * 4; i <= mask; i += 128) *reinterpret_cast<uint4*>(hkey + i) = make_uint4(DT_EMPTY, DT_EMPTY, DT_EMPTY, DT_EMPTY);
 		__syncwarp();
-		// stage the slab and build the target table in one sweep
+		// stage the slab and build the target table in one sweep; every lane carries two slab entries per
+		// iteration (i and i+32), so slabs of up to 64 arcs -- nearly all of them -- take a single iteration
 		bool dup = false;
-		const DArc *pv = arc + off + lane;
-		for (uint32_t i = lane; i < nv; i += 32, pv += 32) {
-			const uint4 a = ld_arc4(pv);       // x = len, z = target
-			tl[i] = a.x;
-			if (i < DT_EAGER) ti[i] = __ldg(idx + a.z);
-			uint32_t h = dt_hash(a.z, mask);
-			for (;;) {
-				const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a.z);
-				if (prev == DT_EMPTY) { hmark[h] = 1; break; }
-				if (prev == a.z) { dup = true; break; }
-				h = (h + 1) & mask;
+		for (uint32_t base = 0; base < nv; base += 64) {
+			const uint32_t i0 = base + lane, i1 = i0 + 32;
+			const bool v0 = i0 < nv, v1 = i1 < nv;
+			uint4 a0, a1;
+			if (v0) a0 = ld_arc4(arc + off + i0);       // x = len, z = target
+			if (v1) a1 = ld_arc4(arc + off + i1);
+			if (v0) {
+				tl[i0] = a0.x;
+				if (i0 < DT_EAGER) ti[i0] = __ldg(idx + a0.z);
+				uint32_t h = dt_hash(a0.z, mask);
+				for (;;) {
+					const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a0.z);
+					if (prev == DT_EMPTY) { hmark[h] = 1; break; }
+					if (prev == a0.z) { dup = true; break; }
+					h = (h + 1) & mask;
+				}
+				slot[i0] = (uint8_t)h;
 			}
-			slot[i] = (uint8_t)h;
+			if (v1) {
+				tl[i1] = a1.x;
+				uint32_t h = dt_hash(a1.z, mask);
+				for (;;) {
+					const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a1.z);
+					if (prev == DT_EMPTY) { hmark[h] = 1; break; }
+					if (prev == a1.z) { dup = true; break; }
+					h = (h + 1) & mask;
+				}
+				slot[i1] = (uint8_t)h;
+			}
 		}
 		const bool has_dup = __any_sync(0xffffffffu, dup); // multi-arcs: several slab entries share one mark
 		__syncwarp();
@@ -347,11 +396,13 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 		// i ascends over the slab entries whose target still carries mark 1 (asg.c:164-168); found by ballot
 		for (uint32_t i = 0;;) {
 			uint32_t nxt = nv;
-			for (uint32_t base = i & ~31u; base < nv; base += 32) {
-				const uint32_t k = base + lane;
-				const bool live = k >= i && k < nv && hmark[slot[k]] == 1;
-				const unsigned m = __ballot_sync(0xffffffffu, live);
-				if (m) { nxt = base + __ffs(m) - 1; break; }
+			for (uint32_t base = i & ~63u; base < nv; base += 64) {
+				const uint32_t k0 = base + lane, k1 = k0 + 32;
+				const bool l0 = k0 >= i && k0 < nv && hmark[slot[k0]] == 1;
+				const bool l1 = k1 >= i && k1 < nv && hmark[slot[k1]] == 1;
+				const unsigned m0 = __ballot_sync(0xffffffffu, l0), m1 = __ballot_sync(0xffffffffu, l1);
+				if (m0) { nxt = base + __ffs(m0) - 1; break; }
+				if (m1) { nxt = base + 32 + __ffs(m1) - 1; break; }
 			}
 			if (nxt >= nv) break;
 			i = nxt;
@@ -359,27 +410,36 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 			const uint64_t iw = i < DT_EAGER ? ti[i] : __ldg(idx + w);
 			const uint32_t nw = (uint32_t)iw;
 			const DArc *pw = arc + (iw >> 32) + lane;
-			for (uint32_t j0 = 0; j0 < nw; j0 += 32, pw += 32) {
-				uint32_t x = 0;
-				bool ok = false;
-				if (j0 + lane < nw) {
-					const uint4 a = ld_arc4(pw);
-					ok = (a.x + li <= L);
-					x = a.z;
-				}
-				const unsigned okm = __ballot_sync(0xffffffffu, ok);
-				const unsigned pre = okm == 0xffffffffu ? okm : ((1u << (__ffs(~okm) - 1)) - 1); // lanes before the first failure
-				if (pre >> lane & 1) {
-					uint32_t h = dt_hash(x, mask);
+			for (uint32_t j0 = 0; j0 < nw; j0 += 64, pw += 64) {
+				const bool in0 = j0 + lane < nw, in1 = j0 + 32 + lane < nw;
+				uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
+				if (in0) a0 = ld_arc4(pw);
+				if (in1) a1 = ld_arc4(pw + 32);
+				const bool ok0 = in0 && a0.x + li <= L, ok1 = in1 && a1.x + li <= L;
+				const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
+				// the scan of the reference stops at the first j that violates the bound: entries before it, in slab order
+				const unsigned pre0 = m0 == 0xffffffffu ? m0 : ((1u << (__ffs(~m0) - 1)) - 1);
+				const unsigned pre1 = m0 != 0xffffffffu ? 0u : (m1 == 0xffffffffu ? m1 : ((1u << (__ffs(~m1) - 1)) - 1));
+				if (pre0 >> lane & 1) {
+					uint32_t h = dt_hash(a0.z, mask);
 					for (;;) {
 						const uint32_t kx = hkey[h];
-						if (kx == x) { hmark[h] = 2; break; }
+						if (kx == a0.z) { hmark[h] = 2; break; }
 						if (kx == DT_EMPTY) break;
 						h = (h + 1) & mask;
 					}
 				}
-				if (STATS && lane == 0) n_inner += __popc(pre);
-				if (okm != 0xffffffffu) break;
+				if (pre1 >> lane & 1) {
+					uint32_t h = dt_hash(a1.z, mask);
+					for (;;) {
+						const uint32_t kx = hkey[h];
+						if (kx == a1.z) { hmark[h] = 2; break; }
+						if (kx == DT_EMPTY) break;
+						h = (h + 1) & mask;
+					}
+				}
+				if (STATS && lane == 0) n_inner += __popc(pre0) + __popc(pre1);
+				if (m0 != 0xffffffffu || m1 != 0xffffffffu) break;
 			}
 			__syncwarp();
 			++i;
@@ -402,7 +462,7 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 	n_red = __reduce_add_sync(0xffffffffu, n_red);
 	if (lane == 0) {
 		if (n_red) atomicAdd(scal + SC_COUNT, (unsigned long long)n_red);
-		if (n_inner) atomicAdd(scal + SC_AUX, n_inner);
+		if (STATS && n_inner) atomicAdd(scal + SC_AUX, n_inner);
 	}
 }
 

@@ -755,9 +755,11 @@ __global__ void k_seq_set(uint32_t n_seq, const uint32_t *len, const uint8_t *de
 	if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_len, mx);
 }
 
-__global__ void k_sg_arcs(const DHit *a, size_t n, uint32_t *seq, HitArcParams p, DArc *arc, uint8_t *flag, unsigned *max_len)
+// one (key, value) column pair per hit: key = u << lb | len (or the sentinel 1 << (lb + vertex bits) when the hit yields no arc),
+// value = ol:del << 32 | v.  Sorting the columns (stable) and dropping the sentinels equals asg.c's append + sort.
+__global__ void k_sg_arcs(const DHit *a, size_t n, uint32_t *seq, HitArcParams p, uint32_t lb, uint64_t sentinel, uint64_t *key, uint64_t *val, unsigned long long *n_emit)
 {
-	unsigned mx = 0;
+	unsigned cnt = 0;
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
 		DHit h = ld_hit(a + i);
 		const uint32_t qn = (uint32_t)(h.qns >> 32);
@@ -770,14 +772,12 @@ __global__ void k_sg_arcs(const DHit *a, size_t n, uint32_t *seq, HitArcParams p
 				if ((uint32_t)h.qns == h.ts && h.qe == h.te && (h.ml_rev >> 31)) atomicOr(&seq[qn], MAB_DEL_BIT);
 			} else emit = true;
 		} else if (r == MAB_HT_QCONT) atomicOr(&seq[qn], MAB_DEL_BIT);
-		flag[i] = emit;
-		if (emit) {
-			*reinterpret_cast<uint4*>(arc + i) = make_uint4((uint32_t)t.ul, (uint32_t)(t.ul >> 32), t.v, t.ol_del);
-			mx = (uint32_t)t.ul > mx ? (uint32_t)t.ul : mx;
-		}
+		key[i] = emit ? ((t.ul >> 32) << lb | (uint32_t)t.ul) : sentinel;
+		val[i] = (uint64_t)t.ol_del << 32 | t.v;
+		cnt += emit;
 	}
-	mx = __reduce_max_sync(0xffffffffu, mx);
-	if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_len, mx);
+	cnt = __reduce_add_sync(0xffffffffu, cnt);
+	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_emit, (unsigned long long)cnt);
 }
 
 void dh_sg_gen(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *del, const HitArcParams &p, DGraph &g)
@@ -786,28 +786,21 @@ void dh_sg_gen(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *de
 	dg_set_nseq(d, g, n_seq);
 	g.n_arc = 0, g.is_srt = false, g.is_symm = false, g.has_idx = false;
 	d.zero_scal(SC_AUX);
+	d.zero_scal(SC_COUNT);
 	unsigned *d_max = (unsigned*)(d.d_scal + SC_AUX);
 	if (n_seq) MAB_LAUNCH(d, k_seq_set, mab_grid(n_seq, 256), 256, 0, n_seq, len, del, g.seq, d_max);
+	const unsigned mx = (unsigned)(d.get_scal(SC_AUX) & 0xffffffffu); // an arc is never longer than its source read (miniasm.h:97-98)
+	const uint32_t lb = bits_for(mx);
 	if (h.n) {
 		if (h.n >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 arcs on one GPU\n"); exit(73); }
-		dg_reserve(d, g, h.n);
-		uint8_t *flag = mab_alloc<uint8_t>(d, h.n);
+		const uint64_t sentinel = 1ull << (lb + bits_for((uint64_t)n_seq * 2 - 1));
+		uint64_t *ka = mab_alloc<uint64_t>(d, h.n), *kb = mab_alloc<uint64_t>(d, h.n), *va = mab_alloc<uint64_t>(d, h.n), *vb = mab_alloc<uint64_t>(d, h.n);
 		// seq lengths are read while other threads may set del bits: lengths are masked, so this is benign
-		MAB_LAUNCH(d, k_sg_arcs, mab_grid(h.n, 256), 256, 0, h.a, h.n, g.seq, p, g.arc2, flag, d_max);
-		size_t tb = 0;
-		unsigned long long *d_n = d.d_scal + SC_NSEL;
-		cub::DeviceSelect::Flagged(nullptr, tb, g.arc2, flag, g.arc, d_n, (int64_t)h.n, d.stream);
-		void *tmp = d.tmp(tb);
-		cub::DeviceSelect::Flagged(tmp, tb, g.arc2, flag, g.arc, d_n, (int64_t)h.n, d.stream);
-		++d.n_lib;
-		g.n_arc = (uint32_t)d.get_scal(SC_NSEL);
-		d.free(flag);
-	} else {
-		dg_reserve(d, g, 1);
-		d.get_scal(SC_AUX);
-	}
-	unsigned mx = (unsigned)(d.h_scal[SC_AUX] & 0xffffffffu);
-	g.len_bits = bits_for(mx);
+		MAB_LAUNCH(d, k_sg_arcs, mab_grid(h.n, 256), 256, 0, h.a, h.n, g.seq, p, lb, sentinel, ka, va, d.d_scal + SC_COUNT);
+		const uint32_t n_arc = (uint32_t)d.get_scal(SC_COUNT);
+		dg_build_sorted(d, g, ka, va, kb, vb, (uint32_t)h.n, n_arc, lb, true);
+		d.free(ka); d.free(kb); d.free(va); d.free(vb);
+	} else dg_reserve(d, g, 1);
 	dg_cleanup(d, g);
 	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", g.n_arc);
 }

@@ -101,23 +101,27 @@ __device__ __forceinline__ uint64_t fmix64(uint64_t k)
 	return k;
 }
 
-// strtol(field, 0, 10) narrowed to uint32, on the byte range [p, e)
+// strtol(field, 0, 10) narrowed to uint32, on the byte range [p, e).  Up to 18 significant digits cannot
+// overflow a long, so the common path is one multiply-add per digit; only longer digit strings take the clamping
+// path (LONG_MAX / LONG_MIN, then truncation to 32 bits, as the reference's assignment does).
 __device__ __forceinline__ uint32_t field_to_u32(const char *p, const char *e)
 {
 	while (p < e && (*p == ' ' || (*p >= '\t' && *p <= '\r'))) ++p;
 	bool neg = false;
 	if (p < e && (*p == '-' || *p == '+')) neg = *p == '-', ++p;
+	while (p < e && *p == '0') ++p;                    // leading zeros carry no value
 	unsigned long long v = 0;
-	bool ovf = false;
-	const unsigned long long lim = neg ? 9223372036854775808ull : 9223372036854775807ull;
-	for (; p < e && *p >= '0' && *p <= '9'; ++p) {
-		unsigned dgt = *p - '0';
-		if (!ovf && v > (lim - dgt) / 10) ovf = true;
-		if (!ovf) v = v * 10 + dgt;
+	int nd = 0;
+	for (; p < e; ++p, ++nd) {
+		const unsigned dgt = (unsigned)(*p - '0');
+		if (dgt > 9) break;
+		if (nd < 18) { v = v * 10 + dgt; continue; }
+		const unsigned long long lim = neg ? 9223372036854775808ull : 9223372036854775807ull; // rare: 19+ digits
+		if (v > (lim - dgt) / 10) { v = lim; while (p < e && (unsigned)(*p - '0') <= 9) ++p; break; }
+		v = v * 10 + dgt;
 	}
-	if (ovf) v = lim;                                   // LONG_MAX / LONG_MIN clamp
-	long long s = neg ? (long long)(0ull - v) : (long long)v;
-	return (uint32_t)s;
+	const long long sv = neg ? (long long)(0ull - v) : (long long)v;
+	return (uint32_t)sv;
 }
 
 // parse one line [p, e) (no terminator, '\r' already dropped); names are hashed with FNV-1a + fmix64
