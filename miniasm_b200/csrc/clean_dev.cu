@@ -761,8 +761,10 @@ __global__ void k_ug_mark(const DUtgMeta *meta, uint32_t n_utg, int32_t *mark)
 {
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_utg; i += gridDim.x * blockDim.x) {
 		if (meta[i].circ) continue;
-		mark[meta[i].start] = (int32_t)(i << 1 | 0);
-		mark[meta[i].end] = (int32_t)(i << 1 | 1); // written second: wins if start == end, like the sequential loop
+		// The sequential loop (asm.c:182-186) lets the last write win when walks on a non-symmetric graph share an end
+		// vertex, or when start == end; "last" = larger unitig index, end after start = the larger value: atomicMax.
+		atomicMax(&mark[meta[i].start], (int32_t)(i << 1 | 0));
+		atomicMax(&mark[meta[i].end], (int32_t)(i << 1 | 1));
 	}
 }
 
