@@ -95,7 +95,7 @@ struct IsLineStart {
 	__device__ __forceinline__ bool operator()(uint64_t p) const { return p == 0 || text[p - 1] == '\n'; }
 };
 
-__device__ __forceinline__ uint64_t fmix64(uint64_t k)
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t k)
 {
 	k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
 	return k;
@@ -130,7 +130,7 @@ __device__ __forceinline__ uint32_t field_to_u32(const char *p, const char *e)
 // strtol(.,10): leading white space, optional sign, digits, stop at the first other byte; clamped to LONG_MIN/MAX
 // and truncated to 32 bits like the reference's assignment.  Names are hashed with FNV-1a 64 + fmix64.
 // vals: this lane's column of a [11][32] shared-memory scratch (numeric results by PAF column).
-__device__ __forceinline__ void parse_line(const char *p, const char *e, uint64_t seed, PLine &r, bool &too_long, uint32_t *vals)
+__host__ __device__ __forceinline__ void parse_line(const char *p, const char *e, uint64_t seed, PLine &r, bool &too_long, uint32_t *vals)
 {
 	const uint64_t h0 = 1469598103934665603ULL ^ seed;
 	uint64_t cur = 0, h = h0, hq = 0, ht = 0;
@@ -515,4 +515,19 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 	// (6) ma_hit_sort
 	dh_sort(d, h, st.max_qs_bits);
 	d.trace("ingest:sort_hits");
+}
+
+// Host-side probe of the device parser (same source, compiled for the host): lets the CPU test tier compare the
+// lockstep parser with the host reader on corner-case lines without a GPU.  out = nf ql qs qe rev tl ts te ml bl qnl tnl tdelta.
+extern "C" int mab_test_parse_line(const char *line, size_t len, uint32_t *out)
+{
+	static uint32_t vals[11 * 32];
+	PLine r;
+	bool too_long = false;
+	size_t eol = len;
+	if (eol > 1 && line[eol - 1] == '\r') --eol;
+	parse_line(line, line + eol, 0, r, too_long, vals);
+	out[0] = r.nf, out[1] = r.ql, out[2] = r.qs, out[3] = r.qe, out[4] = r.ml_rev >> 31, out[5] = r.tl, out[6] = r.ts, out[7] = r.te;
+	out[8] = r.ml_rev & 0x7fffffffu, out[9] = r.bl, out[10] = r.qnl, out[11] = r.tnl, out[12] = r.tdelta;
+	return too_long ? -1 : 0;
 }

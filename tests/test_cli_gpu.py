@@ -33,7 +33,11 @@ def same(args, exact=True):
     if exact:
         assert out_c == out_r
     else:  # outputs whose line order depends on ties of the reference's unstable radix sort
-        assert sorted(out_c.splitlines()) == sorted(out_r.splitlines())
+        a, b = sorted(out_c.splitlines()), sorted(out_r.splitlines())
+        if a != b:
+            sa, sb = set(a), set(b)
+            only_c, only_r = sorted(sa - sb)[:5], sorted(sb - sa)[:5]
+            raise AssertionError(f"{len(a)} vs {len(b)} lines; only ours: {only_c}; only reference: {only_r}")
     return out_c
 
 
@@ -107,7 +111,7 @@ def test_weird_lines(paf_dir):
         if not ln:
             continue
         f = ln.rstrip(b"\r").split(b"\t")
-        if i % 11 == 0:
+        if i % 11 == 0 and i > 0:                             # (not the first line: there the reference's bl is uninitialised stack memory)
             out.append(b"\t".join(f[:10]))                    # 10 fields: bl stays stale
         elif i % 13 == 0:
             out.append(b"\t".join(f[:9]))                     # too short: skipped
