@@ -321,7 +321,7 @@ def main():
             "del_trans": {"n_arc_in": n_arc_in, "inner_iters": inner, "n_vtx": n_vtx, "kernel_ms": dt_ms_trans},
             "phase_ms_last_step": {"ingest": st.ms_ingest, "select": st.ms_select, "layout": st.ms_layout, "unitigs": st.ms_unitigs},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_del_trans_half",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_del_trans_warp",
                          "algorithmic_bytes": alg_bytes, "formula": "16*n_arc + 16*inner_iters + 1*n_arc + 12*n_vtx"},
             "cpu_baseline": cpu, "clocks": clocks, "wall_s_timed_region": wall_dev, "wall_ms_per_step": wall_dev / a.steps * 1e3,
         }))

@@ -467,171 +467,6 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 	}
 }
 
-// ---- half-warp variant: two vertices per warp, slabs of up to DH_MAXD arcs -----------------------------------
-// ncu on the warp-per-vertex kernel: ~460 issue slots per vertex of which only ~15 % are the vectorised per-arc
-// work; the rest is per-vertex bookkeeping executed by a whole warp.  Here 16 lanes own one vertex (typical slabs
-// hold ~50 arcs = 4 entries per lane, kept in registers), so every bookkeeping instruction serves two vertices and
-// shared memory shrinks to the 128-slot target table per vertex.  Tables are emptied by un-writing the slots used.
-constexpr int DH_WARPS = 8;
-constexpr int DH_MAXD = 64;
-constexpr int DH_HASH = 128;
-
-template <bool STATS>
-__global__ void __launch_bounds__(DH_WARPS * 32)
-k_del_trans_half(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, const uint32_t *__restrict__ seq,
-                 uint32_t n_vtx, uint32_t fuzz, uint8_t *__restrict__ flag, uint32_t *__restrict__ med_list, unsigned long long *scal)
-{
-	__shared__ uint32_t s_hkey[DH_WARPS * 2][DH_HASH];
-	__shared__ uint8_t s_hmark[DH_WARPS * 2][DH_HASH];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
-	const unsigned hmask = 0xffffu << (half * 16);
-	uint32_t *hkey = s_hkey[warp * 2 + half];
-	uint8_t *hmark = s_hmark[warp * 2 + half];
-	for (int i = hl; i < DH_HASH; i += 16) hkey[i] = DT_EMPTY;
-	__syncwarp();
-	unsigned n_red = 0;
-	unsigned long long n_inner = 0;
-	const uint32_t n_pair = (n_vtx + 1) >> 1;
-	for (uint32_t pr = blockIdx.x * DH_WARPS + warp; pr < n_pair; pr += gridDim.x * DH_WARPS) {
-		const uint32_t v = 2 * pr + half;
-		uint64_t iv = 0;
-		if (v < n_vtx) iv = __ldg(idx + v);
-		uint32_t nv = (uint32_t)iv;
-		const uint32_t off = (uint32_t)(iv >> 32);
-		if (nv && (__ldg(seq + (v >> 1)) & MAB_DEL_BIT)) { // deleted read: every arc goes (asg.c:158-161)
-			for (uint32_t i = hl; i < nv; i += 16) flag[off + i] = 1;
-			if (hl == 0) n_red += nv;
-			nv = 0;
-		}
-		if (nv > DH_MAXD) { // longer slab: left to the warp kernel
-			if (hl == 0) med_list[atomicAdd(scal + SC_TMP0, 1ull)] = v;
-			nv = 0;
-		}
-		if (__ballot_sync(0xffffffffu, nv != 0) == 0) continue;
-		// own slab -> registers (entry e = k*16 + hl), targets -> table
-		uint32_t tgt[4], len[4], slt[4];
-		bool dup = false;
-		#pragma unroll
-		for (int k = 0; k < 4; ++k) {
-			const uint32_t e = k * 16 + hl;
-			tgt[k] = 0, len[k] = 0, slt[k] = 0;
-			if (e < nv) {
-				const uint4 a = ld_arc4(arc + off + e);
-				tgt[k] = a.z, len[k] = a.x;
-			}
-		}
-		#pragma unroll
-		for (int k = 0; k < 4; ++k) {
-			const uint32_t e = k * 16 + hl;
-			if (e < nv) {
-				uint32_t h = dt_hash(tgt[k], DH_HASH - 1);
-				for (;;) {
-					const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, tgt[k]);
-					if (prev == DT_EMPTY) { hmark[h] = 1; break; }
-					if (prev == tgt[k]) { dup = true; break; }
-					h = (h + 1) & (DH_HASH - 1);
-				}
-				slt[k] = h;
-			}
-		}
-		const bool has_dup = (__ballot_sync(0xffffffffu, dup) & hmask) != 0;
-		__syncwarp();
-		if (has_dup) { // multi-arcs need the lowest-slab-position rule of asg.c:181-184: the warp kernel implements it
-			#pragma unroll
-			for (int k = 0; k < 4; ++k) if (k * 16 + hl < nv) hkey[slt[k]] = DT_EMPTY;
-			if (hl == 0) med_list[atomicAdd(scal + SC_TMP0, 1ull)] = v;
-			nv = 0;
-		}
-		__syncwarp();
-		// L = longest arc + fuzz: entry nv-1
-		uint32_t L;
-		{
-			const uint32_t e = nv ? nv - 1 : 0, k = e >> 4;
-			const uint32_t mine = k == 0 ? len[0] : k == 1 ? len[1] : k == 2 ? len[2] : len[3];
-			L = __shfl_sync(0xffffffffu, mine, e & 15, 16) + fuzz;
-		}
-		// sequential part: i ascends over entries whose target still carries mark 1
-		for (uint32_t i = 0;;) {
-			uint32_t nxt = 0xffffffffu;
-			#pragma unroll
-			for (int k = 3; k >= 0; --k) {
-				const uint32_t e = k * 16 + hl;
-				const bool live = e >= i && e < nv && hmark[slt[k]] == 1;
-				const unsigned m = (__ballot_sync(0xffffffffu, live) & hmask) >> (half * 16);
-				if (m) nxt = k * 16 + __ffs(m) - 1;
-			}
-			const bool go = nxt != 0xffffffffu; // uniform within the half
-			if (__ballot_sync(0xffffffffu, go) == 0) break;
-			i = go ? nxt : i;
-			// fetch target / length of entry i from the lane that owns it
-			const uint32_t k = i >> 4;
-			const uint32_t wt = k == 0 ? tgt[0] : k == 1 ? tgt[1] : k == 2 ? tgt[2] : tgt[3];
-			const uint32_t wl = k == 0 ? len[0] : k == 1 ? len[1] : k == 2 ? len[2] : len[3];
-			const uint32_t w = __shfl_sync(0xffffffffu, wt, i & 15, 16), li = __shfl_sync(0xffffffffu, wl, i & 15, 16);
-			uint64_t iw = 0;
-			if (go) iw = __ldg(idx + w);
-			const uint32_t nw = go ? (uint32_t)iw : 0;
-			const DArc *pw = arc + (iw >> 32) + hl;
-			uint32_t j0 = 0;
-			bool more = nw != 0;
-			while (__ballot_sync(0xffffffffu, more)) { // both halves step together; a finished half idles
-				const bool in0 = more && j0 + hl < nw, in1 = more && j0 + 16 + hl < nw;
-				uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
-				if (in0) a0 = ld_arc4(pw);
-				if (in1) a1 = ld_arc4(pw + 16);
-				const bool ok0 = in0 && a0.x + li <= L, ok1 = in1 && a1.x + li <= L;
-				const unsigned m0 = (__ballot_sync(0xffffffffu, ok0) >> (half * 16)) & 0xffffu;
-				const unsigned m1 = (__ballot_sync(0xffffffffu, ok1) >> (half * 16)) & 0xffffu;
-				// the reference stops at the first j violating the bound: entries before it, in slab order
-				const unsigned pre0 = m0 == 0xffffu ? m0 : ((1u << (__ffs(~m0) - 1)) - 1);
-				const unsigned pre1 = m0 != 0xffffu ? 0u : (m1 == 0xffffu ? m1 : ((1u << (__ffs(~m1) - 1)) - 1));
-				if (pre0 >> hl & 1) {
-					uint32_t h = dt_hash(a0.z, DH_HASH - 1);
-					for (;;) {
-						const uint32_t kx = hkey[h];
-						if (kx == a0.z) { hmark[h] = 2; break; }
-						if (kx == DT_EMPTY) break;
-						h = (h + 1) & (DH_HASH - 1);
-					}
-				}
-				if (pre1 >> hl & 1) {
-					uint32_t h = dt_hash(a1.z, DH_HASH - 1);
-					for (;;) {
-						const uint32_t kx = hkey[h];
-						if (kx == a1.z) { hmark[h] = 2; break; }
-						if (kx == DT_EMPTY) break;
-						h = (h + 1) & (DH_HASH - 1);
-					}
-				}
-				if (STATS && hl == 0 && more) n_inner += __popc(pre0) + __popc(pre1);
-				j0 += 32, pw += 32;
-				more = more && m0 == 0xffffu && m1 == 0xffffu && j0 < nw;
-			}
-			__syncwarp();
-			i = go ? i + 1 : i;
-		}
-		#pragma unroll
-		for (int k = 0; k < 4; ++k) {
-			const uint32_t e = k * 16 + hl;
-			if (e < nv) {
-				const bool r = hmark[slt[k]] == 2;
-				flag[off + e] = r;
-				n_red += r;
-			}
-		}
-		__syncwarp();
-		// empty the table again: every lane un-writes the slots of its own entries
-		#pragma unroll
-		for (int k = 0; k < 4; ++k) if (k * 16 + hl < nv) hkey[slt[k]] = DT_EMPTY;
-		__syncwarp();
-	}
-	n_red = __reduce_add_sync(0xffffffffu, n_red);
-	if (lane == 0) {
-		if (n_red) atomicAdd(scal + SC_COUNT, (unsigned long long)n_red);
-		if (STATS && n_inner) atomicAdd(scal + SC_AUX, n_inner);
-	}
-}
-
 // CTA per vertex, slabs of DT_MAXD < nv <= DT_BIG_MAXD.  Dynamic shared memory:
 //   tv[DT_BIG_MAXD] | hash[2*DT_BIG_MAXD] | fmin[DT_BIG_MAXD] | rep (u16)[DT_BIG_MAXD] | st (u8)[DT_BIG_MAXD]
 constexpr int DT_BIG_MAXD = 8192;
@@ -801,21 +636,12 @@ uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz)
 		cudaEvent_t e0, e1;
 		MAB_CUDA(cudaEventCreate(&e0)); MAB_CUDA(cudaEventCreate(&e1));
 		MAB_CUDA(cudaEventRecord(e0, d.stream));
-		// two vertices per warp for slabs up to DH_MAXD arcs; longer ones (and slabs with multi-arcs) are queued
-		uint32_t *med = mab_alloc<uint32_t>(d, n_vtx);
-		unsigned grid = ((n_vtx + 1) / 2 + DH_WARPS - 1) / DH_WARPS;
+		unsigned grid = (n_vtx + DT_WARPS - 1) / DT_WARPS;
 		if (grid > 148u * 64u) grid = 148u * 64u;
-		if (mab_del_trans_count_inner) MAB_LAUNCH(d, k_del_trans_half<true>, grid, DH_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, med, d.d_scal);
-		else MAB_LAUNCH(d, k_del_trans_half<false>, grid, DH_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, med, d.d_scal);
+		// the inner-iteration counter (for the roofline arithmetic) costs issue slots: only counted when asked for
+		if (mab_del_trans_count_inner) MAB_LAUNCH(d, k_del_trans_warp<true>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr);
+		else MAB_LAUNCH(d, k_del_trans_warp<false>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr);
 		MAB_CUDA(cudaEventRecord(e1, d.stream));
-		const uint32_t n_med = (uint32_t)d.get_scal(SC_TMP0);
-		if (n_med) { // warp per vertex: slabs of 65..128 arcs, multi-arc slabs; longer ones go on to big[]
-			unsigned g2 = (n_med + DT_WARPS - 1) / DT_WARPS;
-			if (g2 > 148u * 64u) g2 = 148u * 64u;
-			if (mab_del_trans_count_inner) MAB_LAUNCH(d, k_del_trans_warp<true>, g2, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_med, fuzz, flag, big, d.d_scal, med);
-			else MAB_LAUNCH(d, k_del_trans_warp<false>, g2, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_med, fuzz, flag, big, d.d_scal, med);
-		}
-		d.free(med);
 		uint32_t n_big = (uint32_t)d.get_scal(SC_BIG);
 		float ms = 0;
 		MAB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
