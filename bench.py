@@ -46,14 +46,14 @@ class PafgenOpt(C.Structure):
                 ("min_olap", C.c_uint32), ("jitter", C.c_uint32), ("seed", C.c_uint64),
                 ("n_hot", C.c_uint32), ("hot_reads", C.c_uint32), ("hot_span", C.c_uint32),
                 ("dup_ppm", C.c_uint32), ("self_ppm", C.c_uint32), ("internal_ppm", C.c_uint32), ("lowid_ppm", C.c_uint32),
-                ("shuffle", C.c_uint32), ("flip_ppm", C.c_uint32)]
+                ("shuffle", C.c_uint32), ("flip_ppm", C.c_uint32), ("name_base", C.c_uint32)]
 
 
 class PafgenStat(C.Structure):
     _fields_ = [("n_lines", C.c_uint64), ("n_bytes", C.c_uint64), ("genome_len", C.c_uint64), ("n_reads_total", C.c_uint32)]
 
 
-def generate(n_reads, seed):
+def generate(n_reads, seed, name_base=0):
     """PAF text in C heap memory: (pointer, n_bytes, n_lines, free_fn)."""
     synth.build()
     lib = C.CDLL(synth.LIB)
@@ -63,7 +63,7 @@ def generate(n_reads, seed):
     lib.pafgen_free.argtypes = [C.c_void_p]
     o, st, buf = PafgenOpt(), PafgenStat(), C.c_void_p()
     lib.pafgen_defaults(C.byref(o))
-    o.n_reads, o.seed = n_reads, seed
+    o.n_reads, o.seed, o.name_base = n_reads, seed, name_base
     n = lib.pafgen_generate(C.byref(o), C.byref(buf), C.byref(st))
     return buf, n, st.n_lines, lambda: lib.pafgen_free(buf)
 
@@ -192,23 +192,35 @@ def main():
     lib.set_verbose(0)
     ctx = lib.mab_create(local_rank)
     opt = lib.default_opt()
+    if world > 1:
+        from miniasm_b200 import sharded
+        sharded.init(lib, ctx, rank, world)        # NCCL communicator inside the library (id handed over through torch.distributed)
 
-    # each rank owns an independent partition of the read set (its own PAF of the named shape): weak scaling
-    buf, n_bytes, n_lines, free = generate(wl["n_reads"], wl["seed"] + 1000 * rank)
+    # Weak scaling: the job's PAF is the concatenation of one partition of the named shape per rank (disjoint read names,
+    # rank order = file order); rank r holds byte range r.  N > 1 runs the hash-sharded pipeline: reads are owned by
+    # id mod N, hits travel in an NCCL all-to-all, interval tables / flags are all-reduced, arcs all-gathered.
+    buf, n_bytes, n_lines, free = generate(wl["n_reads"], wl["seed"] + 1000 * rank, name_base=rank * 100_000_000)
     pinned = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
     C.memmove(pinned.data_ptr(), buf, n_bytes)
     free()
     devnull = capi._libc.fopen(b"/dev/null", b"w")
 
     def device_steps():
-        lib.mab_ingest(ctx, opt.min_span, opt.min_match, 1)
-        lib.mab_select(ctx, C.byref(opt), 0, 0, 100)
-        lib.mab_layout(ctx, C.byref(opt), 100)
+        if world > 1:
+            lib.mab_ingest_sharded(ctx, opt.min_span, opt.min_match, 1)
+            lib.mab_select_sharded(ctx, C.byref(opt))
+            lib.mab_layout_sharded(ctx, C.byref(opt))
+        else:
+            lib.mab_ingest(ctx, opt.min_span, opt.min_match, 1)
+            lib.mab_select(ctx, C.byref(opt), 0, 0, 100)
+            lib.mab_layout(ctx, C.byref(opt), 100)
         lib.mab_unitigs(ctx)
 
     def e2e_step():
         lib.mab_load_paf_text(ctx, pinned.data_ptr(), n_bytes)            # H2D
         device_steps()
+        if rank != 0:                                                      # the result is replicated; rank 0 writes it
+            return 0
         d, sub, ug = lib.mab_export_dict(ctx), lib.mab_export_sub(ctx), lib.mab_export_ug(ctx)   # D2H
         lib.ma_ug_print(ug, d, sub, devnull)                               # GFA text (host C writer)
         nb = 0
@@ -229,7 +241,7 @@ def main():
     lib.mab_load_paf_text(ctx, pinned.data_ptr(), n_bytes)
     lib.mab_count_del_trans_inner(1)          # one untimed pass with the instrumented kernel: inner-loop iterations I
     device_steps()
-    inner = lib.mab_stats(ctx).contents.trans_inner
+    inner = lib.mab_stats(ctx).contents.trans_inner   # (N > 1: this rank's share of the vertices)
     lib.mab_count_del_trans_inner(0)
     for _ in range(a.warmup):
         device_steps()
@@ -254,7 +266,7 @@ def main():
     launches, libcalls = st.n_kernel_launches - launches0, st.n_lib_calls - libcalls0
     dev_ms = sum(x[0] for x in dt_ms)
     dt_ms_trans = sum(x[1] for x in dt_ms) / len(dt_ms)
-    n_arc_in, n_vtx = st.n_arc_trans_in, 2 * st.n_seq_final
+    n_arc_in, n_vtx = st.n_arc_trans_in, 2 * st.n_seq_final // world   # per rank: the vertices this rank reduces
 
     # ---- e2e: host buffers in, host structures + GFA text out --------------------------------------
     for _ in range(min(a.warmup, 2)):
@@ -313,7 +325,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int64/uint32 (+3 float32 predicates)", "data": "synthetic",
             "config": {"workload": wl["label"], "name": a.workload, "paf_lines_per_gpu": n_lines, "paf_bytes_per_gpu": n_bytes,
                        "l2": "inputs larger than L2 (PAF text and hit arrays are GBs; no flush needed)",
-                       "parallelism": f"{world} independent read partitions, one per GPU, no data-path collective" if world > 1 else "1 GPU"},
+                       "parallelism": (f"read ids hash-sharded over {world} GPUs (owner = id mod {world}); NCCL all-to-all of hits, all-reduce of "
+                                       f"interval/flag tables, all-gather of names and arcs; one PAF = {world} partitions of the named shape")
+                       if world > 1 else "1 GPU"},
             "e2e": {"value": lines_all * a.steps / e2e_s, "unit": "PAF records/s", "ms_per_step": e2e_s / a.steps * 1e3,
                     "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "lib_calls": libcalls,

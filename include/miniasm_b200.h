@@ -181,6 +181,16 @@ asg_t *mab_export_sg(mab_ctx_t *ctx);
 ma_ug_t *mab_export_ug(mab_ctx_t *ctx);
 float mab_coverage(const mab_ctx_t *ctx);
 
+/* Hash-sharded multi-GPU run (one process per GPU, read r owned by rank r mod world, NCCL on the context's stream).
+ * rank 0: mab_nccl_unique_id -> launcher broadcasts the bytes -> every rank: mab_shard_init.  Each rank loads ITS byte
+ * range of the PAF (ranges in rank order, cut at line ends), then ingest/select/layout_sharded; afterwards every rank
+ * holds the reduced graph of the whole PAF and mab_unitigs / mab_export_* work as in a single-GPU run. */
+int mab_nccl_unique_id(void *out128);
+int mab_shard_init(mab_ctx_t *ctx, int rank, int world, const void *id128);
+int mab_ingest_sharded(mab_ctx_t *ctx, int min_span, int min_match, int bi_dir);
+int mab_select_sharded(mab_ctx_t *ctx, const ma_opt_t *opt);
+int mab_layout_sharded(mab_ctx_t *ctx, const ma_opt_t *opt);
+
 /* timing helpers for bench.py: CUDA events on the context's stream */
 void *mab_event_create(void);
 void mab_event_record(mab_ctx_t *ctx, void *ev);

@@ -163,6 +163,11 @@ _PRODUCT_ONLY = {
     "mab_sync": (None, [C.c_void_p]),
     "mab_last_clean": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "mab_count_del_trans_inner": (None, [C.c_int]),
+    "mab_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "mab_shard_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "mab_ingest_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mab_select_sharded": (C.c_int, [C.c_void_p, C.POINTER(MaOpt)]),
+    "mab_layout_sharded": (C.c_int, [C.c_void_p, C.POINTER(MaOpt)]),
     "mab_set_verbose": (None, [C.c_int]),
     "mab_last_del_trans": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),

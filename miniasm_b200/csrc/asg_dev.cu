@@ -324,8 +324,9 @@ template <bool STATS>
 __global__ void __launch_bounds__(DT_WARPS * 32, 6)
 k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, const uint32_t *__restrict__ seq,
                  uint32_t n_vtx, uint32_t fuzz, uint8_t *__restrict__ flag,
-                 uint32_t *__restrict__ big_list, unsigned long long *scal, const uint32_t *__restrict__ list)
+                 uint32_t *__restrict__ big_list, unsigned long long *scal, const uint32_t *__restrict__ list, uint32_t own_lo, uint32_t own_hi)
 {	// list == nullptr: every vertex 0..n_vtx-1; otherwise the n_vtx vertices named by list[]
+	// [own_lo, own_hi): arc positions this rank is responsible for (sharded runs); a vertex is processed iff its slab starts there
 	__shared__ __align__(16) uint32_t s_hkey[DT_WARPS][DT_HASH];
 	__shared__ uint32_t s_tl[DT_WARPS][DT_MAXD];
 	__shared__ uint32_t s_fmin[DT_WARPS][DT_HASH];
@@ -344,7 +345,7 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 		const uint32_t v = list ? list[vi] : vi;
 		const uint64_t iv = __ldg(idx + v);
 		const uint32_t nv = (uint32_t)iv, off = (uint32_t)(iv >> 32);
-		if (nv == 0) continue;
+		if (nv == 0 || off < own_lo || off >= own_hi) continue;
 		if (__ldg(seq + (v >> 1)) & MAB_DEL_BIT) { // deleted read: every arc goes (asg.c:158-161)
 			for (uint32_t i = lane; i < nv; i += 32) flag[off + i] = 1;
 			if (lane == 0) n_red += nv;
@@ -623,6 +624,21 @@ k_del_trans_huge(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 
 uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz)
 {
+	uint8_t *flag = nullptr;
+	uint32_t n_reduced = dg_del_trans_flags(d, g, fuzz, 0, 0xffffffffu, &flag);
+	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] transitively reduced %d arcs\n", "asg_arc_del_trans", n_reduced);
+	if (n_reduced) {
+		dg_cleanup(d, g, flag);
+		dg_symm(d, g);
+	}
+	d.free(flag);
+	return n_reduced;
+}
+
+// the marking part of asg_arc_del_trans for the vertices whose slabs start in [own_lo, own_hi): one flag byte per arc
+// of those slabs (other positions of *flag_out are not written); returns the number of arcs flagged
+uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo, uint32_t own_hi, uint8_t **flag_out)
+{
 	const uint32_t n_vtx = g.n_seq * 2;
 	uint32_t n_reduced = 0;
 	memset(&g_del_trans_stats, 0, sizeof(g_del_trans_stats));
@@ -639,8 +655,8 @@ uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz)
 		unsigned grid = (n_vtx + DT_WARPS - 1) / DT_WARPS;
 		if (grid > 148u * 64u) grid = 148u * 64u;
 		// the inner-iteration counter (for the roofline arithmetic) costs issue slots: only counted when asked for
-		if (mab_del_trans_count_inner) MAB_LAUNCH(d, k_del_trans_warp<true>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr);
-		else MAB_LAUNCH(d, k_del_trans_warp<false>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr);
+		if (mab_del_trans_count_inner) MAB_LAUNCH(d, k_del_trans_warp<true>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr, own_lo, own_hi);
+		else MAB_LAUNCH(d, k_del_trans_warp<false>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr, own_lo, own_hi);
 		MAB_CUDA(cudaEventRecord(e1, d.stream));
 		uint32_t n_big = (uint32_t)d.get_scal(SC_BIG);
 		float ms = 0;
@@ -672,12 +688,7 @@ uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz)
 		d.free(big);
 	}
 	g_del_trans_stats.n_reduced = n_reduced;
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] transitively reduced %d arcs\n", "asg_arc_del_trans", n_reduced);
-	if (n_reduced) {
-		dg_cleanup(d, g, flag);
-		dg_symm(d, g);
-	}
-	d.free(flag);
+	*flag_out = flag;
 	return n_reduced;
 }
 

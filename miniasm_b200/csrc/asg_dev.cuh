@@ -29,6 +29,7 @@ uint32_t dg_del_multi(MabDev &d, DGraph &g);     // asg.c:104-121
 uint32_t dg_del_asymm(MabDev &d, DGraph &g);     // asg.c:124-138
 void dg_symm(MabDev &d, DGraph &g);              // asg.c:140-145
 uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz);  // asg.c:148-193
+uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo, uint32_t own_hi, uint8_t **flag_out);
 uint32_t dg_del_short(MabDev &d, DGraph &g, float ratio);    // asg.c:83-101
 
 // statistics of the last dg_del_trans call (for the roofline arithmetic in bench.py)

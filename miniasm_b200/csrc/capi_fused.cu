@@ -6,6 +6,7 @@
 #include "hit_dev.cuh"
 #include "clean_dev.cuh"
 #include "ingest_dev.cuh"
+#include "shard_comm.cuh"
 #include <cub/cub.cuh>
 #include <zlib.h>
 #include <fcntl.h>
@@ -33,6 +34,9 @@ struct mab_ctx {
 	// pinned staging for file loads
 	char *pin[2] = {nullptr, nullptr};
 	size_t pin_bytes = 0;
+	// sharded runs (mab_shard_init): communicator + the packed names of all ranks (names.off indexes it instead of d_text)
+	ShardComm sc;
+	char *name_text = nullptr;
 };
 
 __global__ void k_sg_len(uint32_t n, const DSub *sub, const uint32_t *slen, const uint32_t *orig, uint32_t *len, uint8_t *del)
@@ -77,6 +81,8 @@ struct PhaseTimer { // CUDA-event stopwatch around one step of the fused API (+ 
 	}
 };
 
+extern "C" { static void layout_tail(mab_ctx *c, const ma_opt_t *opt, int stage); }
+
 static void ctx_drop_graphs(mab_ctx *c)
 {
 	if (c->have_ug) dg_ug_free(c->dev, c->ug), c->have_ug = false;
@@ -90,6 +96,7 @@ static void ctx_reset_reads(mab_ctx *c)
 	d.free(c->sub), c->sub = nullptr;
 	d.free(c->orig_id), c->orig_id = nullptr;
 	names_free(d, c->names);
+	d.free(c->name_text), c->name_text = nullptr;
 	c->hits.n = 0, c->hits.n_seq = 0;
 	c->n_seq = 0;
 }
@@ -343,6 +350,15 @@ int mab_layout(mab_ctx_t *c, const ma_opt_t *opt, int stage)
 		c->stats.trans_inner = g_del_trans_stats.inner_iters, c->stats.ms_del_trans_kernel = g_del_trans_stats.kernel_ms;
 		d.trace("layout:del_trans+cleanup+symm");
 	}
+	layout_tail(c, opt, stage);
+	return 0;
+}
+
+/* main.c:160-188: the passes after transitive reduction, on the (replicated) reduced graph */
+static void layout_tail(mab_ctx *c, const ma_opt_t *opt, int stage)
+{
+	MabDev &d = c->dev;
+	DGraph &g = c->sg;
 	if (stage >= 7) {
 		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.2: initial tip cutting and bubble popping <===\n");
 		dg_cut_tip(d, g, opt->max_ext);
@@ -375,7 +391,6 @@ int mab_layout(mab_ctx_t *c, const ma_opt_t *opt, int stage)
 	c->stats.n_arc_final = g.n_arc;
 	d.sync();
 	d.trace("layout:cleaning passes");
-	return 0;
 }
 
 /* Step 5 (asm.c:121-210) */
@@ -416,7 +431,7 @@ sdict_t *mab_export_dict(mab_ctx_t *c)
 	const size_t bytes = last_pos + last_sz;
 	char *d_pack = (char*)d.alloc(bytes), *pack = (char*)malloc(bytes);
 	uint32_t *slen = (uint32_t*)malloc((size_t)n * 4);
-	MAB_LAUNCH(d, k_name_pack, mab_grid(n, 256), 256, 0, n, c->orig_id, c->names.off, c->names.nlen, c->names.slen, c->d_text, pos, d_pack, d_slen);
+	MAB_LAUNCH(d, k_name_pack, mab_grid(n, 256), 256, 0, n, c->orig_id, c->names.off, c->names.nlen, c->names.slen, c->name_text ? c->name_text : c->d_text, pos, d_pack, d_slen);
 	MAB_CUDA(cudaMemcpyAsync(pack, d_pack, bytes, cudaMemcpyDeviceToHost, d.stream));
 	MAB_CUDA(cudaMemcpyAsync(slen, d_slen, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream));
 	d.sync();
@@ -477,4 +492,177 @@ float mab_event_elapsed_ms(void *a, void *b) { float ms = 0; MAB_CUDA(cudaEventS
 void mab_event_destroy(void *e) { MAB_CUDA(cudaEventDestroy((cudaEvent_t)e)); }
 void mab_sync(mab_ctx_t *c) { c->dev.sync(); }
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Hash-sharded multi-GPU run: one process per GPU, read r owned by rank r mod world.
+ *   mab_nccl_unique_id (rank 0) -> bytes broadcast by the launcher -> mab_shard_init (all ranks)
+ *   mab_load_paf_text/file with THIS RANK'S byte range of the PAF (ranges in rank order, cut at line ends)
+ *   mab_ingest_sharded -> mab_select_sharded -> mab_layout_sharded: afterwards every rank holds the same reduced
+ *   graph as a single-GPU run of the concatenated PAF would, and mab_unitigs / mab_export_* work as usual.
+ * Exchanges: all-gather of distinct names, all-to-all of hits, all-reduce of the interval tables and of the
+ * containment / deletion flags, all-gather of raw arcs (for neighbour slabs) and of the reduced arcs.
+ * ------------------------------------------------------------------------------------------------------------ */
+int mab_nccl_unique_id(void *out128)
+{
+	ncclUniqueId id;
+	MAB_NCCL(ncclGetUniqueId(&id));
+	memcpy(out128, &id, sizeof(id) < 128 ? sizeof(id) : 128);
+	return (int)sizeof(id);
+}
+
+int mab_shard_init(mab_ctx_t *c, int rank, int world, const void *id128)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	c->sc.rank = rank, c->sc.world = world;
+	if (world > 1) {
+		ncclUniqueId id;
+		memcpy(&id, id128, sizeof(id) < 128 ? sizeof(id) : 128);
+		MAB_NCCL(ncclCommInitRank(&c->sc.comm, world, id, rank));
+	}
+	return 0;
+}
+
+int mab_ingest_sharded(mab_ctx_t *c, int min_span, int min_match, int bi_dir)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	PhaseTimer pt(d, &c->stats.ms_ingest, "mab_ingest_sharded");
+	ctx_reset_reads(c);
+	ingest_paf_sharded(d, c->sc, c->d_text, c->text_len, min_span, min_match, bi_dir, c->hits, c->names, &c->name_text, c->ist);
+	c->n_seq = c->names.n_seq;
+	c->stats.n_lines = c->ist.n_parsed, c->stats.n_hits_stored = c->ist.n_hits, c->stats.n_seq_in = c->ist.n_seq;
+	if (ma_verbose >= 3 && c->sc.rank == 0)
+		fprintf(stderr, "[M::%s::%s] read %ld hits; stored %ld hits and %d sequences (%ld bp)\n", "ma_hit_read", sys_timestamp(),
+				(long)c->ist.n_parsed, (long)c->ist.n_hits, (int)c->ist.n_seq, (long)c->ist.tot_len);
+	return 0;
+}
+
+/* default read selection (main.c:119-142 with no -1/-2/-S): the interval tables are completed by all-reduce */
+int mab_select_sharded(mab_ctx_t *c, const ma_opt_t *opt)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	DHits &h = c->hits;
+	ShardComm &sc = c->sc;
+	PhaseTimer pt(d, &c->stats.ms_select, "mab_select_sharded");
+	ctx_drop_graphs(c);
+	const int vsave = ma_verbose;
+	if (sc.rank != 0) ma_verbose = 0; // counts in the log lines are per rank: only rank 0 talks
+	const uint32_t n = c->n_seq;
+	d.free(c->sub);
+	c->sub = mab_alloc<DSub>(d, n);
+	dh_sub(d, h, opt->min_dp, opt->min_iden, 0, c->sub);                  // rows of the reads this rank owns; zeros elsewhere
+	sc_allreduce(d, sc, c->sub, n, ncclUint64, ncclSum);                   // every row is written by exactly one rank
+	dh_cut_flt(d, h, c->sub, opt->min_span, (int)(opt->max_hang * 1.5), (int)(opt->min_ovlp * .5), &c->cov);
+	DSub *sub2 = mab_alloc<DSub>(d, n), *cut2 = mab_alloc<DSub>(d, n);
+	dh_sub(d, h, opt->min_dp, opt->min_iden, opt->min_span / 2, sub2);
+	sc_allreduce(d, sc, sub2, n, ncclUint64, ncclSum);
+	if (n) MAB_CUDA(cudaMemcpyAsync(cut2, sub2, (size_t)n * sizeof(DSub), cudaMemcpyDeviceToDevice, d.stream));
+	dh_sub_merge(d, n, c->sub, sub2);
+	d.free(sub2);
+	int32_t *map = mab_alloc<int32_t>(d, n);
+	HitArcParams p = { opt->max_hang, opt->int_frac, opt->min_ovlp };
+	std::function<void(DSub*, uint8_t*, uint32_t)> ex = [&](DSub *sub, uint8_t *used, uint32_t n_seq) {
+		// containment flags are the top bit of the first word: an element-wise max over ranks is their OR (the other bits agree)
+		sc_allreduce(d, sc, sub, (size_t)n_seq * 2, ncclUint32, ncclMax);
+		sc_allreduce(d, sc, used, n_seq, ncclUint8, ncclMax);
+	};
+	dh_contained(d, h, c->sub, nullptr, p, map, cut2, opt->min_span, &ex);
+	uint32_t *orig_new = mab_alloc<uint32_t>(d, h.n_seq);
+	if (n) MAB_LAUNCH(d, k_orig_from_map, mab_grid(n, 256), 256, 0, n, map, c->orig_id, orig_new);
+	d.free(c->orig_id);
+	c->orig_id = orig_new;
+	c->n_seq = h.n_seq;
+	d.free(map); d.free(cut2);
+	ma_verbose = vsave;
+	c->stats.n_hits_final = h.n, c->stats.n_seq_final = c->n_seq;
+	d.sync();
+	return 0;
+}
+
+__global__ void k_not_flag(const uint8_t *flag, uint32_t n, uint8_t *out)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = !flag[i];
+}
+
+/* ma_sg_gen + asg_arc_del_trans sharded, then the cleaning passes on the replicated reduced graph */
+int mab_layout_sharded(mab_ctx_t *c, const ma_opt_t *opt)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	ShardComm &sc = c->sc;
+	const int G = sc.world;
+	PhaseTimer pt(d, &c->stats.ms_layout, "mab_layout_sharded");
+	ctx_drop_graphs(c);
+	const int vsave = ma_verbose, mvsave = mab_verbose;
+	if (sc.rank != 0) ma_verbose = 0, mab_verbose = 0;
+	const uint32_t n = c->n_seq;
+	uint32_t *len = mab_alloc<uint32_t>(d, n);
+	uint8_t *del = mab_alloc<uint8_t>(d, n);
+	if (n) MAB_LAUNCH(d, k_sg_len, mab_grid(n, 256), 256, 0, n, c->sub, c->names.slen, c->orig_id, len, del);
+	HitArcParams p = { opt->max_hang, opt->int_frac, opt->min_ovlp };
+	c->hits.n_seq = n;
+	DGraph loc;                                             // arcs of the reads this rank owns, sorted
+	dh_sg_emit(d, c->hits, len, del, p, loc);
+	d.free(len); d.free(del);
+	sc_allreduce(d, sc, loc.seq, n, ncclUint32, ncclMax);   // deletion flags raised by any rank (top bit; lengths agree)
+	dg_arc_rm(d, loc, nullptr);
+	// all ranks' raw arcs, concatenated in rank order: every vertex's slab is contiguous in it, which is all the index needs
+	std::vector<uint64_t> cnt = sc_allgather_u64(d, sc, loc.n_arc);
+	uint64_t tot = 0, my_off = 0;
+	std::vector<uint64_t> bytes(G);
+	for (int r = 0; r < G; ++r) { if (r == sc.rank) my_off = tot; tot += cnt[r]; bytes[r] = cnt[r] * sizeof(DArc); }
+	if (tot >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 arcs in the gathered graph\n"); exit(73); }
+	DGraph &g = c->sg;
+	dg_set_nseq(d, g, n);
+	dg_reserve(d, g, tot ? tot : 1);
+	if (n) MAB_CUDA(cudaMemcpyAsync(g.seq, loc.seq, (size_t)n * 4, cudaMemcpyDeviceToDevice, d.stream));
+	sc_allgather_v(d, sc, loc.arc, bytes, g.arc);
+	g.n_arc = (uint32_t)tot, g.is_srt = true, g.is_symm = false, g.len_bits = loc.len_bits;
+	dg_arc_index(d, g);
+	c->have_sg = true;
+	c->stats.n_arc_sg = tot;
+	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", g.n_arc);
+	// transitive reduction of the vertices this rank owns (their slabs start inside its block of the concatenation)
+	uint8_t *flag = nullptr;
+	uint32_t n_red = dg_del_trans_flags(d, g, (uint32_t)opt->gap_fuzz, (uint32_t)my_off, (uint32_t)(my_off + cnt[sc.rank]), &flag);
+	c->stats.ms_del_trans_kernel = g_del_trans_stats.kernel_ms, c->stats.trans_inner = g_del_trans_stats.inner_iters;
+	std::vector<uint64_t> reds = sc_allgather_u64(d, sc, n_red);
+	uint64_t n_red_all = 0;
+	for (int r = 0; r < G; ++r) n_red_all += reds[r];
+	c->stats.n_arc_trans_in = cnt[sc.rank], c->stats.n_reduced = n_red_all; // arcs of the vertices this rank reduces
+	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] transitively reduced %d arcs\n", "asg_arc_del_trans", (int)n_red_all);
+	// survivors of the own block -> all ranks; their stable sort by (vertex, length) is the single-GPU arc array
+	uint32_t n_keep = 0;
+	DArc *keep = mab_alloc<DArc>(d, cnt[sc.rank]);
+	if (cnt[sc.rank]) {
+		uint8_t *nf = mab_alloc<uint8_t>(d, cnt[sc.rank]);
+		MAB_LAUNCH(d, k_not_flag, mab_grid(cnt[sc.rank], 256), 256, 0, flag + my_off, (uint32_t)cnt[sc.rank], nf);
+		size_t tb = 0;
+		unsigned long long *d_n = d.d_scal + SC_NSEL;
+		cub::DeviceSelect::Flagged(nullptr, tb, g.arc + my_off, nf, keep, d_n, (int)cnt[sc.rank], d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceSelect::Flagged(tmp, tb, g.arc + my_off, nf, keep, d_n, (int)cnt[sc.rank], d.stream);
+		++d.n_lib;
+		n_keep = (uint32_t)d.get_scal(SC_NSEL);
+		d.free(nf);
+	}
+	d.free(flag);
+	std::vector<uint64_t> kc = sc_allgather_u64(d, sc, n_keep);
+	uint64_t ktot = 0;
+	for (int r = 0; r < G; ++r) { ktot += kc[r]; bytes[r] = kc[r] * sizeof(DArc); }
+	DArc *all = mab_alloc<DArc>(d, ktot);
+	sc_allgather_v(d, sc, keep, bytes, all);
+	d.free(keep);
+	dg_reserve(d, g, ktot ? ktot : 1);
+	if (ktot) MAB_CUDA(cudaMemcpyAsync(g.arc, all, ktot * sizeof(DArc), cudaMemcpyDeviceToDevice, d.stream));
+	d.free(all);
+	g.n_arc = (uint32_t)ktot, g.is_srt = false, g.has_idx = false;
+	dg_cleanup(d, g);                                       // stable radix sort by ul + index (nothing left to remove)
+	if (n_red_all) dg_symm(d, g);                           // asg.c:188-191
+	dg_free(d, loc);
+	layout_tail(c, opt, 100);
+	ma_verbose = vsave, mab_verbose = mvsave;
+	return 0;
+}
 }

@@ -4,6 +4,7 @@
 #include "hit_dev.cuh"
 #include "hit2arc.cuh"
 #include <cub/cub.cuh>
+#include <functional>
 
 extern "C" int ma_verbose;              // hit.c prints its [M::fn::timestamp] lines only when ma_verbose >= 3
 extern "C" const char *sys_timestamp(void);
@@ -690,7 +691,8 @@ __global__ void k_cont_apply(DHit *a, size_t n, const int32_t *__restrict__ map,
 	}
 }
 
-size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, const HitArcParams &p, int32_t *map_out, const DSub *cut_reg, int min_span)
+size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, const HitArcParams &p, int32_t *map_out, const DSub *cut_reg, int min_span,
+                    const std::function<void(DSub*, uint8_t*, uint32_t)> *exchange)
 {
 	const uint32_t n_seq = h.n_seq;
 	uint32_t n_new = 0;
@@ -707,6 +709,7 @@ size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, cons
 			MAB_LAUNCH(d, k_cut_cont_mark, mab_grid(h.n, 256), 256, 0, h.a, h.n, cut_reg, sub, min_span, p, used, cut_flag, d.d_scal + SC_COUNT);
 		} else
 		if (h.n) MAB_LAUNCH(d, k_cont_mark, mab_grid(h.n, 256), 256, 0, h.a, h.n, sub, p, used);
+		if (exchange) (*exchange)(sub, used, n_seq); // sharded runs: OR the containment flags and the "used" marks of all ranks
 		MAB_LAUNCH(d, k_cont_keep, mab_grid(n_seq, 256), 256, 0, n_seq, sub, used, seq_del, keep);
 		size_t tb = 0;
 		cub::DeviceScan::ExclusiveSum(nullptr, tb, keep, excl, (int)n_seq, d.stream);
@@ -782,6 +785,13 @@ __global__ void k_sg_arcs(const DHit *a, size_t n, uint32_t *seq, HitArcParams p
 
 void dh_sg_gen(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *del, const HitArcParams &p, DGraph &g)
 {
+	dh_sg_emit(d, h, len, del, p, g);
+	dg_cleanup(d, g);
+	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", g.n_arc);
+}
+
+void dh_sg_emit(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *del, const HitArcParams &p, DGraph &g)
+{
 	const uint32_t n_seq = h.n_seq;
 	dg_set_nseq(d, g, n_seq);
 	g.n_arc = 0, g.is_srt = false, g.is_symm = false, g.has_idx = false;
@@ -800,7 +810,5 @@ void dh_sg_gen(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *de
 		const uint32_t n_arc = (uint32_t)d.get_scal(SC_COUNT);
 		dg_build_sorted(d, g, ka, va, kb, vb, (uint32_t)h.n, n_arc, lb, true);
 		d.free(ka); d.free(kb); d.free(va); d.free(vb);
-	} else dg_reserve(d, g, 1);
-	dg_cleanup(d, g);
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", g.n_arc);
+	} else { dg_reserve(d, g, 1); g.is_srt = true; }
 }

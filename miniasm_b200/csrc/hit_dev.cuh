@@ -3,6 +3,7 @@
 #pragma once
 #include "mab_common.cuh"
 #include "asg_dev.cuh"
+#include <functional>
 
 struct DHits {
 	DHit *a = nullptr, *a2 = nullptr;   // hit array + ping-pong buffer for compaction
@@ -36,8 +37,12 @@ void dh_sub_merge(MabDev &d, uint32_t n_sub, DSub *a, const DSub *b);
 // On return sub is compacted in place, hits renumbered/compacted, map_out[old] = new id or -1, and
 // h.n_seq is the surviving read count.  Returns the new hit count.
 // With cut_reg != null the call first applies ma_hit_cut(cut_reg, min_span) to the hits (fused sweep, one compaction).
+// `exchange` (sharded runs) is called between the flag pass and the renumbering with (sub, used, n_seq).
 size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, const HitArcParams &p, int32_t *map_out,
-                    const DSub *cut_reg = nullptr, int min_span = 0);
+                    const DSub *cut_reg = nullptr, int min_span = 0,
+                    const std::function<void(DSub*, uint8_t*, uint32_t)> *exchange = nullptr);
+// ma_sg_gen without the final asg_cleanup: seq table + sorted local arcs (sharded runs clean up after exchanging seq flags)
+void dh_sg_emit(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *del, const HitArcParams &p, DGraph &g);
 // ma_hit_cut immediately followed by ma_hit_flt on the same table (main.c:123-125), fused
 size_t dh_cut_flt(MabDev &d, DHits &h, const DSub *sub, int min_span, int max_hang, int min_ovlp, float *cov);
 

@@ -18,6 +18,7 @@
 // probabilistic), (4) distinct names ranked by first occurrence = ids, (5) hits emitted at scanned offsets,
 // (6) radix sort (hit_dev.cu).
 #include "ingest_dev.cuh"
+#include "shard_comm.cuh"
 #include <cub/cub.cuh>
 
 struct PLine {                 // one parsed PAF line, 64 bytes
@@ -226,15 +227,15 @@ k_parse(const char *__restrict__ text, size_t len, const uint64_t *__restrict__ 
 }
 
 // stale bl for 10-field lines + the store filter (needs the final bl? no: the filter uses qe,qs,te,ts,ml only)
-__global__ void k_fix_filter(PLine *ln, uint64_t n_lines, int min_span, int min_match, unsigned long long *n_pass)
-{
+__global__ void k_fix_filter(PLine *ln, uint64_t n_lines, int min_span, int min_match, unsigned long long *n_pass, uint32_t carry_bl = 0)
+{	// carry_bl: bl left behind by the lines before this rank's byte range (sharded runs), else 0
 	unsigned cnt = 0;
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
 		PLine *r = ln + i;
 		bool pass = false;
 		if (r->nf >= 10) {
 			if (r->nf == 10) { // bl keeps the value of the closest earlier line that had an 11th field (paf.c:47, hit.c:73)
-				uint32_t bl = 0;
+				uint32_t bl = carry_bl;
 				for (uint64_t j = i; j-- > 0;)
 					if (ln[j].nf >= 11) { bl = ln[j].bl; break; }
 				r->bl = bl;
@@ -530,4 +531,445 @@ extern "C" int mab_test_parse_line(const char *line, size_t len, uint32_t *out)
 	out[0] = r.nf, out[1] = r.ql, out[2] = r.qs, out[3] = r.qe, out[4] = r.ml_rev >> 31, out[5] = r.tl, out[6] = r.ts, out[7] = r.te;
 	out[8] = r.ml_rev & 0x7fffffffu, out[9] = r.bl, out[10] = r.qnl, out[11] = r.tnl, out[12] = r.tdelta;
 	return too_long ? -1 : 0;
+}
+
+// =============================================================================================================
+// Sharded ingest: every rank parses its own byte range of the PAF (ranges follow rank order, so
+// "line i of rank r" has the global line number base[r] + i), the distinct names of all ranks are all-gathered and
+// ranked by global first occurrence -- which reproduces the single-GPU ids exactly -- and every hit travels to the
+// rank that owns its query read (id mod world) in one all-to-all; per-source order is file order, so the stable sort
+// that follows sees the hits of a read in the same order as a single GPU would.
+// =============================================================================================================
+__global__ void k_last_bl(const PLine *ln, uint64_t n_lines, unsigned long long *out) // out[0] = 1 + index of the last line with an 11th field
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x)
+		if (ln[i].nf >= 11) atomicMax(out, (unsigned long long)(i + 1));
+}
+
+struct GEntry { unsigned long long hash, first; uint32_t slen, nlen; }; // a distinct name of one rank, 24 bytes
+
+__global__ void k_local_entries(const uint64_t *slots, uint32_t n, NameTab t, const uint64_t *start, const PLine *ln, uint64_t line_base,
+                                GEntry *ent, uint32_t *name_sz)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint64_t s = slots[i], occ = t.first[s];
+		const PLine &r = ln[occ >> 1];
+		GEntry e;
+		e.hash = t.key[s], e.first = 2 * line_base + occ;
+		e.nlen = occ & 1 ? r.tnl : r.qnl, e.slen = occ & 1 ? r.tl : r.ql;
+		ent[i] = e;
+		name_sz[i] = e.nlen;
+	}
+}
+
+__global__ void k_local_names(const uint64_t *slots, uint32_t n, NameTab t, const uint64_t *start, const PLine *ln, const char *text,
+                              const uint64_t *pos, char *out)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint64_t occ = t.first[slots[i]];
+		const PLine &r = ln[occ >> 1];
+		const uint32_t l = occ & 1 ? r.tnl : r.qnl;
+		const char *src = text + start[occ >> 1] + (occ & 1 ? r.tdelta : 0);
+		char *dst = out + pos[i];
+		for (uint32_t k = 0; k < l; ++k) dst[k] = src[k];
+	}
+}
+
+struct GTab { unsigned long long *key, *first; uint32_t *win, *id; uint64_t mask; }; // global table: winner entry and read id per slot
+
+__global__ void k_gtab_insert(const GEntry *ent, uint64_t n, GTab t, uint32_t *slot_of, unsigned long long *overflow)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		const unsigned long long h = ent[i].hash;
+		uint64_t s = h & t.mask;
+		uint32_t found = 0xffffffffu;
+		for (int probe = 0; probe < 1 << 14; ++probe, s = (s + 1) & t.mask) {
+			unsigned long long k = t.key[s];
+			if (k == 0) { k = atomicCAS(&t.key[s], 0ull, h); if (k == 0) k = h; }
+			if (k == h) { atomicMin(&t.first[s], ent[i].first); found = (uint32_t)s; break; }
+		}
+		if (found == 0xffffffffu) atomicAdd(overflow, 1ull);
+		slot_of[i] = found;
+	}
+}
+
+__global__ void k_gtab_winner(const GEntry *ent, uint64_t n, GTab t, const uint32_t *slot_of)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		if (t.first[slot_of[i]] == ent[i].first) t.win[slot_of[i]] = (uint32_t)i; // first occurrences are unique: exactly one winner
+}
+
+__global__ void k_gtab_verify(const GEntry *ent, uint64_t n, GTab t, const uint32_t *slot_of, const uint64_t *name_pos, const char *names, unsigned long long *n_bad)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t w = t.win[slot_of[i]];
+		if (w == i) continue;
+		bool ok = ent[w].nlen == ent[i].nlen;
+		const char *a = names + name_pos[i], *b = names + name_pos[w];
+		for (uint32_t k = 0; ok && k < ent[i].nlen; ++k) ok = a[k] == b[k];
+		if (!ok) atomicAdd(n_bad, 1ull);
+	}
+}
+
+struct GSlotUsed { const unsigned long long *key; __device__ __forceinline__ bool operator()(uint64_t s) const { return key[s] != 0; } };
+
+__global__ void k_gtab_first(const uint64_t *slots, uint32_t n, GTab t, unsigned long long *first_out)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) first_out[i] = t.first[slots[i]];
+}
+
+__global__ void k_gtab_rank(const uint64_t *slot_sorted, uint32_t n, GTab t, const GEntry *ent, const uint64_t *name_pos,
+                            uint64_t *noff, uint32_t *nlen, uint32_t *slen, unsigned long long *tot_len)
+{
+	unsigned long long sum = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint64_t s = slot_sorted[i];
+		const uint32_t w = t.win[s];
+		t.id[s] = i;
+		noff[i] = name_pos[w], nlen[i] = ent[w].nlen, slen[i] = ent[w].slen;
+		sum += ent[w].slen;
+	}
+	typedef cub::BlockReduce<unsigned long long, 256> BR;
+	__shared__ typename BR::TempStorage ts;
+	unsigned long long sm = BR(ts).Sum(sum);
+	if (threadIdx.x == 0 && sm) atomicAdd(tot_len, sm);
+}
+
+// global read ids of the two names of every stored line + number of hits the line yields
+__global__ void k_line_gids(PLine *ln, uint64_t n_lines, NameTab lt, GTab gt, int bi_dir, uint32_t *cnt)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t c = 0;
+		if (ln[i].pass) {
+			uint32_t g[2];
+			#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				const unsigned long long h = lt.key[k ? ln[i].slot_t : ln[i].slot_q];
+				uint64_t s = h & gt.mask;
+				while (gt.key[s] != h) s = (s + 1) & gt.mask; // present by construction
+				g[k] = gt.id[s];
+			}
+			ln[i].slot_q = g[0], ln[i].slot_t = g[1]; // the slot fields now carry global read ids
+			c = bi_dir && g[0] != g[1] ? 2 : 1;
+		}
+		cnt[i] = c;
+	}
+}
+
+__global__ void k_hit_emit_gid(const PLine *ln, uint64_t n_lines, const uint32_t *cnt, const uint64_t *off, uint32_t world, DHit *out, uint32_t *dest, unsigned *max_qs)
+{
+	unsigned mx = 0;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t c = cnt[i];
+		if (c == 0) continue;
+		const PLine r = ln[i];
+		const uint32_t qid = (uint32_t)r.slot_q, tid = (uint32_t)r.slot_t, bl = r.bl & 0x7fffffffu;
+		uint4 *o = reinterpret_cast<uint4*>(out + off[i]);
+		o[0] = make_uint4(r.qs, qid, r.qe, tid);
+		o[1] = make_uint4(r.ts, r.te, r.ml_rev, bl);
+		dest[off[i]] = qid % world;
+		mx = r.qs > mx ? r.qs : mx;
+		if (c == 2) {
+			o[2] = make_uint4(r.ts, tid, r.te, qid);
+			o[3] = make_uint4(r.qs, r.qe, r.ml_rev, bl);
+			dest[off[i] + 1] = tid % world;
+			mx = r.ts > mx ? r.ts : mx;
+		}
+	}
+	mx = __reduce_max_sync(0xffffffffu, mx);
+	if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_qs, mx);
+}
+
+__global__ void k_dest_count(const uint32_t *dest, uint64_t n, unsigned long long *cnt) // cnt[world]
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) atomicAdd(&cnt[dest[i]], 1ull);
+}
+
+__global__ void k_gather_hits(const DHit *a, const uint32_t *pos, uint64_t n, DHit *out)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint4 *q = reinterpret_cast<const uint4*>(a + pos[i]);
+		uint4 x = __ldg(q), y = __ldg(q + 1);
+		uint4 *o = reinterpret_cast<uint4*>(out + i);
+		o[0] = x, o[1] = y;
+	}
+}
+
+__global__ void k_add_u64(uint64_t *a, uint64_t n, uint64_t add) { for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) a[i] += add; }
+
+__global__ void k_iota32(uint32_t *a, uint64_t n) { for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) a[i] = (uint32_t)i; }
+
+void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len, int min_span, int min_match, int bi_dir,
+                        DHits &h, DNames &names, char **name_text_out, IngestStats &st)
+{
+	memset(&st, 0, sizeof(st));
+	names = DNames();
+	h.n = 0, h.n_seq = 0;
+	const int G = sc.world;
+	// (1) local line starts and parse
+	uint64_t *start = nullptr, n_lines = 0;
+	if (len) {
+		const uint64_t n_tile = (len + NL_TILE - 1) / NL_TILE;
+		uint64_t *cnt = mab_alloc<uint64_t>(d, n_tile + 1), *base = mab_alloc<uint64_t>(d, n_tile + 1);
+		MAB_LAUNCH(d, k_nl_count, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, cnt);
+		size_t tb = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, base, (int64_t)(n_tile + 1), d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, base, (int64_t)(n_tile + 1), d.stream);
+		++d.n_lib;
+		uint64_t n_nl;
+		MAB_CUDA(cudaMemcpyAsync(&n_nl, base + n_tile, 8, cudaMemcpyDeviceToHost, d.stream));
+		d.sync();
+		n_lines = n_nl + 1;
+		start = mab_alloc<uint64_t>(d, n_lines + 1);
+		MAB_CUDA(cudaMemsetAsync(start, 0, 8, d.stream));
+		MAB_LAUNCH(d, k_nl_write, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, base, start + 1);
+		d.free(cnt); d.free(base);
+	}
+	PLine *ln = mab_alloc<PLine>(d, n_lines);
+	std::vector<uint64_t> all_lines = sc_allgather_u64(d, sc, n_lines);
+	uint64_t line_base = 0, n_lines_all = 0;
+	for (int r = 0; r < G; ++r) { if (r < sc.rank) line_base += all_lines[r]; n_lines_all += all_lines[r]; }
+	st.n_lines = n_lines_all;
+
+	uint64_t seed = 0, cap = 0;
+	NameTab tab{nullptr, nullptr, nullptr, 0};
+	GTab gt{nullptr, nullptr, nullptr, nullptr, 0};
+	GEntry *g_ent = nullptr;
+	char *g_names = nullptr;
+	uint64_t *g_pos = nullptr;
+	uint64_t n_ent_all = 0, name_bytes_all = 0;
+	for (int attempt = 0;; ++attempt) {
+		d.zero_scal(SC_COUNT, 4);
+		if (n_lines) MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, n_lines, seed, ln, d.d_scal + SC_COUNT);
+		// bl carried over from earlier ranks for 10-field lines at the head of this range
+		d.zero_scal(SC_TMP0, 1);
+		if (n_lines) MAB_LAUNCH(d, k_last_bl, mab_grid(n_lines, 256), 256, 0, ln, n_lines, d.d_scal + SC_TMP0);
+		uint64_t last11 = d.get_scal(SC_TMP0);
+		uint32_t my_bl = 0;
+		if (last11) { MAB_CUDA(cudaMemcpyAsync(&my_bl, &ln[last11 - 1].bl, 4, cudaMemcpyDeviceToHost, d.stream)); d.sync(); }
+		std::vector<uint64_t> bls = sc_allgather_u64(d, sc, last11 ? ((uint64_t)1 << 32 | my_bl) : 0);
+		uint32_t carry = 0;
+		for (int r = 0; r < sc.rank; ++r) if (bls[r] >> 32) carry = (uint32_t)bls[r];
+		if (n_lines) MAB_LAUNCH(d, k_fix_filter, mab_grid(n_lines, 256), 256, 0, ln, n_lines, min_span, min_match, d.d_scal + SC_AUX, carry);
+		st.n_parsed = d.get_scal(SC_COUNT);
+		const uint64_t n_pass = d.h_scal[SC_AUX];
+		if (d.h_scal[SC_COUNT + 1]) { fprintf(stderr, "[E::miniasm_b200] a read name in the PAF is longer than 65535 bytes\n"); exit(78); }
+		// (2) local dictionary
+		if (cap == 0) { cap = 1ull << 20; while (cap < n_pass / 4) cap <<= 1; }
+		bool bad = false, overflowed = false;
+		tab.key = (unsigned long long*)mab_alloc<uint64_t>(d, cap); tab.first = (unsigned long long*)mab_alloc<uint64_t>(d, cap); tab.id = mab_alloc<uint32_t>(d, cap);
+		tab.mask = cap - 1;
+		MAB_CUDA(cudaMemsetAsync(tab.key, 0, cap * 8, d.stream));
+		MAB_CUDA(cudaMemsetAsync(tab.first, 0xff, cap * 8, d.stream));
+		d.zero_scal(SC_BIG, 1); d.zero_scal(SC_AUX2, 1);
+		if (n_lines) MAB_LAUNCH(d, k_dict_insert, mab_grid(n_lines, 256), 256, 0, ln, n_lines, tab, d.d_scal + SC_BIG);
+		if (d.get_scal(SC_BIG) == 0) {
+			if (n_lines) MAB_LAUNCH(d, k_dict_verify, mab_grid(n_lines, 256), 256, 0, d_text, start, ln, n_lines, tab, d.d_scal + SC_AUX2);
+			bad = d.get_scal(SC_AUX2) != 0;
+		} else overflowed = true;
+		// every rank must take the same branch: agree on the outcome
+		{
+			std::vector<uint64_t> f = sc_allgather_u64(d, sc, (uint64_t)bad | (uint64_t)overflowed << 1);
+			bad = overflowed = false;
+			for (int r = 0; r < G; ++r) bad |= f[r] & 1, overflowed |= (f[r] >> 1) & 1;
+		}
+		if (overflowed) { d.free(tab.key); d.free(tab.first); d.free(tab.id); cap <<= 2; continue; }
+		// (3) distinct names of this rank -> entries + packed names, all-gathered
+		uint32_t n_ent = 0;
+		uint64_t *slots = mab_alloc<uint64_t>(d, cap);
+		if (!bad) {
+			cub::CountingInputIterator<uint64_t> pos(0);
+			SlotUsed used{tab.key};
+			size_t tb = 0;
+			unsigned long long *d_n = d.d_scal + SC_NSEL;
+			cub::DeviceSelect::If(nullptr, tb, pos, slots, d_n, (int64_t)cap, used, d.stream);
+			void *tmp = d.tmp(tb);
+			cub::DeviceSelect::If(tmp, tb, pos, slots, d_n, (int64_t)cap, used, d.stream);
+			++d.n_lib;
+			n_ent = (uint32_t)d.get_scal(SC_NSEL);
+		}
+		GEntry *ent = mab_alloc<GEntry>(d, n_ent);
+		uint32_t *nsz = mab_alloc<uint32_t>(d, (size_t)n_ent + 1);
+		uint64_t *npos = mab_alloc<uint64_t>(d, (size_t)n_ent + 1);
+		uint64_t my_name_bytes = 0;
+		char *my_names = nullptr;
+		if (n_ent) {
+			MAB_LAUNCH(d, k_local_entries, mab_grid(n_ent, 256), 256, 0, slots, n_ent, tab, start, ln, line_base, ent, nsz);
+			size_t tb = 0;
+			cub::DeviceScan::ExclusiveSum(nullptr, tb, nsz, npos, (int)n_ent, d.stream);
+			void *tmp = d.tmp(tb);
+			cub::DeviceScan::ExclusiveSum(tmp, tb, nsz, npos, (int)n_ent, d.stream);
+			++d.n_lib;
+			uint64_t lp; uint32_t ls;
+			MAB_CUDA(cudaMemcpyAsync(&lp, npos + n_ent - 1, 8, cudaMemcpyDeviceToHost, d.stream));
+			MAB_CUDA(cudaMemcpyAsync(&ls, nsz + n_ent - 1, 4, cudaMemcpyDeviceToHost, d.stream));
+			d.sync();
+			my_name_bytes = lp + ls;
+			my_names = (char*)d.alloc(my_name_bytes);
+			MAB_LAUNCH(d, k_local_names, mab_grid(n_ent, 256), 256, 0, slots, n_ent, tab, start, ln, d_text, npos, my_names);
+		}
+		std::vector<uint64_t> ents = sc_allgather_u64(d, sc, n_ent), nbytes = sc_allgather_u64(d, sc, my_name_bytes);
+		n_ent_all = name_bytes_all = 0;
+		std::vector<uint64_t> ent_bytes(G), pos_bytes(G);
+		uint64_t my_ent_off = 0, my_name_off = 0;
+		for (int r = 0; r < G; ++r) {
+			if (r == sc.rank) my_ent_off = n_ent_all, my_name_off = name_bytes_all;
+			n_ent_all += ents[r], name_bytes_all += nbytes[r];
+			ent_bytes[r] = ents[r] * sizeof(GEntry), pos_bytes[r] = ents[r] * 8;
+		}
+		g_ent = mab_alloc<GEntry>(d, n_ent_all);
+		g_names = (char*)d.alloc(name_bytes_all ? name_bytes_all : 1);
+		g_pos = mab_alloc<uint64_t>(d, n_ent_all);
+		sc_allgather_v(d, sc, ent, ent_bytes, g_ent);
+		sc_allgather_v(d, sc, my_names, nbytes, g_names);
+		sc_allgather_v(d, sc, npos, pos_bytes, g_pos); // positions are local to each rank's block: rebased below
+		{
+			// rebase name positions: entry block of rank r gets the byte offset of rank r's name block
+			std::vector<uint64_t> eoff(G + 1, 0), noff(G + 1, 0);
+			for (int r = 0; r < G; ++r) eoff[r + 1] = eoff[r] + ents[r], noff[r + 1] = noff[r] + nbytes[r];
+			for (int r = 0; r < G; ++r) if (ents[r] && noff[r]) {
+				MAB_LAUNCH(d, k_add_u64, mab_grid(ents[r], 256), 256, 0, g_pos + eoff[r], ents[r], noff[r]);
+			}
+		}
+		(void)my_ent_off; (void)my_name_off;
+		d.free(ent); d.free(nsz); d.free(npos); if (my_names) d.free(my_names);
+		d.free(slots);
+		// (4) global table (replicated): same insert on every rank -> same result
+		uint64_t gcap = 1ull << 16; while (gcap < 2 * n_ent_all + 2) gcap <<= 1;
+		gt.key = (unsigned long long*)mab_alloc<uint64_t>(d, gcap); gt.first = (unsigned long long*)mab_alloc<uint64_t>(d, gcap);
+		gt.win = mab_alloc<uint32_t>(d, gcap); gt.id = mab_alloc<uint32_t>(d, gcap); gt.mask = gcap - 1;
+		MAB_CUDA(cudaMemsetAsync(gt.key, 0, gcap * 8, d.stream));
+		MAB_CUDA(cudaMemsetAsync(gt.first, 0xff, gcap * 8, d.stream));
+		uint32_t *slot_of = mab_alloc<uint32_t>(d, n_ent_all);
+		d.zero_scal(SC_BIG, 1); d.zero_scal(SC_AUX2, 1);
+		if (n_ent_all) {
+			MAB_LAUNCH(d, k_gtab_insert, mab_grid(n_ent_all, 256), 256, 0, g_ent, n_ent_all, gt, slot_of, d.d_scal + SC_BIG);
+			MAB_LAUNCH(d, k_gtab_winner, mab_grid(n_ent_all, 256), 256, 0, g_ent, n_ent_all, gt, slot_of);
+			MAB_LAUNCH(d, k_gtab_verify, mab_grid(n_ent_all, 256), 256, 0, g_ent, n_ent_all, gt, slot_of, g_pos, g_names, d.d_scal + SC_AUX2);
+		}
+		const bool gbad = d.get_scal(SC_AUX2) != 0 || d.h_scal[SC_BIG] != 0; // identical on all ranks (replicated computation)
+		d.free(slot_of);
+		if (!bad && !gbad) break;
+		d.free(tab.key); d.free(tab.first); d.free(tab.id);
+		d.free(gt.key); d.free(gt.first); d.free(gt.win); d.free(gt.id);
+		d.free(g_ent); d.free(g_names); d.free(g_pos);
+		seed = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+		++st.hash_retries;
+		if (attempt > 16) { fprintf(stderr, "[E::miniasm_b200] read-name hashing keeps colliding\n"); exit(77); }
+	}
+	// (5) global ids = rank of the global first occurrence
+	uint32_t n_seq;
+	{
+		const uint64_t gcap = gt.mask + 1;
+		uint64_t *slots = mab_alloc<uint64_t>(d, gcap);
+		cub::CountingInputIterator<uint64_t> pos(0);
+		GSlotUsed used{gt.key};
+		size_t tb = 0;
+		unsigned long long *d_n = d.d_scal + SC_NSEL;
+		cub::DeviceSelect::If(nullptr, tb, pos, slots, d_n, (int64_t)gcap, used, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceSelect::If(tmp, tb, pos, slots, d_n, (int64_t)gcap, used, d.stream);
+		++d.n_lib;
+		uint64_t n = d.get_scal(SC_NSEL);
+		if (n >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 reads\n"); exit(73); }
+		n_seq = (uint32_t)n;
+		names.n_seq = n_seq;
+		names.off = mab_alloc<uint64_t>(d, n_seq); names.nlen = mab_alloc<uint32_t>(d, n_seq); names.slen = mab_alloc<uint32_t>(d, n_seq);
+		if (n_seq) {
+			unsigned long long *fa = (unsigned long long*)mab_alloc<uint64_t>(d, n_seq), *fb = (unsigned long long*)mab_alloc<uint64_t>(d, n_seq);
+			uint64_t *sb = mab_alloc<uint64_t>(d, n_seq);
+			MAB_LAUNCH(d, k_gtab_first, mab_grid(n_seq, 256), 256, 0, slots, n_seq, gt, fa);
+			cub::DoubleBuffer<unsigned long long> dk(fa, fb);
+			cub::DoubleBuffer<uint64_t> dv(slots, sb);
+			size_t tb2 = 0;
+			int end_bit = (int)bits_for(2 * n_lines_all + 1);
+			cub::DeviceRadixSort::SortPairs(nullptr, tb2, dk, dv, (int)n_seq, 0, end_bit, d.stream);
+			void *tmp2 = d.tmp(tb2);
+			cub::DeviceRadixSort::SortPairs(tmp2, tb2, dk, dv, (int)n_seq, 0, end_bit, d.stream);
+			++d.n_lib;
+			d.zero_scal(SC_AUX, 1);
+			MAB_LAUNCH(d, k_gtab_rank, mab_grid(n_seq, 256), 256, 0, dv.Current(), n_seq, gt, g_ent, g_pos, names.off, names.nlen, names.slen, d.d_scal + SC_AUX);
+			st.tot_len = d.get_scal(SC_AUX);
+			d.free(fa); d.free(fb); d.free(sb);
+		}
+		d.free(slots);
+	}
+	*name_text_out = g_names; // names.off points into this buffer (owned by the caller from now on)
+	// (6) local hits with global ids, bucketed by owner rank, exchanged
+	uint32_t *cnt = mab_alloc<uint32_t>(d, n_lines + 1);
+	uint64_t *off = mab_alloc<uint64_t>(d, n_lines + 1);
+	uint64_t n_loc = 0;
+	if (n_lines) {
+		MAB_LAUNCH(d, k_line_gids, mab_grid(n_lines, 256), 256, 0, ln, n_lines, tab, gt, bi_dir, cnt);
+		size_t tb = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, off, (int64_t)n_lines, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, off, (int64_t)n_lines, d.stream);
+		++d.n_lib;
+		uint64_t lo; uint32_t lc;
+		MAB_CUDA(cudaMemcpyAsync(&lo, off + n_lines - 1, 8, cudaMemcpyDeviceToHost, d.stream));
+		MAB_CUDA(cudaMemcpyAsync(&lc, cnt + n_lines - 1, 4, cudaMemcpyDeviceToHost, d.stream));
+		d.sync();
+		n_loc = lo + lc;
+	}
+	if (n_loc >= (1ull << 32)) { fprintf(stderr, "[E::miniasm_b200] more than 2^32 hits parsed by one rank\n"); exit(73); }
+	DHit *loc = mab_alloc<DHit>(d, n_loc), *snd = mab_alloc<DHit>(d, n_loc);
+	uint32_t *dest = mab_alloc<uint32_t>(d, n_loc), *dest2 = mab_alloc<uint32_t>(d, n_loc), *ia = mab_alloc<uint32_t>(d, n_loc), *ib = mab_alloc<uint32_t>(d, n_loc);
+	d.zero_scal(SC_AUX, 1);
+	MAB_CUDA(cudaMemsetAsync(d.d_scal + 16, 0, 32 * 8, d.stream));
+	if (n_loc) {
+		MAB_LAUNCH(d, k_hit_emit_gid, mab_grid(n_lines, 256), 256, 0, ln, n_lines, cnt, off, (uint32_t)G, loc, dest, (unsigned*)(d.d_scal + SC_AUX));
+		MAB_LAUNCH(d, k_dest_count, mab_grid(n_loc, 256), 256, 0, dest, n_loc, d.d_scal + 16);
+		MAB_LAUNCH(d, k_iota32, mab_grid(n_loc, 256), 256, 0, ia, n_loc);
+		cub::DoubleBuffer<uint32_t> dk(dest, dest2), dv(ia, ib);
+		size_t tb = 0;
+		int eb = (int)bits_for((uint64_t)G - 1);
+		cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int64_t)n_loc, 0, eb, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int64_t)n_loc, 0, eb, d.stream); // stable: file order kept inside every bucket
+		++d.n_lib;
+		MAB_LAUNCH(d, k_gather_hits, mab_grid(n_loc, 256), 256, 0, loc, dv.Current(), n_loc, snd);
+	}
+	if (G > 32) { fprintf(stderr, "[E::miniasm_b200] more than 32 ranks\n"); exit(79); }
+	uint32_t max_qs = (uint32_t)(d.get_scal(SC_AUX) & 0xffffffffu);
+	std::vector<uint64_t> send_cnt(G), recv_cnt(G);
+	for (int r = 0; r < G; ++r) send_cnt[r] = d.h_scal[16 + r];
+	{ // counts matrix: every rank learns how much it receives from whom
+		uint64_t *m = mab_alloc<uint64_t>(d, (size_t)G * G + G);
+		MAB_CUDA(cudaMemcpyAsync(m + (size_t)G * G, send_cnt.data(), 8 * (size_t)G, cudaMemcpyHostToDevice, d.stream));
+		if (sc.active()) MAB_NCCL(ncclAllGather(m + (size_t)G * G, m, G, ncclUint64, sc.comm, d.stream));
+		else MAB_CUDA(cudaMemcpyAsync(m, m + (size_t)G * G, 8 * (size_t)G, cudaMemcpyDeviceToDevice, d.stream));
+		std::vector<uint64_t> mat((size_t)G * G);
+		MAB_CUDA(cudaMemcpyAsync(mat.data(), m, 8 * (size_t)G * G, cudaMemcpyDeviceToHost, d.stream));
+		d.sync();
+		for (int r = 0; r < G; ++r) recv_cnt[r] = mat[(size_t)r * G + sc.rank];
+		d.free(m);
+	}
+	uint64_t n_recv = 0;
+	for (int r = 0; r < G; ++r) n_recv += recv_cnt[r];
+	if (n_recv >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 hits on one GPU\n"); exit(73); }
+	dh_reserve(d, h, n_recv ? n_recv : 1);
+	{
+		std::vector<uint64_t> sb(G), rb(G);
+		for (int r = 0; r < G; ++r) sb[r] = send_cnt[r] * sizeof(DHit), rb[r] = recv_cnt[r] * sizeof(DHit);
+		if (sc.active()) sc_alltoall_v(d, sc, snd, sb, h.a, rb);
+		else if (n_loc) MAB_CUDA(cudaMemcpyAsync(h.a, snd, n_loc * sizeof(DHit), cudaMemcpyDeviceToDevice, d.stream));
+	}
+	h.n = n_recv, h.n_seq = n_seq;
+	{ // sort key width must cover the largest query start of any rank
+		std::vector<uint64_t> mq = sc_allgather_u64(d, sc, max_qs);
+		for (int r = 0; r < G; ++r) if (mq[r] > max_qs) max_qs = (uint32_t)mq[r];
+	}
+	d.sync();
+	d.free(loc); d.free(snd); d.free(dest); d.free(dest2); d.free(ia); d.free(ib); d.free(cnt); d.free(off);
+	d.free(ln); d.free(start);
+	d.free(tab.key); d.free(tab.first); d.free(tab.id);
+	d.free(gt.key); d.free(gt.first); d.free(gt.win); d.free(gt.id);
+	d.free(g_ent); d.free(g_pos);
+	std::vector<uint64_t> hits_all = sc_allgather_u64(d, sc, n_recv), parsed_all = sc_allgather_u64(d, sc, st.n_parsed);
+	st.n_hits = st.n_parsed = 0;
+	for (int r = 0; r < G; ++r) st.n_hits += hits_all[r], st.n_parsed += parsed_all[r];
+	st.n_seq = n_seq, st.max_qs_bits = bits_for(max_qs);
+	dh_sort(d, h, st.max_qs_bits);
 }

@@ -20,3 +20,9 @@ struct IngestStats { uint64_t n_lines, n_parsed, n_hits, n_seq, tot_len; uint32_
 void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min_match, int bi_dir,
                 DHits &h, DNames &names, IngestStats &st);
 void names_free(MabDev &d, DNames &n);
+
+struct ShardComm;
+// Sharded variant: this rank's byte range of the PAF in, the hits of the reads this rank owns out.
+// *name_text_out receives a device buffer with all read names packed (names.off indexes it); the caller frees it.
+void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len, int min_span, int min_match, int bi_dir,
+                        DHits &h, DNames &names, char **name_text_out, IngestStats &st);

@@ -28,6 +28,7 @@ typedef struct {
 	uint32_t lowid_ppm;      /* per-million chance of a low-identity line (ml = bl/50) */
 	uint32_t shuffle;        /* shuffle line order */
 	uint32_t flip_ppm;       /* per-million chance to swap q/t role is fixed at 50%; this adds CR line ends */
+	uint32_t name_base;      /* added to every read number: disjoint names for the partitions of a multi-GPU run */
 } pafgen_opt_t;
 
 typedef struct { uint64_t n_lines, n_bytes, genome_len; uint32_t n_reads_total; } pafgen_stat_t;
@@ -108,7 +109,7 @@ size_t pafgen_generate(const pafgen_opt_t *o, char **out, pafgen_stat_t *st)
 		r[i].len = o->len_min + (uint32_t)rnd_below(&rng, (uint64_t)o->len_max - o->len_min + 1);
 		r[i].start = rnd_below(&rng, G - r[i].len + 1);
 		r[i].rev = sm64(&rng) >> 63;
-		r[i].name = perm[i];
+		r[i].name = perm[i] + o->name_base;
 	}
 	for (k = 0; k < o->n_hot; ++k) {
 		uint64_t locus = rnd_below(&rng, G - o->len_max - o->hot_span);
@@ -116,7 +117,7 @@ size_t pafgen_generate(const pafgen_opt_t *o, char **out, pafgen_stat_t *st)
 			r[i].len = o->len_min + (uint32_t)rnd_below(&rng, (uint64_t)o->len_max - o->len_min + 1);
 			r[i].start = locus + rnd_below(&rng, o->hot_span + 1);
 			r[i].rev = sm64(&rng) >> 63;
-			r[i].name = perm[i];
+			r[i].name = perm[i] + o->name_base;
 		}
 	}
 	free(perm);
@@ -194,7 +195,7 @@ int main(int argc, char *argv[])
 	size_t len;
 	int c;
 	pafgen_defaults(&o);
-	while ((c = getopt(argc, argv, "n:l:L:c:m:j:s:H:R:W:d:S:I:D:xC:")) >= 0) {
+	while ((c = getopt(argc, argv, "n:l:L:c:m:j:s:H:R:W:d:S:I:D:xC:B:")) >= 0) {
 		if (c == 'n') o.n_reads = strtoul(optarg, 0, 10);
 		else if (c == 'l') o.len_min = atoi(optarg);
 		else if (c == 'L') o.len_max = atoi(optarg);
@@ -211,6 +212,7 @@ int main(int argc, char *argv[])
 		else if (c == 'D') o.lowid_ppm = atoi(optarg);
 		else if (c == 'C') o.flip_ppm = atoi(optarg);
 		else if (c == 'x') o.shuffle = 1;
+		else if (c == 'B') o.name_base = strtoul(optarg, 0, 10);
 	}
 	if (o.len_max < o.len_min) o.len_max = o.len_min;
 	len = pafgen_generate(&o, &buf, &st);

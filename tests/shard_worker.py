@@ -1,0 +1,40 @@
+"""One rank of the sharded parity run (launched by tests/test_shard_gpu.py through torch.distributed.run).
+argv: paf_path out_gfa_path"""
+import ctypes as C
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from miniasm_b200 import capi, sharded  # noqa: E402
+
+
+def main():
+    paf, out = sys.argv[1], sys.argv[2]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")                      # only carries the 128-byte NCCL id; the data path is NCCL inside the library
+    lib = capi.load_product()
+    lib.set_verbose(0)
+    ctx = lib.mab_create(local)
+    sharded.init(lib, ctx, rank, world)
+    data = open(paf, "rb").read()
+    b, e = sharded.split_ranges(data, world)[rank]
+    part = data[b:e]
+    lib.mab_load_paf_text(ctx, part, len(part))
+    opt = lib.default_opt()
+    sharded.run(lib, ctx, opt)
+    if rank == 0:
+        d, sub, ug = lib.mab_export_dict(ctx), lib.mab_export_sub(ctx), lib.mab_export_ug(ctx)
+        text = lib.print_to_string("ma_ug_print", ug, d, sub)
+        with open(out, "wb") as f:
+            f.write(text)
+    dist.barrier()
+    lib.mab_destroy(ctx)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
