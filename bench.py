@@ -180,6 +180,9 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    saved_stdout = os.dup(1)                  # libraries (NCCL banner ...) must not add lines to stdout: the JSON line is the only one
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from miniasm_b200 import capi
@@ -319,6 +322,8 @@ def main():
                        "seconds_by_function": {k: round(v, 4) for k, v in t.items() if isinstance(v, float) and k not in ("total", "wall")}}
             except Exception as ex:  # noqa: BLE001
                 cpu = {"value": None, "error": str(ex)}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps({
             "metric": "paf_overlaps_per_sec_ingest_to_gfa", "value": lines_all * a.steps / (dev_ms * 1e-3), "unit": "PAF records/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
@@ -338,7 +343,8 @@ def main():
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_del_trans_warp",
                          "algorithmic_bytes": alg_bytes, "formula": "16*n_arc + 16*inner_iters + 1*n_arc + 12*n_vtx"},
             "cpu_baseline": cpu, "clocks": clocks, "wall_s_timed_region": wall_dev, "wall_ms_per_step": wall_dev / a.steps * 1e3,
-        }))
+        }), flush=True)
+        os.dup2(2, 1)
     lib.mab_event_destroy(e0), lib.mab_event_destroy(e1)
     lib.mab_destroy(ctx)
     if world > 1:

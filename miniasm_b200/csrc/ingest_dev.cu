@@ -680,9 +680,20 @@ __global__ void k_hit_emit_gid(const PLine *ln, uint64_t n_lines, const uint32_t
 	if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_qs, mx);
 }
 
-__global__ void k_dest_count(const uint32_t *dest, uint64_t n, unsigned long long *cnt) // cnt[world]
+// bucket sizes from the SORTED destination keys: bucket g = [lower_bound(g), lower_bound(g+1)); one thread per rank
+// (a per-element atomicAdd on `world` counters serialised 100 M atomics on two addresses: 85 ms at N=2)
+__global__ void k_dest_bounds(const uint32_t *sorted_dest, uint64_t n, uint32_t world, unsigned long long *cnt)
 {
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) atomicAdd(&cnt[dest[i]], 1ull);
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= world) return;
+	uint64_t lo[2];
+	for (int k = 0; k < 2; ++k) {
+		uint64_t a = 0, b = n;
+		const uint32_t key = g + k;
+		while (a < b) { const uint64_t m = (a + b) >> 1; if (sorted_dest[m] < key) a = m + 1; else b = m; }
+		lo[k] = a;
+	}
+	cnt[g] = lo[1] - lo[0];
 }
 
 __global__ void k_gather_hits(const DHit *a, const uint32_t *pos, uint64_t n, DHit *out)
@@ -726,6 +737,7 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		MAB_LAUNCH(d, k_nl_write, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, base, start + 1);
 		d.free(cnt); d.free(base);
 	}
+	d.trace("shard-ingest:line_starts");
 	PLine *ln = mab_alloc<PLine>(d, n_lines);
 	std::vector<uint64_t> all_lines = sc_allgather_u64(d, sc, n_lines);
 	uint64_t line_base = 0, n_lines_all = 0;
@@ -755,6 +767,7 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		st.n_parsed = d.get_scal(SC_COUNT);
 		const uint64_t n_pass = d.h_scal[SC_AUX];
 		if (d.h_scal[SC_COUNT + 1]) { fprintf(stderr, "[E::miniasm_b200] a read name in the PAF is longer than 65535 bytes\n"); exit(78); }
+		d.trace("shard-ingest:parse+filter");
 		// (2) local dictionary
 		if (cap == 0) { cap = 1ull << 20; while (cap < n_pass / 4) cap <<= 1; }
 		bool bad = false, overflowed = false;
@@ -775,6 +788,7 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 			for (int r = 0; r < G; ++r) bad |= f[r] & 1, overflowed |= (f[r] >> 1) & 1;
 		}
 		if (overflowed) { d.free(tab.key); d.free(tab.first); d.free(tab.id); cap <<= 2; continue; }
+		d.trace("shard-ingest:local dictionary");
 		// (3) distinct names of this rank -> entries + packed names, all-gathered
 		uint32_t n_ent = 0;
 		uint64_t *slots = mab_alloc<uint64_t>(d, cap);
@@ -835,6 +849,7 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		(void)my_ent_off; (void)my_name_off;
 		d.free(ent); d.free(nsz); d.free(npos); if (my_names) d.free(my_names);
 		d.free(slots);
+		d.trace("shard-ingest:name all-gather");
 		// (4) global table (replicated): same insert on every rank -> same result
 		uint64_t gcap = 1ull << 16; while (gcap < 2 * n_ent_all + 2) gcap <<= 1;
 		gt.key = (unsigned long long*)mab_alloc<uint64_t>(d, gcap); gt.first = (unsigned long long*)mab_alloc<uint64_t>(d, gcap);
@@ -858,6 +873,7 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		++st.hash_retries;
 		if (attempt > 16) { fprintf(stderr, "[E::miniasm_b200] read-name hashing keeps colliding\n"); exit(77); }
 	}
+	d.trace("shard-ingest:global table");
 	// (5) global ids = rank of the global first occurrence
 	uint32_t n_seq;
 	{
@@ -896,6 +912,7 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		d.free(slots);
 	}
 	*name_text_out = g_names; // names.off points into this buffer (owned by the caller from now on)
+	d.trace("shard-ingest:global ids");
 	// (6) local hits with global ids, bucketed by owner rank, exchanged
 	uint32_t *cnt = mab_alloc<uint32_t>(d, n_lines + 1);
 	uint64_t *off = mab_alloc<uint64_t>(d, n_lines + 1);
@@ -920,7 +937,6 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 	MAB_CUDA(cudaMemsetAsync(d.d_scal + 16, 0, 32 * 8, d.stream));
 	if (n_loc) {
 		MAB_LAUNCH(d, k_hit_emit_gid, mab_grid(n_lines, 256), 256, 0, ln, n_lines, cnt, off, (uint32_t)G, loc, dest, (unsigned*)(d.d_scal + SC_AUX));
-		MAB_LAUNCH(d, k_dest_count, mab_grid(n_loc, 256), 256, 0, dest, n_loc, d.d_scal + 16);
 		MAB_LAUNCH(d, k_iota32, mab_grid(n_loc, 256), 256, 0, ia, n_loc);
 		cub::DoubleBuffer<uint32_t> dk(dest, dest2), dv(ia, ib);
 		size_t tb = 0;
@@ -930,7 +946,9 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int64_t)n_loc, 0, eb, d.stream); // stable: file order kept inside every bucket
 		++d.n_lib;
 		MAB_LAUNCH(d, k_gather_hits, mab_grid(n_loc, 256), 256, 0, loc, dv.Current(), n_loc, snd);
+		MAB_LAUNCH(d, k_dest_bounds, 1, 32, 0, dk.Current(), n_loc, (uint32_t)G, d.d_scal + 16);
 	}
+	d.trace("shard-ingest:emit+bucket hits");
 	if (G > 32) { fprintf(stderr, "[E::miniasm_b200] more than 32 ranks\n"); exit(79); }
 	uint32_t max_qs = (uint32_t)(d.get_scal(SC_AUX) & 0xffffffffu);
 	std::vector<uint64_t> send_cnt(G), recv_cnt(G);
@@ -957,6 +975,7 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		else if (n_loc) MAB_CUDA(cudaMemcpyAsync(h.a, snd, n_loc * sizeof(DHit), cudaMemcpyDeviceToDevice, d.stream));
 	}
 	h.n = n_recv, h.n_seq = n_seq;
+	d.trace("shard-ingest:all-to-all");
 	{ // sort key width must cover the largest query start of any rank
 		std::vector<uint64_t> mq = sc_allgather_u64(d, sc, max_qs);
 		for (int r = 0; r < G; ++r) if (mq[r] > max_qs) max_qs = (uint32_t)mq[r];
@@ -972,4 +991,5 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 	for (int r = 0; r < G; ++r) st.n_hits += hits_all[r], st.n_parsed += parsed_all[r];
 	st.n_seq = n_seq, st.max_qs_bits = bits_for(max_qs);
 	dh_sort(d, h, st.max_qs_bits);
+	d.trace("shard-ingest:sort");
 }
