@@ -542,8 +542,12 @@ extern "C" int mab_test_parse_line(const char *line, size_t len, uint32_t *out)
 // =============================================================================================================
 __global__ void k_last_bl(const PLine *ln, uint64_t n_lines, unsigned long long *out) // out[0] = 1 + index of the last line with an 11th field
 {
+	unsigned long long mx = 0; // per-thread maximum over its grid-stride share, one atomic per warp at the end
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x)
-		if (ln[i].nf >= 11) atomicMax(out, (unsigned long long)(i + 1));
+		if (ln[i].nf >= 11) mx = i + 1;
+	#pragma unroll
+	for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o); mx = t > mx ? t : mx; }
+	if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
 }
 
 struct GEntry { unsigned long long hash, first; uint32_t slen, nlen; }; // a distinct name of one rank, 24 bytes

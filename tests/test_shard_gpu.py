@@ -21,9 +21,12 @@ def n_gpus():
         return 0
 
 
+WORLDS = [w for w in (2, 3, 4, 8) if w <= n_gpus()]
+
+
 @pytest.mark.skipif(n_gpus() < 2, reason="needs at least 2 GPUs")
 @pytest.mark.parametrize("name", ["chaos_small", "chaos", "bubbles800", "tiny_exact", "shuffled", "lowcov"])
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", WORLDS or [2])
 def test_sharded_gfa_equals_reference(name, world, built, paf_dir):
     paf = synth.generate(name, f"{paf_dir}/sh_{name}.paf")
     out = f"{paf_dir}/sh_{name}_{world}.gfa"
