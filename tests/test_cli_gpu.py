@@ -150,3 +150,17 @@ def test_link_seam(opts, pafs):
         assert sorted(out_s.splitlines()) == sorted(out_r.splitlines())
     else:
         assert out_s == out_r
+
+
+@pytest.mark.parametrize("content", [b"", b"\n", b"\n\n\n", b"not a paf line\n", b"a\t1\t2\n",
+                                     b"q\t5000\t0\t4000\t+\tt\t5000\t1000\t5000\t800\t4000\t255\n",            # one overlap: too shallow for min_dp
+                                     b"q\t5000\t0\t100\t+\tt\t5000\t0\t100\t80\t100\t255\n",                   # below min_span: nothing stored
+                                     b"q\t5000\t0\t4000\t+\tq\t5000\t1000\t5000\t800\t4000\t255\n"])           # self hit only
+def test_degenerate_inputs(content, paf_dir):
+    """Empty / all-filtered / single-line inputs: same (possibly empty) output and exit status as the reference."""
+    path = os.path.join(paf_dir, "degenerate.paf")
+    with open(path, "wb") as f:
+        f.write(content)
+    same([path])
+    same(["-S", "2", "-p", "paf", path], exact=False)
+    same(["-p", "sg", path], exact=False)
