@@ -104,3 +104,49 @@ def test_no_cont_prefilter_against_reference(built, ref, paf_dir):
     na = [a.contents.seq[i].name for i in range(a.contents.n_seq)]
     nb = [b.contents.seq[i].name for i in range(b.contents.n_seq)]
     assert na == nb and len(na) > 10
+
+
+def test_device_parser_matches_host_reader(built, paf_dir):
+    """The GPU line parser (ingest_dev.cu parse_line, compiled for the host through mab_test_parse_line) against the host
+    reader on ~140 K lines with CRLF, 9/10-field lines, tags, signs, junk, blanks, empty lines."""
+    from tests.test_cli_gpu import test_weird_lines  # noqa: F401  (same recipe, rebuilt here without the GPU)
+    prod = capi.load_product()
+    f = prod.dll.mab_test_parse_line
+    f.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32)]
+    base = synth.generate("-n 3000 -s 31 -j 200 -C 200000", os.path.join(paf_dir, "pw_base.paf"))
+    out = []
+    for i, ln in enumerate(open(base, "rb").read().split(b"\n")):
+        if not ln:
+            continue
+        fl = ln.rstrip(b"\r").split(b"\t")
+        if i % 11 == 0 and i > 0:
+            out.append(b"\t".join(fl[:10]))
+        elif i % 13 == 0:
+            out.append(b"\t".join(fl[:9]))
+        elif i % 17 == 0:
+            out.append(ln + b"\ttp:A:S\tcm:i:12")
+        elif i % 19 == 0:
+            out += [b"", ln]
+        elif i % 23 == 0:
+            fl[2] = b"+" + fl[2]; fl[9] = fl[9] + b"xyz"; fl[7] = b"-" + fl[7]; out.append(b"\t".join(fl))
+        elif i % 29 == 0:
+            fl[1] = b" " + fl[1]; fl[6] = b"000000000000000000000" + fl[6]; out.append(b"\t".join(fl) + b"\r")
+        elif i % 31 == 0:
+            fl[3] = b"99999999999999999999999"; fl[8] = b"-99999999999999999999999"; out.append(b"\t".join(fl))
+        else:
+            out.append(ln)
+    path = os.path.join(paf_dir, "pw.paf")
+    with open(path, "wb") as fo:
+        fo.write(b"\n".join(out))
+    want = paf_records(prod, path)
+    got, stale = [], 0
+    for ln in out:
+        o = (C.c_uint32 * 13)()
+        f(ln, len(ln), o)
+        o = list(o)
+        if o[0] >= 11:
+            stale = o[9]
+        if o[0] >= 10:
+            l2 = ln[:-1] if len(ln) > 1 and ln.endswith(b"\r") else ln
+            got.append((l2[:o[10]], o[1], o[2], o[3], o[4], l2[o[12]:o[12] + o[11]], o[5], o[6], o[7], o[8], o[9] if o[0] >= 11 else stale))
+    assert len(got) == len(want) > 100000 and got == want
