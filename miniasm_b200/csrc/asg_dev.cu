@@ -332,17 +332,14 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 	__shared__ uint32_t s_fmin[DT_WARPS][DT_HASH];
 	__shared__ uint64_t s_ti[DT_WARPS][DT_EAGER];
 	__shared__ uint8_t  s_hmark[DT_WARPS][DT_HASH];
-	__shared__ uint8_t  s_hent[DT_WARPS][DT_HASH];   // slab position of the entry that created the slot (fast path)
 	__shared__ uint8_t  s_slot[DT_WARPS][DT_MAXD];
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	uint32_t *hkey = s_hkey[warp], *tl = s_tl[warp], *fmin = s_fmin[warp];
 	uint64_t *ti = s_ti[warp];
-	uint8_t *hmark = s_hmark[warp], *slot = s_slot[warp], *hent = s_hent[warp];
+	uint8_t *hmark = s_hmark[warp], *slot = s_slot[warp];
 	unsigned n_red = 0;
 	unsigned long long n_inner = 0;
-	for (uint32_t i = lane; i < DT_HASH; i += 32) hkey[i] = DT_EMPTY; // invariant: the table is empty between vertices
-	__syncwarp();
 
 	for (uint32_t vi = blockIdx.x * DT_WARPS + warp; vi < n_vtx; vi += gridDim.x * DT_WARPS) {
 		const uint32_t v = list ? list[vi] : vi;
@@ -359,94 +356,6 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 			continue;
 		}
 		const uint32_t mask = nv <= 16 ? 31u : (0xffffffffu >> __clz(2 * nv - 1)); // table = next power of two >= 2*nv, at least 32 slots
-		if (nv <= 64) {
-			// ---- fast path (nearly every vertex): both entries of a lane stay in registers, a probe that promotes a
-			// mark writes the arc's flag right away (flag[] is pre-zeroed), the table is emptied by un-writing the slots
-			const bool v0 = lane < nv, v1 = lane + 32 < nv;
-			uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
-			if (v0) a0 = ld_arc4(arc + off + lane);
-			if (v1) a1 = ld_arc4(arc + off + lane + 32);
-			uint32_t s0 = 0, s1 = 0;
-			bool dup = false;
-			if (v0) {
-				if (lane < DT_EAGER) ti[lane] = __ldg(idx + a0.z);
-				uint32_t h = dt_hash(a0.z, mask);
-				for (;;) {
-					const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a0.z);
-					if (prev == DT_EMPTY) { hmark[h] = 1; hent[h] = (uint8_t)lane; break; }
-					if (prev == a0.z) { dup = true; break; }
-					h = (h + 1) & mask;
-				}
-				s0 = h;
-			}
-			if (v1) {
-				uint32_t h = dt_hash(a1.z, mask);
-				for (;;) {
-					const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a1.z);
-					if (prev == DT_EMPTY) { hmark[h] = 1; hent[h] = (uint8_t)(lane + 32); break; }
-					if (prev == a1.z) { dup = true; break; }
-					h = (h + 1) & mask;
-				}
-				s1 = h;
-			}
-			const bool any_dup = __any_sync(0xffffffffu, dup);
-			__syncwarp();
-			if (!any_dup) {
-				const uint32_t last = nv - 1;
-				const uint32_t L = __shfl_sync(0xffffffffu, last < 32 ? a0.x : a1.x, last & 31) + fuzz;
-				for (uint32_t i = 0;;) {
-					const bool l0 = v0 && lane >= i && hmark[s0] == 1, l1 = v1 && lane + 32 >= i && hmark[s1] == 1;
-					const unsigned m0 = __ballot_sync(0xffffffffu, l0), m1 = __ballot_sync(0xffffffffu, l1);
-					if (m0) i = __ffs(m0) - 1;
-					else if (m1) i = 32 + __ffs(m1) - 1;
-					else break;
-					const uint32_t w = __shfl_sync(0xffffffffu, i < 32 ? a0.z : a1.z, i & 31);
-					const uint32_t li = __shfl_sync(0xffffffffu, i < 32 ? a0.x : a1.x, i & 31);
-					const uint64_t iw = i < DT_EAGER ? ti[i] : __ldg(idx + w);
-					const uint32_t nw = (uint32_t)iw;
-					const DArc *pw = arc + (iw >> 32) + lane;
-					for (uint32_t j0 = 0; j0 < nw; j0 += 64, pw += 64) {
-						const bool in0 = j0 + lane < nw, in1 = j0 + 32 + lane < nw;
-						uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
-						if (in0) b0 = ld_arc4(pw);
-						if (in1) b1 = ld_arc4(pw + 32);
-						const bool ok0 = in0 && b0.x + li <= L, ok1 = in1 && b1.x + li <= L;
-						const unsigned k0 = __ballot_sync(0xffffffffu, ok0), k1 = __ballot_sync(0xffffffffu, ok1);
-						const unsigned pre0 = k0 == 0xffffffffu ? k0 : ((1u << (__ffs(~k0) - 1)) - 1);
-						const unsigned pre1 = k0 != 0xffffffffu ? 0u : (k1 == 0xffffffffu ? k1 : ((1u << (__ffs(~k1) - 1)) - 1));
-						if (pre0 >> lane & 1) {
-							uint32_t h = dt_hash(b0.z, mask);
-							for (;;) {
-								const uint32_t kx = hkey[h];
-								if (kx == b0.z) { hmark[h] = 2; flag[off + hent[h]] = 1; break; }
-								if (kx == DT_EMPTY) break;
-								h = (h + 1) & mask;
-							}
-						}
-						if (pre1 >> lane & 1) {
-							uint32_t h = dt_hash(b1.z, mask);
-							for (;;) {
-								const uint32_t kx = hkey[h];
-								if (kx == b1.z) { hmark[h] = 2; flag[off + hent[h]] = 1; break; }
-								if (kx == DT_EMPTY) break;
-								h = (h + 1) & mask;
-							}
-						}
-						if (STATS && lane == 0) n_inner += __popc(pre0) + __popc(pre1);
-						if (k0 != 0xffffffffu || k1 != 0xffffffffu) break;
-					}
-					__syncwarp();
-					++i;
-				}
-				n_red += (v0 && hmark[s0] == 2) + (v1 && hmark[s1] == 2);
-			}
-			__syncwarp();
-			if (v0) hkey[s0] = DT_EMPTY;
-			if (v1) hkey[s1] = DT_EMPTY;
-			__syncwarp();
-			if (!any_dup) continue;
-			// multi-arcs: take the general path below, which applies the lowest-slab-position rule
-		}
 		if (mask == 31) hkey[lane] = DT_EMPTY;
 		else for (uint32_t i = lane * 4; i <= mask; i += 128) *reinterpret_cast<uint4*>(hkey + i) = make_uint4(DT_EMPTY, DT_EMPTY, DT_EMPTY, DT_EMPTY);
 		__syncwarp();
@@ -550,8 +459,6 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 			flag[off + i] = r;
 			n_red += r;
 		}
-		__syncwarp();
-		for (uint32_t i = lane; i <= mask; i += 32) hkey[i] = DT_EMPTY; // keep the table empty for the next vertex
 		__syncwarp();
 	}
 	n_red = __reduce_add_sync(0xffffffffu, n_red);
@@ -740,11 +647,11 @@ uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo
 	if (g.n_arc) {
 		flag = mab_alloc<uint8_t>(d, g.n_arc);
 		uint32_t *big = mab_alloc<uint32_t>(d, n_vtx);
+		// no memset of flag[]: every arc lies in the slab of exactly one vertex, and every vertex with arcs writes its slab's flags
 		MAB_CUDA(cudaMemsetAsync(d.d_scal, 0, 10 * sizeof(unsigned long long), d.stream));
 		cudaEvent_t e0, e1;
 		MAB_CUDA(cudaEventCreate(&e0)); MAB_CUDA(cudaEventCreate(&e1));
 		MAB_CUDA(cudaEventRecord(e0, d.stream));
-		MAB_CUDA(cudaMemsetAsync(flag, 0, g.n_arc, d.stream)); // the fast path only writes the flags it raises (inside the timed region on purpose)
 		unsigned grid = (n_vtx + DT_WARPS - 1) / DT_WARPS;
 		if (grid > 148u * 64u) grid = 148u * 64u;
 		// the inner-iteration counter (for the roofline arithmetic) costs issue slots: only counted when asked for

@@ -208,7 +208,7 @@ k_sub_sweep(const uint64_t *key, const uint64_t *grp, uint32_t n_seq, int min_dp
 // with more hits than a CTA can hold go through the device-wide sort above.
 constexpr int SUBW_WARPS = 8;
 constexpr int SUBW_HITS = 256;               // per warp: 512 keys = 2 KB
-constexpr int SUBC_HITS = 12288;             // per CTA: 24576 keys = 96 KB of dynamic shared memory
+constexpr int SUBC_HITS = 16384;             // per CTA: 32768 keys = 128 KB of dynamic shared memory (a power of two: the bitonic network pads up to it)
 
 // depth sweep over n sorted keys in shared memory by one warp; returns the interval through *out (lane 0 writes)
 __device__ __forceinline__ bool sub_sweep_smem(const uint32_t *key, uint32_t n, int min_dp, uint32_t clip, DSub *out, int lane)

@@ -127,11 +127,11 @@ def test_empty_inputs(prod):
 
 
 def test_sub_group_sizes(ref, prod):
-    """Groups beyond the warp kernel (256 hits), beyond the CTA kernel (12288 hits) and tiny ones, in one array:
+    """Groups beyond the warp kernel (256 hits), beyond the CTA kernel (16384 hits) and tiny ones, in one array:
     the shared-memory paths and the device-wide-sort fallback of ma_hit_sub must agree with the reference."""
     rng = np.random.default_rng(9)
     rows = []
-    sizes = {0: 3, 1: 40, 2: 256, 3: 257, 4: 700, 5: 5000, 6: 12288, 7: 12289, 8: 20000, 9: 1}
+    sizes = {0: 3, 1: 40, 2: 256, 3: 257, 4: 700, 5: 5000, 6: 16384, 7: 16385, 8: 20000, 9: 1, 10: 9000, 11: 12288}
     for q, n in sizes.items():
         qs = rng.integers(0, 30000, size=n)
         ln = rng.integers(500, 20000, size=n)
