@@ -45,6 +45,23 @@ __device__ __forceinline__ uint4 ld_arc4(const DArc *p)
 	return t;
 }
 
+// Where the slab of a NEIGHBOUR vertex lives.  Single GPU: peer == nullptr, slab = arc + (idx[w] >> 32).
+// Sharded run with peer access: nidx[w] is (offset in the owner's arc array) << 32 | count, owner = orig[w >> 1] % world
+// (orig == nullptr: identity) and peer[owner] is that rank's arc array mapped through CUDA IPC -- the transitive
+// reduction then reads remote slabs over NVLink as it needs them instead of first all-gathering every arc.
+struct SlabView {
+	const DArc *const *peer;
+	const uint64_t *nidx;
+	const uint32_t *orig;
+	uint32_t world;
+};
+__device__ __forceinline__ const DArc *slab_base(const SlabView &sv, const DArc *arc, uint32_t w)
+{
+	if (sv.peer == nullptr) return arc;
+	const uint32_t r = (sv.orig ? __ldg(sv.orig + (w >> 1)) : (w >> 1)) % sv.world;
+	return sv.peer[r];
+}
+
 static inline uint32_t bits_for(uint64_t x) { uint32_t b = 0; while (x) ++b, x >>= 1; return b ? b : 1; }
 
 void dg_reserve(MabDev &d, DGraph &g, size_t m_arc)
@@ -324,7 +341,8 @@ template <bool STATS>
 __global__ void __launch_bounds__(DT_WARPS * 32, 6)
 k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, const uint32_t *__restrict__ seq,
                  uint32_t n_vtx, uint32_t fuzz, uint8_t *__restrict__ flag,
-                 uint32_t *__restrict__ big_list, unsigned long long *scal, const uint32_t *__restrict__ list, uint32_t own_lo, uint32_t own_hi)
+                 uint32_t *__restrict__ big_list, unsigned long long *scal, const uint32_t *__restrict__ list, uint32_t own_lo, uint32_t own_hi,
+                 SlabView sv)
 {	// list == nullptr: every vertex 0..n_vtx-1; otherwise the n_vtx vertices named by list[]
 	// [own_lo, own_hi): arc positions this rank is responsible for (sharded runs); a vertex is processed iff its slab starts there
 	__shared__ __align__(16) uint32_t s_hkey[DT_WARPS][DT_HASH];
@@ -370,7 +388,7 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 			if (v1) a1 = ld_arc4(arc + off + i1);
 			if (v0) {
 				tl[i0] = a0.x;
-				if (i0 < DT_EAGER) ti[i0] = __ldg(idx + a0.z);
+				if (i0 < DT_EAGER) ti[i0] = __ldg((sv.peer ? sv.nidx : idx) + a0.z);
 				uint32_t h = dt_hash(a0.z, mask);
 				for (;;) {
 					const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a0.z);
@@ -409,9 +427,9 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 			if (nxt >= nv) break;
 			i = nxt;
 			const uint32_t w = hkey[slot[i]], li = tl[i];
-			const uint64_t iw = i < DT_EAGER ? ti[i] : __ldg(idx + w);
+			const uint64_t iw = i < DT_EAGER ? ti[i] : __ldg((sv.peer ? sv.nidx : idx) + w);
 			const uint32_t nw = (uint32_t)iw;
-			const DArc *pw = arc + (iw >> 32) + lane;
+			const DArc *pw = slab_base(sv, arc, w) + (iw >> 32) + lane;
 			for (uint32_t j0 = 0; j0 < nw; j0 += 64, pw += 64) {
 				const bool in0 = j0 + lane < nw, in1 = j0 + 32 + lane < nw;
 				uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
@@ -476,7 +494,7 @@ constexpr size_t DT_BIG_SMEM = (size_t)DT_BIG_MAXD * 4 + (size_t)DT_BIG_HASH * 4
 
 __global__ void __launch_bounds__(256)
 k_del_trans_cta(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, uint32_t fuzz, uint8_t *__restrict__ flag,
-                const uint32_t *__restrict__ big_list, uint32_t n_big, uint32_t *__restrict__ huge_list, unsigned long long *scal)
+                const uint32_t *__restrict__ big_list, uint32_t n_big, uint32_t *__restrict__ huge_list, unsigned long long *scal, SlabView sv)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	uint32_t *tv = (uint32_t*)smem;
@@ -515,9 +533,9 @@ k_del_trans_cta(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, 
 		const uint32_t L = (uint32_t)arc[off + nv - 1].ul + fuzz;
 		for (uint32_t i = 0; i < nv; ++i) {
 			if (st[rep[i]] != 1) continue; // uniform: shared state, barrier at the end of the previous round
-			const uint64_t iw = idx[tv[i]];
+			const uint64_t iw = (sv.peer ? sv.nidx : idx)[tv[i]];
 			const uint32_t nw = (uint32_t)iw, li = (uint32_t)arc[off + i].ul;
-			const DArc *aw = arc + (iw >> 32);
+			const DArc *aw = slab_base(sv, arc, tv[i]) + (iw >> 32);
 			// the scan stops at the first j violating the bound; lengths ascend, so find it per chunk
 			for (uint32_t j0 = 0; j0 < nw; j0 += nt) {
 				if (tid == 0) s_go = 0xffffffffu;
@@ -567,7 +585,7 @@ k_del_trans_cta(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, 
 // reference's own formulation (mark[] indexed by target vertex), the j loop spread over the CTA.
 __global__ void __launch_bounds__(1024)
 k_del_trans_huge(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, uint32_t fuzz, uint8_t *__restrict__ flag,
-                 const uint32_t *__restrict__ huge_list, uint32_t n_huge, uint8_t *mark, uint32_t *first_pos, unsigned long long *scal)
+                 const uint32_t *__restrict__ huge_list, uint32_t n_huge, uint8_t *mark, uint32_t *first_pos, unsigned long long *scal, SlabView sv)
 {
 	__shared__ uint32_t s_go, s_red;
 	__shared__ unsigned long long s_inner;
@@ -584,9 +602,9 @@ k_del_trans_huge(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 		for (uint32_t i = 0; i < nv; ++i) {
 			const uint32_t w = arc[off + i].v;
 			if (mark[w] != 1) continue;
-			const uint64_t iw = idx[w];
+			const uint64_t iw = (sv.peer ? sv.nidx : idx)[w];
 			const uint32_t nw = (uint32_t)iw, li = (uint32_t)arc[off + i].ul;
-			const DArc *aw = arc + (iw >> 32);
+			const DArc *aw = slab_base(sv, arc, w) + (iw >> 32);
 			for (uint32_t j0 = 0; j0 < nw; j0 += nt) {
 				if (tid == 0) s_go = 0xffffffffu;
 				__syncthreads();
@@ -625,7 +643,7 @@ k_del_trans_huge(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz)
 {
 	uint8_t *flag = nullptr;
-	uint32_t n_reduced = dg_del_trans_flags(d, g, fuzz, 0, 0xffffffffu, &flag);
+	uint32_t n_reduced = dg_del_trans_flags(d, g, fuzz, 0, 0xffffffffu, &flag, nullptr, nullptr, nullptr, 1);
 	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] transitively reduced %d arcs\n", "asg_arc_del_trans", n_reduced);
 	if (n_reduced) {
 		dg_cleanup(d, g, flag);
@@ -637,8 +655,10 @@ uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz)
 
 // the marking part of asg_arc_del_trans for the vertices whose slabs start in [own_lo, own_hi): one flag byte per arc
 // of those slabs (other positions of *flag_out are not written); returns the number of arcs flagged
-uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo, uint32_t own_hi, uint8_t **flag_out)
+uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo, uint32_t own_hi, uint8_t **flag_out,
+                            const DArc *const *peer, const uint64_t *nidx, const uint32_t *orig, uint32_t world)
 {
+	SlabView sv{peer, nidx, orig, world};
 	const uint32_t n_vtx = g.n_seq * 2;
 	uint32_t n_reduced = 0;
 	memset(&g_del_trans_stats, 0, sizeof(g_del_trans_stats));
@@ -655,8 +675,8 @@ uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo
 		unsigned grid = (n_vtx + DT_WARPS - 1) / DT_WARPS;
 		if (grid > 148u * 64u) grid = 148u * 64u;
 		// the inner-iteration counter (for the roofline arithmetic) costs issue slots: only counted when asked for
-		if (mab_del_trans_count_inner) MAB_LAUNCH(d, k_del_trans_warp<true>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr, own_lo, own_hi);
-		else MAB_LAUNCH(d, k_del_trans_warp<false>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr, own_lo, own_hi);
+		if (mab_del_trans_count_inner) MAB_LAUNCH(d, k_del_trans_warp<true>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr, own_lo, own_hi, sv);
+		else MAB_LAUNCH(d, k_del_trans_warp<false>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr, own_lo, own_hi, sv);
 		MAB_CUDA(cudaEventRecord(e1, d.stream));
 		uint32_t n_big = (uint32_t)d.get_scal(SC_BIG);
 		float ms = 0;
@@ -670,14 +690,14 @@ uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo
 				attr_set = true;
 			}
 			uint32_t *huge = mab_alloc<uint32_t>(d, n_big);
-			MAB_LAUNCH(d, k_del_trans_cta, n_big < 148u * 2 ? n_big : 148u * 2, 256, DT_BIG_SMEM, g.arc, g.idx, fuzz, flag, big, n_big, huge, d.d_scal);
+			MAB_LAUNCH(d, k_del_trans_cta, n_big < 148u * 2 ? n_big : 148u * 2, 256, DT_BIG_SMEM, g.arc, g.idx, fuzz, flag, big, n_big, huge, d.d_scal, sv);
 			uint32_t n_huge = (uint32_t)d.get_scal(SC_AUX2);
 			if (n_huge) {
 				uint8_t *mark = mab_alloc<uint8_t>(d, n_vtx);
 				uint32_t *first_pos = mab_alloc<uint32_t>(d, n_vtx);
 				MAB_CUDA(cudaMemsetAsync(mark, 0, n_vtx, d.stream));
 				MAB_CUDA(cudaMemsetAsync(first_pos, 0xff, (size_t)n_vtx * 4, d.stream));
-				MAB_LAUNCH(d, k_del_trans_huge, 1, 1024, 0, g.arc, g.idx, fuzz, flag, huge, n_huge, mark, first_pos, d.d_scal);
+				MAB_LAUNCH(d, k_del_trans_huge, 1, 1024, 0, g.arc, g.idx, fuzz, flag, huge, n_huge, mark, first_pos, d.d_scal, sv);
 				d.free(mark); d.free(first_pos);
 			}
 			d.free(huge);

@@ -29,7 +29,9 @@ uint32_t dg_del_multi(MabDev &d, DGraph &g);     // asg.c:104-121
 uint32_t dg_del_asymm(MabDev &d, DGraph &g);     // asg.c:124-138
 void dg_symm(MabDev &d, DGraph &g);              // asg.c:140-145
 uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz);  // asg.c:148-193
-uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo, uint32_t own_hi, uint8_t **flag_out);
+// peer != null: neighbour slabs are read from peer[owner] + (nidx[w] >> 32) (sharded run with CUDA IPC peer access)
+uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo, uint32_t own_hi, uint8_t **flag_out,
+                            const DArc *const *peer = nullptr, const uint64_t *nidx = nullptr, const uint32_t *orig = nullptr, uint32_t world = 1);
 uint32_t dg_del_short(MabDev &d, DGraph &g, float ratio);    // asg.c:83-101
 
 // statistics of the last dg_del_trans call (for the roofline arithmetic in bench.py)

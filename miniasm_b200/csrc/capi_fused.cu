@@ -8,6 +8,8 @@
 #include "ingest_dev.cuh"
 #include "shard_comm.cuh"
 #include <cub/cub.cuh>
+#include <map>
+#include <string>
 #include <zlib.h>
 #include <fcntl.h>
 #include <unistd.h>
@@ -37,6 +39,7 @@ struct mab_ctx {
 	// sharded runs (mab_shard_init): communicator + the packed names of all ranks (names.off indexes it instead of d_text)
 	ShardComm sc;
 	char *name_text = nullptr;
+	std::map<std::string, void*> ipc_open;   // peer segments mapped through CUDA IPC (handle bytes -> local address)
 };
 
 __global__ void k_sg_len(uint32_t n, const DSub *sub, const uint32_t *slen, const uint32_t *orig, uint32_t *len, uint8_t *del)
@@ -122,6 +125,7 @@ void mab_destroy(mab_ctx_t *c)
 	d.free(c->d_text);
 	d.sync();
 	for (int i = 0; i < 2; ++i) if (c->pin[i]) MAB_CUDA(cudaFreeHost(c->pin[i]));
+	for (auto &kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
 	d.destroy();
 	delete c;
 }
@@ -607,13 +611,88 @@ int mab_layout_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	d.free(len); d.free(del);
 	sc_allreduce(d, sc, loc.seq, n, ncclUint32, ncclMax);   // deletion flags raised by any rank (top bit; lengths agree)
 	dg_arc_rm(d, loc, nullptr);
-	// all ranks' raw arcs, concatenated in rank order: every vertex's slab is contiguous in it, which is all the index needs
-	std::vector<uint64_t> cnt = sc_allgather_u64(d, sc, loc.n_arc);
-	uint64_t tot = 0, my_off = 0;
-	std::vector<uint64_t> bytes(G);
-	for (int r = 0; r < G; ++r) { if (r == sc.rank) my_off = tot; tot += cnt[r]; bytes[r] = cnt[r] * sizeof(DArc); }
-	if (tot >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 arcs in the gathered graph\n"); exit(73); }
 	DGraph &g = c->sg;
+	uint32_t n_keep = 0;
+	DArc *keep = nullptr;
+	uint64_t n_red_all = 0, tot = 0;
+	std::vector<uint64_t> cnt = sc_allgather_u64(d, sc, loc.n_arc);
+	for (int r = 0; r < G; ++r) tot += cnt[r];
+	if (tot >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 arcs in the graph\n"); exit(73); }
+	c->stats.n_arc_sg = tot;
+	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", (int)tot);
+	// ---- neighbour slabs: peer access over NVLink (CUDA IPC) when every rank can offer it, else an all-gather of all arcs
+	struct PeerInfo { cudaIpcMemHandle_t h; uint64_t off, ok; };
+	PeerInfo mine;
+	memset(&mine, 0, sizeof(mine));
+	{
+		char *base; size_t off;
+		const char *env = getenv("MAB_SHARD_P2P");
+		if (!(env && atoi(env) == 0) && d.arena.segment_of(loc.arc, &base, &off) && cudaIpcGetMemHandle(&mine.h, base) == cudaSuccess) mine.off = off, mine.ok = 1;
+		else cudaGetLastError();
+	}
+	std::vector<PeerInfo> peers((size_t)G);
+	{
+		PeerInfo *buf = (PeerInfo*)d.alloc(sizeof(PeerInfo) * ((size_t)G + 1));
+		MAB_CUDA(cudaMemcpyAsync(buf + G, &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice, d.stream));
+		if (sc.active()) MAB_NCCL(ncclAllGather(buf + G, buf, sizeof(PeerInfo), ncclUint8, sc.comm, d.stream));
+		else MAB_CUDA(cudaMemcpyAsync(buf, buf + G, sizeof(PeerInfo), cudaMemcpyDeviceToDevice, d.stream));
+		MAB_CUDA(cudaMemcpyAsync(peers.data(), buf, sizeof(PeerInfo) * (size_t)G, cudaMemcpyDeviceToHost, d.stream));
+		d.sync();
+		d.free(buf);
+	}
+	bool p2p = true;
+	std::vector<const DArc*> peer_ptr((size_t)G, nullptr);
+	for (int r = 0; r < G && p2p; ++r) {
+		if (!peers[r].ok) { p2p = false; break; }
+		if (r == sc.rank) { peer_ptr[r] = loc.arc; continue; }
+		std::string key((const char*)&peers[r].h, sizeof(cudaIpcMemHandle_t));
+		auto it = c->ipc_open.find(key);
+		void *base = nullptr;
+		if (it != c->ipc_open.end()) base = it->second;
+		else if (cudaIpcOpenMemHandle(&base, peers[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) c->ipc_open[key] = base;
+		else { cudaGetLastError(); p2p = false; break; }
+		peer_ptr[r] = (const DArc*)((const char*)base + peers[r].off);
+	}
+	{ // all ranks take the same route
+		std::vector<uint64_t> okv = sc_allgather_u64(d, sc, p2p ? 1 : 0);
+		for (int r = 0; r < G; ++r) p2p = p2p && okv[r] != 0;
+	}
+	if (p2p) {
+		dg_arc_index(d, loc);                                   // slabs of the vertices this rank owns
+		uint64_t *nidx = mab_alloc<uint64_t>(d, (size_t)n * 2);
+		if (n) MAB_CUDA(cudaMemcpyAsync(nidx, loc.idx, (size_t)n * 16, cudaMemcpyDeviceToDevice, d.stream));
+		sc_allreduce(d, sc, nidx, (size_t)n * 2, ncclUint64, ncclSum); // every vertex is indexed by exactly one rank
+		const DArc **d_peer = (const DArc**)d.alloc(sizeof(void*) * (size_t)G);
+		MAB_CUDA(cudaMemcpyAsync(d_peer, peer_ptr.data(), sizeof(void*) * (size_t)G, cudaMemcpyHostToDevice, d.stream));
+		uint8_t *flag = nullptr;
+		uint32_t n_red = dg_del_trans_flags(d, loc, (uint32_t)opt->gap_fuzz, 0, 0xffffffffu, &flag, d_peer, nidx, c->orig_id, (uint32_t)G);
+		c->stats.ms_del_trans_kernel = g_del_trans_stats.kernel_ms, c->stats.trans_inner = g_del_trans_stats.inner_iters;
+		std::vector<uint64_t> reds = sc_allgather_u64(d, sc, n_red);
+		for (int r = 0; r < G; ++r) n_red_all += reds[r];
+		keep = mab_alloc<DArc>(d, loc.n_arc);
+		if (loc.n_arc) {
+			uint8_t *nf = mab_alloc<uint8_t>(d, loc.n_arc);
+			MAB_LAUNCH(d, k_not_flag, mab_grid(loc.n_arc, 256), 256, 0, flag, loc.n_arc, nf);
+			size_t tb = 0;
+			unsigned long long *d_n = d.d_scal + SC_NSEL;
+			cub::DeviceSelect::Flagged(nullptr, tb, loc.arc, nf, keep, d_n, (int)loc.n_arc, d.stream);
+			void *tmp = d.tmp(tb);
+			cub::DeviceSelect::Flagged(tmp, tb, loc.arc, nf, keep, d_n, (int)loc.n_arc, d.stream);
+			++d.n_lib;
+			n_keep = (uint32_t)d.get_scal(SC_NSEL);
+			d.free(nf);
+		}
+		d.free(flag); d.free(nidx); d.free((void*)d_peer);
+		dg_set_nseq(d, g, n);
+		if (n) MAB_CUDA(cudaMemcpyAsync(g.seq, loc.seq, (size_t)n * 4, cudaMemcpyDeviceToDevice, d.stream));
+		g.len_bits = loc.len_bits, g.is_symm = false;
+		c->have_sg = true;
+		c->stats.n_arc_trans_in = loc.n_arc;
+	} else {
+	// all ranks' raw arcs, concatenated in rank order: every vertex's slab is contiguous in it, which is all the index needs
+	uint64_t my_off = 0, run = 0;
+	std::vector<uint64_t> bytes(G);
+	for (int r = 0; r < G; ++r) { if (r == sc.rank) my_off = run; run += cnt[r]; bytes[r] = cnt[r] * sizeof(DArc); }
 	dg_set_nseq(d, g, n);
 	dg_reserve(d, g, tot ? tot : 1);
 	if (n) MAB_CUDA(cudaMemcpyAsync(g.seq, loc.seq, (size_t)n * 4, cudaMemcpyDeviceToDevice, d.stream));
@@ -621,20 +700,15 @@ int mab_layout_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	g.n_arc = (uint32_t)tot, g.is_srt = true, g.is_symm = false, g.len_bits = loc.len_bits;
 	dg_arc_index(d, g);
 	c->have_sg = true;
-	c->stats.n_arc_sg = tot;
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", g.n_arc);
 	// transitive reduction of the vertices this rank owns (their slabs start inside its block of the concatenation)
 	uint8_t *flag = nullptr;
 	uint32_t n_red = dg_del_trans_flags(d, g, (uint32_t)opt->gap_fuzz, (uint32_t)my_off, (uint32_t)(my_off + cnt[sc.rank]), &flag);
 	c->stats.ms_del_trans_kernel = g_del_trans_stats.kernel_ms, c->stats.trans_inner = g_del_trans_stats.inner_iters;
 	std::vector<uint64_t> reds = sc_allgather_u64(d, sc, n_red);
-	uint64_t n_red_all = 0;
 	for (int r = 0; r < G; ++r) n_red_all += reds[r];
-	c->stats.n_arc_trans_in = cnt[sc.rank], c->stats.n_reduced = n_red_all; // arcs of the vertices this rank reduces
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] transitively reduced %d arcs\n", "asg_arc_del_trans", (int)n_red_all);
-	// survivors of the own block -> all ranks; their stable sort by (vertex, length) is the single-GPU arc array
-	uint32_t n_keep = 0;
-	DArc *keep = mab_alloc<DArc>(d, cnt[sc.rank]);
+	c->stats.n_arc_trans_in = cnt[sc.rank]; // arcs of the vertices this rank reduces
+	// survivors of the own block
+	keep = mab_alloc<DArc>(d, cnt[sc.rank]);
 	if (cnt[sc.rank]) {
 		uint8_t *nf = mab_alloc<uint8_t>(d, cnt[sc.rank]);
 		MAB_LAUNCH(d, k_not_flag, mab_grid(cnt[sc.rank], 256), 256, 0, flag + my_off, (uint32_t)cnt[sc.rank], nf);
@@ -648,6 +722,11 @@ int mab_layout_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 		d.free(nf);
 	}
 	d.free(flag);
+	}
+	c->stats.n_reduced = n_red_all;
+	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] transitively reduced %d arcs\n", "asg_arc_del_trans", (int)n_red_all);
+	// survivors -> all ranks; their stable sort by (vertex, length) is the single-GPU arc array
+	std::vector<uint64_t> bytes(G);
 	std::vector<uint64_t> kc = sc_allgather_u64(d, sc, n_keep);
 	uint64_t ktot = 0;
 	for (int r = 0; r < G; ++r) { ktot += kc[r]; bytes[r] = kc[r] * sizeof(DArc); }

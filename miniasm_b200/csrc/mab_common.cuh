@@ -61,6 +61,12 @@ struct MabArena {
 	void *alloc(size_t bytes);
 	void free(void *p);
 	void release_all();
+	bool segment_of(const void *p, char **base, size_t *offset) const // the cudaMalloc'd segment holding p (for CUDA IPC handles)
+	{
+		for (const Seg &s : segs)
+			if ((const char*)p >= s.base && (const char*)p < s.base + s.size) { *base = s.base; *offset = (size_t)((const char*)p - s.base); return true; }
+		return false;
+	}
 };
 
 struct MabDev {
