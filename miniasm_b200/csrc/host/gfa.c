@@ -6,6 +6,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <ctype.h>
+#include <unistd.h>
+#include <pthread.h>
+#include <sched.h>
 #include "miniasm_b200.h"
 
 void ma_ug_destroy(ma_ug_t *ug)
@@ -41,6 +44,11 @@ typedef struct { char *s; size_t l, m; FILE *fp; } obuf_t;
 static inline void ob_room(obuf_t *b, size_t k)
 {
 	if (b->l + k <= b->m) return;
+	if (b->fp == 0) { /* memory-only buffer (one per writer thread): grow */
+		b->m = b->l + k > 2 * b->m ? b->l + k + (1 << 20) : 2 * b->m;
+		b->s = (char*)realloc(b->s, b->m);
+		return;
+	}
 	if (b->l) fwrite(b->s, 1, b->l, b->fp), b->l = 0;
 	if (k > b->m) { b->m = k + (1 << 20); b->s = (char*)realloc(b->s, b->m); }
 }
@@ -70,34 +78,186 @@ static inline void ob_read(obuf_t *b, const sdict_t *d, const ma_sub_t *sub, uin
 	if (sub) { ob_c(b, ':'); ob_int(b, (int32_t)(sub[r].s + 1)); ob_c(b, '-'); ob_int(b, (int32_t)sub[r].e); }
 }
 
-void ma_ug_print(const ma_ug_t *ug, const sdict_t *d, const ma_sub_t *sub, FILE *fp)
+/* S line, circularising L lines (item 0 of a unitig) and `a` lines (items 1..n) of unitig i, items [it0, it1).
+ * off0 = layout offset of the first `a` line emitted. */
+static void ug_emit_items(obuf_t *b, const ma_ug_t *ug, const sdict_t *d, const ma_sub_t *sub, uint32_t i, uint32_t it0, uint32_t it1, uint32_t off0)
 {
-	uint32_t i, j;
-	obuf_t b = {0, 0, 0, fp};
-	ob_room(&b, 1 << 22);
-	for (i = 0; i < ug->u.n; ++i) { /* segments, circularising links, read layout */
-		const ma_utg_t *p = &ug->u.a[i];
-		uint32_t off = 0;
-		ob_room(&b, 256);
-		ob_c(&b, 'S'); ob_c(&b, '\t'); ob_utg(&b, i, p->circ); ob_c(&b, '\t');
-		if (p->s) { size_t n = strlen(p->s); ob_room(&b, n + 256); memcpy(b.s + b.l, p->s, n); b.l += n; }
-		else ob_c(&b, '*');
-		memcpy(b.s + b.l, "\tLN:i:", 6), b.l += 6; ob_int(&b, (int32_t)p->len); ob_c(&b, '\n');
+	const ma_utg_t *p = &ug->u.a[i];
+	uint32_t j, off = off0;
+	if (it0 == 0 && it1 > 0) {
+		ob_room(b, 256);
+		ob_c(b, 'S'); ob_c(b, '\t'); ob_utg(b, i, p->circ); ob_c(b, '\t');
+		if (p->s) { size_t n = strlen(p->s); ob_room(b, n + 256); memcpy(b->s + b->l, p->s, n); b->l += n; }
+		else ob_c(b, '*');
+		memcpy(b->s + b->l, "\tLN:i:", 6), b->l += 6; ob_int(b, (int32_t)p->len); ob_c(b, '\n');
 		if (p->circ) {
 			int k;
 			for (k = 0; k < 2; ++k) {
-				ob_c(&b, 'L'); ob_c(&b, '\t'); ob_utg(&b, i, 1); ob_c(&b, '\t'); ob_c(&b, "+-"[k]); ob_c(&b, '\t');
-				ob_utg(&b, i, 1); ob_c(&b, '\t'); ob_c(&b, "+-"[k]); ob_c(&b, '\t'); ob_c(&b, '0'); ob_c(&b, 'M'); ob_c(&b, '\n');
+				ob_c(b, 'L'); ob_c(b, '\t'); ob_utg(b, i, 1); ob_c(b, '\t'); ob_c(b, "+-"[k]); ob_c(b, '\t');
+				ob_utg(b, i, 1); ob_c(b, '\t'); ob_c(b, "+-"[k]); ob_c(b, '\t'); ob_c(b, '0'); ob_c(b, 'M'); ob_c(b, '\n');
 			}
 		}
-		for (j = 0; j < p->n; ++j) {
-			const uint32_t r = (uint32_t)(p->a[j] >> 33), l = (uint32_t)p->a[j];
-			ob_room(&b, 256);
-			ob_c(&b, 'a'); ob_c(&b, '\t'); ob_utg(&b, i, p->circ); ob_c(&b, '\t'); ob_int(&b, (int32_t)off); ob_c(&b, '\t');
-			ob_read(&b, d, sub, r);
-			ob_c(&b, '\t'); ob_c(&b, "+-"[p->a[j] >> 32 & 1]); ob_c(&b, '\t'); ob_int(&b, (int32_t)l); ob_c(&b, '\n');
-			off += l;
+	}
+	for (j = it0 ? it0 - 1 : 0; j + 1 < it1; ++j) {
+		const uint32_t r = (uint32_t)(p->a[j] >> 33), l = (uint32_t)p->a[j];
+		ob_room(b, 256);
+		ob_c(b, 'a'); ob_c(b, '\t'); ob_utg(b, i, p->circ); ob_c(b, '\t'); ob_int(b, (int32_t)off); ob_c(b, '\t');
+		ob_read(b, d, sub, r);
+		ob_c(b, '\t'); ob_c(b, "+-"[p->a[j] >> 32 & 1]); ob_c(b, '\t'); ob_int(b, (int32_t)l); ob_c(b, '\n');
+		off += l;
+	}
+}
+
+/* The `a` lines are one per read and each touches three scattered host records (name, interval, layout entry),
+ * so on million-read layouts the writer is bound by cache misses and integer formatting.  Large outputs are
+ * therefore formatted by worker threads in blocks of UGW_BLOCK items (block b belongs to worker b mod T, two
+ * reusable buffers per worker) while the calling thread writes the finished blocks to `fp` in order. */
+#define UGW_BLOCK 4096
+#define UGW_MAX_THREADS 16
+
+typedef struct { uint32_t i, it, off; } ugw_cur_t; /* unitig, item inside it, layout offset of its next `a` line */
+
+typedef struct {
+	const ma_ug_t *ug; const sdict_t *d; const ma_sub_t *sub;
+	const ugw_cur_t *cur;  /* cursor at the start of each block */
+	uint64_t n_items;
+	uint32_t n_blk, n_written;
+	int n_thr, go;
+	uint8_t *ready;
+	obuf_t *buf;           /* 2 per worker */
+	pthread_mutex_t mtx;
+	pthread_cond_t cv;
+} ugw_shared_t;
+
+typedef struct { ugw_shared_t *sh; int k; } ugw_arg_t;
+
+/* Blocks take ~0.1 ms to format, far less than a futex sleep/wake round trip, so the hand-over between the workers
+ * and the writing thread polls (release/acquire flags), yielding the core once the wait gets long. */
+static inline void ugw_relax(unsigned *spins)
+{
+	if (++*spins < 2000) {
+#if defined(__x86_64__) || defined(__i386__)
+		__builtin_ia32_pause();
+#endif
+	} else sched_yield();
+}
+
+static void ug_emit_block(obuf_t *b, const ugw_shared_t *sh, uint32_t blk)
+{
+	uint64_t left = sh->n_items - (uint64_t)blk * UGW_BLOCK;
+	uint32_t i = sh->cur[blk].i, it = sh->cur[blk].it, off = sh->cur[blk].off;
+	if (left > UGW_BLOCK) left = UGW_BLOCK;
+	while (left) {
+		const uint32_t n_it = sh->ug->u.a[i].n + 1;
+		const uint32_t end = (uint64_t)(n_it - it) <= left ? n_it : it + (uint32_t)left;
+		ug_emit_items(b, sh->ug, sh->d, sh->sub, i, it, end, off);
+		left -= end - it;
+		++i, it = 0, off = 0;
+	}
+}
+
+static void *ug_worker(void *arg)
+{
+	ugw_shared_t *sh = ((ugw_arg_t*)arg)->sh;
+	const int k = ((ugw_arg_t*)arg)->k;
+	uint32_t b;
+	int T;
+	pthread_mutex_lock(&sh->mtx);
+	while (!sh->go) pthread_cond_wait(&sh->cv, &sh->mtx);
+	T = sh->n_thr;
+	pthread_mutex_unlock(&sh->mtx);
+	if (k >= T) return 0;
+	for (b = k; b < sh->n_blk; b += T) {
+		obuf_t *ob = &sh->buf[2 * k + (b / T & 1)];
+		if (b >= 2u * T) { /* the buffer last held block b - 2T: wait until that one has been written out */
+			unsigned spins = 0;
+			while (__atomic_load_n(&sh->n_written, __ATOMIC_ACQUIRE) <= b - 2u * T) ugw_relax(&spins);
 		}
+		ob->l = 0;
+		ug_emit_block(ob, sh, b);
+		__atomic_store_n(&sh->ready[b], 1, __ATOMIC_RELEASE);
+	}
+	return 0;
+}
+
+static int ug_writer_threads(uint64_t n_items)
+{
+	long nc = sysconf(_SC_NPROCESSORS_ONLN);
+	const char *e = getenv("MAB_WRITER_THREADS");
+	int t = (int)(n_items / (8 * UGW_BLOCK)); /* at least 8 blocks per worker, else not worth starting threads */
+	if (nc < 1) nc = 1;
+	if (t > nc - 1) t = (int)nc - 1; /* the caller's thread does the writing */
+	if (e && atoi(e) >= 0) t = atoi(e);
+	if (t > UGW_MAX_THREADS) t = UGW_MAX_THREADS;
+	return t;
+}
+
+void ma_ug_print(const ma_ug_t *ug, const sdict_t *d, const ma_sub_t *sub, FILE *fp)
+{
+	uint32_t i, j;
+	uint64_t n_items = 0;
+	int n_thr;
+	obuf_t b = {0, 0, 0, fp};
+	ob_room(&b, 1 << 20);
+	for (i = 0; i < ug->u.n; ++i) n_items += (uint64_t)ug->u.a[i].n + 1;
+	n_thr = ug_writer_threads(n_items);
+	if (n_thr >= 1 && n_items > UGW_BLOCK && n_items / UGW_BLOCK < (1u << 31)) { /* segments, circularising links, read layout */
+		ugw_shared_t sh;
+		ugw_arg_t *arg = (ugw_arg_t*)calloc(n_thr, sizeof(ugw_arg_t));
+		pthread_t *tid = (pthread_t*)calloc(n_thr, sizeof(pthread_t));
+		ugw_cur_t *cur;
+		uint32_t ui = 0, it = 0, off = 0, blk;
+		int k, n_started = 0;
+		memset(&sh, 0, sizeof(sh));
+		sh.ug = ug, sh.d = d, sh.sub = sub, sh.n_items = n_items;
+		sh.n_blk = (uint32_t)((n_items + UGW_BLOCK - 1) / UGW_BLOCK);
+		cur = (ugw_cur_t*)malloc((size_t)sh.n_blk * sizeof(ugw_cur_t));
+		for (blk = 0; blk < sh.n_blk; ++blk) { /* one serial pass over the layout: where each block starts */
+			uint64_t left = n_items - (uint64_t)blk * UGW_BLOCK;
+			if (left > UGW_BLOCK) left = UGW_BLOCK;
+			cur[blk].i = ui, cur[blk].it = it, cur[blk].off = off;
+			while (left) {
+				const ma_utg_t *p = &ug->u.a[ui];
+				const uint32_t n_it = p->n + 1;
+				const uint32_t end = (uint64_t)(n_it - it) <= left ? n_it : it + (uint32_t)left;
+				for (j = it ? it - 1 : 0; j + 1 < end; ++j) off += (uint32_t)p->a[j];
+				left -= end - it;
+				if (end == n_it) ++ui, it = 0, off = 0;
+				else it = end;
+			}
+		}
+		sh.cur = cur;
+		sh.ready = (uint8_t*)calloc(sh.n_blk, 1);
+		sh.buf = (obuf_t*)calloc(2 * (size_t)n_thr, sizeof(obuf_t));
+		pthread_mutex_init(&sh.mtx, 0);
+		pthread_cond_init(&sh.cv, 0);
+		for (k = 0; k < n_thr; ++k) {
+			arg[k].sh = &sh, arg[k].k = k;
+			if (pthread_create(&tid[k], 0, ug_worker, &arg[k]) != 0) break;
+			++n_started;
+		}
+		pthread_mutex_lock(&sh.mtx);
+		sh.n_thr = n_started, sh.go = 1;
+		pthread_cond_broadcast(&sh.cv);
+		pthread_mutex_unlock(&sh.mtx);
+		if (n_started == 0) { /* no thread could be started: format here */
+			for (i = 0; i < ug->u.n; ++i) ug_emit_items(&b, ug, d, sub, i, 0, ug->u.a[i].n + 1, 0);
+		} else {
+			for (blk = 0; blk < sh.n_blk; ++blk) {
+				const obuf_t *ob = &sh.buf[2 * (blk % n_started) + (blk / n_started & 1)];
+				unsigned spins = 0;
+				while (!__atomic_load_n(&sh.ready[blk], __ATOMIC_ACQUIRE)) ugw_relax(&spins);
+				if (ob->l) fwrite(ob->s, 1, ob->l, fp);
+				__atomic_store_n(&sh.n_written, blk + 1, __ATOMIC_RELEASE);
+			}
+		}
+		for (k = 0; k < n_started; ++k) pthread_join(tid[k], 0);
+		for (k = 0; k < 2 * n_thr; ++k) free(sh.buf[k].s);
+		pthread_mutex_destroy(&sh.mtx);
+		pthread_cond_destroy(&sh.cv);
+		free(sh.buf); free(sh.ready); free(cur); free(arg); free(tid);
+	} else {
+		for (i = 0; i < ug->u.n; ++i) ug_emit_items(&b, ug, d, sub, i, 0, ug->u.a[i].n + 1, 0);
 	}
 	for (i = 0; i < ug->g->n_arc; ++i) { /* links between unitigs */
 		const asg_arc_t *a = &ug->g->arc[i];

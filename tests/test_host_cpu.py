@@ -150,3 +150,69 @@ def test_device_parser_matches_host_reader(built, paf_dir):
             l2 = ln[:-1] if len(ln) > 1 and ln.endswith(b"\r") else ln
             got.append((l2[:o[10]], o[1], o[2], o[3], o[4], l2[o[12]:o[12] + o[11]], o[5], o[6], o[7], o[8], o[9] if o[0] >= 11 else stale))
     assert len(got) == len(want) > 100000 and got == want
+
+
+def _synthetic_layout(lib, n_utg, seed):
+    """A ma_ug_t built by hand (miniasm.h:42-55): unitigs of 1..3000 reads, some circular, plus a few links."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    n_reads = 40000
+    d = lib.sd_init()
+    for i in range(n_reads):
+        lib.sd_put(d, b"r%d_%s" % (i * 7919 % 100003, b"x" * (i % 23)), 5000 + i % 9000)
+    sub = np.zeros(n_reads, dtype=capi.SUB_DT)
+    sub["s_del"] = rng.integers(0, 500, n_reads)
+    sub["e"] = 5000 + rng.integers(0, 3000, n_reads)
+    keep = []                                                              # numpy buffers the C structs point into
+    utg = (capi.MaUtg * n_utg)()
+    for i in range(n_utg):
+        n = int(rng.choice([1, 2, 3, 50, 700, 3000, 4095, 4096, 4097]))
+        a = (rng.integers(0, n_reads, n).astype(np.uint64) << np.uint64(33)) | (rng.integers(0, 2, n).astype(np.uint64) << np.uint64(32)) \
+            | rng.integers(1, 20000, n).astype(np.uint64)
+        keep.append(a)
+        circ = i % 5 == 3
+        utg[i].len_circ = int(a.astype(np.uint32).sum() & 0x7fffffff) | (int(circ) << 31)
+        utg[i].start = 0xffffffff if circ else int(a[0] >> np.uint64(32))
+        utg[i].end = 0xffffffff if circ else int(a[-1] >> np.uint64(32)) ^ 1
+        utg[i].n = utg[i].m = n
+        utg[i].a = a.ctypes.data_as(C.POINTER(C.c_uint64))
+        utg[i].s = None
+    arcs = np.zeros(7, dtype=capi.ARC_DT)
+    arcs["ul"] = (rng.integers(0, 2 * n_utg, 7).astype(np.uint64) << np.uint64(32)) | rng.integers(1, 9999, 7).astype(np.uint64)
+    arcs["v"] = rng.integers(0, 2 * n_utg, 7)
+    arcs["ol_del"] = rng.integers(1, 5000, 7)
+    idx = rng.integers(0, 3, 2 * n_utg).astype(np.uint64)
+    g = capi.AsgT()
+    g.m_arc, g.n_arc_srt, g.arc = 7, 7, arcs.ctypes.data
+    g.m_seq, g.n_seq_symm, g.seq, g.idx = n_utg, n_utg, None, idx.ctypes.data
+    ug = capi.MaUg()
+    ug.n = ug.m = n_utg
+    ug.a = C.cast(utg, C.POINTER(capi.MaUtg))
+    ug.g = C.pointer(g)
+    keep += [utg, arcs, idx, g]
+    return ug, d, sub, keep
+
+
+def test_ug_writer_threads_keep_the_byte_stream(built, monkeypatch):
+    """ma_ug_print formats large layouts with worker threads (gfa.c); the bytes must not depend on the thread count."""
+    prod = capi.load_product(strict=False)
+    ug, d, sub, keep = _synthetic_layout(prod, 60, 5)
+    subp = C.c_void_p(sub.ctypes.data)
+    outs = {}
+    for t in ("0", "1", "3", "7", "16"):
+        monkeypatch.setenv("MAB_WRITER_THREADS", t)
+        outs[t] = prod.print_to_string("ma_ug_print", C.pointer(ug), d, subp)
+    assert len(outs["0"]) > 1_000_000 and outs["0"].count(b"\na\t") > 50_000
+    for t in outs:
+        assert outs[t] == outs["0"], t
+    plain = {}
+    for t in ("0", "5"):                                                  # sub == NULL: names without the :s-e suffix
+        monkeypatch.setenv("MAB_WRITER_THREADS", t)
+        plain[t] = prod.print_to_string("ma_ug_print", C.pointer(ug), d, None)
+    assert plain["0"] == plain["5"] and len(plain["0"]) < len(outs["0"])
+    if os.path.exists(capi.REFERENCE_SO):                                # and they are the reference's bytes (asm.c:64-116)
+        ref = capi.load_reference()
+        d2 = ref.sd_init()
+        for i in range(d.contents.n_seq):
+            ref.sd_put(d2, d.contents.seq[i].name, d.contents.seq[i].len)
+        assert ref.print_to_string("ma_ug_print", C.pointer(ug), d2, subp) == outs["0"]
