@@ -52,16 +52,101 @@ void dh_free(MabDev &d, DHits &h)
 	h = DHits();
 }
 
-// stable compaction of hits by a byte flag array; returns the number kept
+// ---------------------------------------------------------------------------------------------
+// Stable compaction of hits by a byte flag array.  32-byte records: the generic library selection moves them at
+// ~2.2 TB/s (ncu: 2.8 ms per 100 M hits), so the hit path has its own three-step compaction -- per-tile keep counts
+// (flags only), a scan of the ~n/2048 tile counts, and a scatter in which every warp row reads 1 KB of contiguous
+// records and writes them behind the tile's offset.  Order of the kept hits is the input order.
+// MAB_CUB_SELECT=1 switches back to cub::DeviceSelect::Flagged.
+// ---------------------------------------------------------------------------------------------
+constexpr int SEL_ROWS = 8, SEL_THREADS = 256, SEL_TILE = SEL_ROWS * SEL_THREADS;
+static_assert(SEL_ROWS * (SEL_THREADS / 32) == 64, "k_sel_scatter scans exactly two counts per lane of one warp");
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_sel_count(const uint8_t *__restrict__ flag, size_t n, uint32_t *__restrict__ tile_cnt)
+{
+	__shared__ unsigned s_w[SEL_THREADS / 32];
+	const size_t base = (size_t)blockIdx.x * SEL_TILE;
+	unsigned c = 0;
+	#pragma unroll
+	for (int k = 0; k < SEL_ROWS; ++k) {
+		const size_t i = base + (size_t)k * SEL_THREADS + threadIdx.x;
+		c += (i < n && flag[i] != 0) ? 1u : 0u;
+	}
+	c = __reduce_add_sync(0xffffffffu, c);
+	if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned t = 0;
+		#pragma unroll
+		for (int w = 0; w < SEL_THREADS / 32; ++w) t += s_w[w];
+		tile_cnt[blockIdx.x] = t;
+	}
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_sel_scatter(const DHit *__restrict__ in, const uint8_t *__restrict__ flag, size_t n, const uint32_t *__restrict__ tile_off,
+              DHit *__restrict__ out, unsigned long long *__restrict__ n_out)
+{
+	constexpr int NW = SEL_THREADS / 32;
+	__shared__ uint32_t s_off[SEL_ROWS * NW];   // (row, warp) -> kept records of the tile before that warp row
+	__shared__ uint32_t s_total;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const size_t base = (size_t)blockIdx.x * SEL_TILE;
+	unsigned bal[SEL_ROWS];
+	#pragma unroll
+	for (int k = 0; k < SEL_ROWS; ++k) {
+		const size_t i = base + (size_t)k * SEL_THREADS + tid;
+		const bool f = i < n && flag[i] != 0;
+		bal[k] = __ballot_sync(0xffffffffu, f);
+		if (lane == 0) s_off[k * NW + warp] = __popc(bal[k]);
+	}
+	__syncthreads();
+	if (warp == 0) { // exclusive scan of the SEL_ROWS * NW = 64 counts in record order, two per lane
+		const uint32_t c0 = s_off[2 * lane], c1 = s_off[2 * lane + 1];
+		uint32_t inc = c0 + c1;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+		const uint32_t exc = inc - (c0 + c1);
+		s_off[2 * lane] = exc, s_off[2 * lane + 1] = exc + c0;
+		if (lane == 31) s_total = inc;
+	}
+	__syncthreads();
+	const uint32_t tbase = tile_off[blockIdx.x];
+	#pragma unroll
+	for (int k = 0; k < SEL_ROWS; ++k) {
+		if (bal[k] >> lane & 1u) {
+			const size_t i = base + (size_t)k * SEL_THREADS + tid;
+			const uint32_t pos = tbase + s_off[k * NW + warp] + __popc(bal[k] & ((1u << lane) - 1u));
+			st_hit(out + pos, ld_hit(in + i));
+		}
+	}
+	if (blockIdx.x == gridDim.x - 1 && tid == 0) *n_out = (unsigned long long)tbase + s_total;
+}
+
 static size_t select_hits(MabDev &d, DHits &h, const uint8_t *flag)
 {
 	if (h.n == 0) return 0;
-	size_t tb = 0;
+	static const bool use_cub = getenv("MAB_CUB_SELECT") && atoi(getenv("MAB_CUB_SELECT")) != 0;
 	unsigned long long *d_n = d.d_scal + SC_NSEL;
-	cub::DeviceSelect::Flagged(nullptr, tb, h.a, flag, h.a2, d_n, (int64_t)h.n, d.stream);
-	void *tmp = d.tmp(tb);
-	cub::DeviceSelect::Flagged(tmp, tb, h.a, flag, h.a2, d_n, (int64_t)h.n, d.stream);
-	++d.n_lib;
+	if (use_cub || h.n >= (1ull << 32)) {
+		size_t tb = 0;
+		cub::DeviceSelect::Flagged(nullptr, tb, h.a, flag, h.a2, d_n, (int64_t)h.n, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceSelect::Flagged(tmp, tb, h.a, flag, h.a2, d_n, (int64_t)h.n, d.stream);
+		++d.n_lib;
+	} else {
+		const uint32_t n_tile = (uint32_t)((h.n + SEL_TILE - 1) / SEL_TILE);
+		uint32_t *cnt = mab_alloc<uint32_t>(d, n_tile), *off = mab_alloc<uint32_t>(d, n_tile);
+		MAB_LAUNCH(d, k_sel_count, n_tile, SEL_THREADS, 0, flag, h.n, cnt);
+		size_t tb = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, off, (int)n_tile, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, off, (int)n_tile, d.stream);
+		++d.n_lib;
+		MAB_LAUNCH(d, k_sel_scatter, n_tile, SEL_THREADS, 0, h.a, flag, h.n, off, h.a2, d_n);
+		d.free(cnt); d.free(off);   // stream-ordered arena: reuse is ordered behind the kernels above
+	}
 	size_t n = (size_t)d.get_scal(SC_NSEL);
 	DHit *t = h.a; h.a = h.a2; h.a2 = t;
 	h.n = n;
@@ -291,10 +376,13 @@ k_sub_warp(const DHit *__restrict__ a, const uint64_t *__restrict__ grp, uint32_
 		uint32_t np = 32; while (np < n) np <<= 1;
 		for (uint32_t i = n + lane; i < np; i += 32) key[i] = 0xffffffffu;
 		__syncwarp();
-		for (uint32_t k = 2; k <= np; k <<= 1)
-			for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+		// bitonic network; j = 1 << lj is a power of two, so the pair index comes from shifts (a 32-bit division per
+		// compare-exchange made this loop ~90 % of the kernel's instructions: ncu, profiles/r01_launches_c3_summary.txt)
+		for (uint32_t k = 2, lk = 1; k <= np; k <<= 1, ++lk)
+			for (uint32_t lj = lk; lj-- > 0;) {
+				const uint32_t j = 1u << lj;
 				for (uint32_t t = lane; t < np / 2; t += 32) {
-					const uint32_t lo = (t / j) * 2 * j + (t % j), hi = lo + j;
+					const uint32_t lo = ((t >> lj) << (lj + 1)) | (t & (j - 1)), hi = lo + j;
 					const uint32_t x = key[lo], y = key[hi];
 					const bool asc = (lo & k) == 0;
 					if ((x > y) == asc) key[lo] = y, key[hi] = x;
@@ -330,10 +418,11 @@ k_sub_cta(const DHit *__restrict__ a, const uint64_t *__restrict__ grp, const ui
 		uint32_t np = 32; while (np < n) np <<= 1;
 		for (uint32_t i = n + tid; i < np; i += nt) c_key[i] = 0xffffffffu;
 		__syncthreads();
-		for (uint32_t k = 2; k <= np; k <<= 1)
-			for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+		for (uint32_t k = 2, lk = 1; k <= np; k <<= 1, ++lk)
+			for (uint32_t lj = lk; lj-- > 0;) {
+				const uint32_t j = 1u << lj;
 				for (uint32_t t = tid; t < np / 2; t += nt) {
-					const uint32_t lo = (t / j) * 2 * j + (t % j), hi = lo + j;
+					const uint32_t lo = ((t >> lj) << (lj + 1)) | (t & (j - 1)), hi = lo + j;
 					const uint32_t x = c_key[lo], y = c_key[hi];
 					const bool asc = (lo & k) == 0;
 					if ((x > y) == asc) c_key[lo] = y, c_key[hi] = x;
