@@ -317,15 +317,17 @@ __device__ __forceinline__ bool sub_sweep_smem(const uint32_t *key, uint32_t n, 
 		const int src = below ? 31 - __clz(below) : 0;
 		uint32_t st = __shfl_sync(0xffffffffu, pos, src);
 		if (!below) st = carry_start;
-		unsigned long long cand = 0;
-		if (down) cand = (unsigned long long)(pos - st) << 32 | (0xffffffffu - i);
-		unsigned long long m = cand;
-		#pragma unroll
-		for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
-		if (m > best && (m >> 32) != 0) {
-			const unsigned who = __ballot_sync(0xffffffffu, down && cand == m);
-			best = m;
-			best_end = __shfl_sync(0xffffffffu, pos, __ffs(who) - 1);
+		if (__any_sync(0xffffffffu, down)) { // an interval closes in this chunk (a handful per read): longest, earliest on ties
+			unsigned long long cand = 0;
+			if (down) cand = (unsigned long long)(pos - st) << 32 | (0xffffffffu - i);
+			unsigned long long m = cand;
+			#pragma unroll
+			for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+			if (m > best && (m >> 32) != 0) {
+				const unsigned who = __ballot_sync(0xffffffffu, down && cand == m);
+				best = m;
+				best_end = __shfl_sync(0xffffffffu, pos, __ffs(who) - 1);
+			}
 		}
 		if (upm) carry_start = __shfl_sync(0xffffffffu, pos, 31 - __clz(upm));
 		depth = __shfl_sync(0xffffffffu, dp, 31);
@@ -350,9 +352,54 @@ __device__ __forceinline__ bool sub_hit_keys(const DHit &h, uint32_t qid, float 
 	return true;
 }
 
+// Bitonic network over 32*M keys held in registers, element e = 32*m + lane: exchanges at distance j < 32 are lane
+// shuffles, distances >= 32 pair two registers of the same lane -- no shared-memory traffic and none of the 2-way bank
+// conflicts the strided pair indexing has (ncu: 0.41 G conflicts per launch in the shared-memory version).
+template <int M>
+__device__ __forceinline__ void warp_bitonic_regs(uint32_t (&v)[M], const int lane)
+{
+	#pragma unroll
+	for (int k = 2; k <= 32 * M; k <<= 1) {
+		#pragma unroll
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			if (j >= 32) {
+				#pragma unroll
+				for (int m = 0; m < M; ++m) {
+					const int pm = m ^ (j >> 5);
+					if (pm > m) {
+						const bool asc = ((32 * m) & k) == 0; // k >= 64 here: the lane bits do not reach it
+						const uint32_t x = v[m], y = v[pm];
+						const uint32_t lo = min(x, y), hi = max(x, y);
+						v[m] = asc ? lo : hi, v[pm] = asc ? hi : lo;
+					}
+				}
+			} else {
+				const bool low = (lane & j) == 0;
+				#pragma unroll
+				for (int m = 0; m < M; ++m) {
+					const uint32_t y = __shfl_xor_sync(0xffffffffu, v[m], j);
+					const bool asc = ((32 * m + lane) & k) == 0;
+					v[m] = asc == low ? min(v[m], y) : max(v[m], y);
+				}
+			}
+		}
+	}
+}
+
+template <int M>
+__device__ __forceinline__ void sub_sort_regs(uint32_t *key, const uint32_t n, const int lane)
+{
+	uint32_t v[M];
+	#pragma unroll
+	for (int m = 0; m < M; ++m) v[m] = 32u * m + lane < n ? key[32 * m + lane] : 0xffffffffu;
+	warp_bitonic_regs<M>(v, lane);
+	#pragma unroll
+	for (int m = 0; m < M; ++m) key[32 * m + lane] = v[m];
+}
+
 __global__ void __launch_bounds__(SUBW_WARPS * 32)
 k_sub_warp(const DHit *__restrict__ a, const uint64_t *__restrict__ grp, uint32_t n_seq, int min_dp, float min_iden, uint32_t clip,
-           DSub *sub, uint32_t *big_list, unsigned long long *scal)
+           DSub *sub, uint32_t *big_list, unsigned long long *scal, int smem_sort)
 {
 	__shared__ uint32_t s_key[SUBW_WARPS][2 * SUBW_HITS];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -374,6 +421,20 @@ k_sub_warp(const DHit *__restrict__ a, const uint64_t *__restrict__ grp, uint32_
 			n += 2 * __popc(m);
 		}
 		uint32_t np = 32; while (np < n) np <<= 1;
+		__syncwarp();
+		if (!smem_sort) { // keys of the read sorted in registers (np is uniform across the warp)
+			switch (np) {
+				case 32: sub_sort_regs<1>(key, n, lane); break;
+				case 64: sub_sort_regs<2>(key, n, lane); break;
+				case 128: sub_sort_regs<4>(key, n, lane); break;
+				case 256: sub_sort_regs<8>(key, n, lane); break;
+				default: sub_sort_regs<16>(key, n, lane); break;
+			}
+			__syncwarp();
+			remained += sub_sweep_smem(key, n, min_dp, clip, sub + r, lane);
+			__syncwarp();
+			continue;
+		}
 		for (uint32_t i = n + lane; i < np; i += 32) key[i] = 0xffffffffu;
 		__syncwarp();
 		// bitonic network; j = 1 << lj is a power of two, so the pair index comes from shifts (a 32-bit division per
@@ -460,7 +521,8 @@ uint64_t dh_sub(MabDev &d, const DHits &h, int min_dp, float min_iden, int end_c
 	MAB_LAUNCH(d, k_group_bounds, mab_grid(h.n, 256), 256, 0, h.a, h.n, (uint32_t*)grp);
 	unsigned grid = (n_seq + SUBW_WARPS - 1) / SUBW_WARPS;
 	if (grid > 148u * 32u) grid = 148u * 32u;
-	MAB_LAUNCH(d, k_sub_warp, grid, SUBW_WARPS * 32, 0, h.a, grp, n_seq, min_dp, min_iden, (uint32_t)end_clip, sub_out, big, d.d_scal);
+	static const int smem_sort = getenv("MAB_SUB_SMEM_SORT") && atoi(getenv("MAB_SUB_SMEM_SORT")) != 0; // 1: the shared-memory network
+	MAB_LAUNCH(d, k_sub_warp, grid, SUBW_WARPS * 32, 0, h.a, grp, n_seq, min_dp, min_iden, (uint32_t)end_clip, sub_out, big, d.d_scal, smem_sort);
 	uint32_t n_big = (uint32_t)d.get_scal(SC_BIG);
 	if (n_big) {
 		static bool attr_set = false;
