@@ -934,6 +934,196 @@ __global__ void k_sg_arcs(const DHit *a, size_t n, uint32_t *seq, HitArcParams p
 	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_emit, (unsigned long long)cnt);
 }
 
+// ---------------------------------------------------------------------------------------------
+// ma_sg_gen without a device-wide sort (experimental, MAB_SG_SEGSORT=1; the default is the column sort above).
+// Hits arrive grouped by query read, and an arc's source vertex is its hit's query, so asg.c's "append, then sort by
+// ul" only has to order each read's arcs by (direction, length), hit order on ties -- a per-read problem of ~100
+// elements.  Pass 1 classifies every hit (flag byte, group bounds, the deletion side effects of asm.c:27-33) and
+// checks that query ids ascend; a scan of the flags gives each read its output offset; pass 2 re-classifies a read's
+// hits (cheaper than storing 16 B per hit), sorts the keys ((dir << lb | len) << 9 | arc number) with the register
+// network of ma_hit_sub and writes the read's arcs in place.  Reads with 257..8192 hits take a CTA and a shared-memory
+// network; anything the scheme cannot take (unsorted ids, a read beyond 8192 hits, reads longer than 4 Mb) falls
+// back to the column sort, so results never depend on the switch.
+// ---------------------------------------------------------------------------------------------
+constexpr int SGW_WARPS = 8, SGW_HITS = 256, SGW_IDX_BITS = 9;
+constexpr int SGC_HITS = 8192;
+
+__global__ void k_sg_classify(const DHit *a, size_t n, uint32_t *seq, HitArcParams p, uint8_t *emit_flag, uint32_t *g32, unsigned long long *scal)
+{
+	unsigned cnt = 0;
+	bool bad = false;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		DHit h = ld_hit(a + i);
+		const uint32_t qn = (uint32_t)(h.qns >> 32);
+		DArc t;
+		t.ul = 0, t.v = 0, t.ol_del = 0;
+		const int r = mab_hit2arc(h, (int)(seq[qn] & 0x7fffffffu), (int)(seq[h.tn] & 0x7fffffffu), p.max_hang, p.int_frac, p.min_ovlp, &t);
+		bool emit = false;
+		if (r >= 0) {
+			if (qn == h.tn) {
+				if ((uint32_t)h.qns == h.ts && h.qe == h.te && (h.ml_rev >> 31)) atomicOr(&seq[qn], MAB_DEL_BIT);
+			} else emit = true;
+		} else if (r == MAB_HT_QCONT) atomicOr(&seq[qn], MAB_DEL_BIT);
+		emit_flag[i] = emit;
+		cnt += emit;
+		const uint32_t prev = i ? (uint32_t)(a[i - 1].qns >> 32) : 0;
+		if (i == 0 || prev != qn) g32[2 * (size_t)qn + 1] = (uint32_t)i;
+		if (i == n - 1 || (uint32_t)(a[i + 1].qns >> 32) != qn) g32[2 * (size_t)qn] = (uint32_t)(i + 1);
+		if (i && prev > qn) bad = true;
+	}
+	cnt = __reduce_add_sync(0xffffffffu, cnt);
+	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(scal + SC_COUNT, (unsigned long long)cnt);
+	if (bad) scal[SC_AUX2] = 1ull;
+}
+
+struct U8ToU32 { __host__ __device__ __forceinline__ uint32_t operator()(uint8_t x) const { return x; } };
+
+__global__ void __launch_bounds__(SGW_WARPS * 32)
+k_sg_sort_warp(const DHit *__restrict__ a, const uint64_t *__restrict__ grp, const uint32_t *__restrict__ epos, const uint32_t *__restrict__ seq,
+               uint32_t n_seq, HitArcParams p, uint32_t lb, DArc *__restrict__ out, uint32_t *big_list, unsigned long long *scal)
+{
+	__shared__ uint32_t s_key[SGW_WARPS][SGW_HITS], s_v[SGW_WARPS][SGW_HITS], s_ol[SGW_WARPS][SGW_HITS];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t *key = s_key[warp], *pv = s_v[warp], *pol = s_ol[warp];
+	const uint32_t len_mask = (1u << lb) - 1u; // lb <= 22 on this path
+	for (uint32_t r = blockIdx.x * SGW_WARPS + warp; r < n_seq; r += gridDim.x * SGW_WARPS) {
+		const uint64_t g = grp[r];
+		const uint32_t end = (uint32_t)g, first = (uint32_t)(g >> 32);
+		if (end == 0) continue;
+		const uint32_t cnt = end - first;
+		if (cnt > SGW_HITS) { if (lane == 0) big_list[atomicAdd(scal + SC_BIG, 1ull)] = r; continue; }
+		const int ql = (int)(seq[r] & 0x7fffffffu);
+		uint32_t n = 0; // arcs of this read so far (uniform)
+		for (uint32_t c = 0; c < cnt; c += 32) {
+			bool ok = false;
+			DArc t;
+			t.ul = 0, t.v = 0, t.ol_del = 0;
+			if (c + lane < cnt) {
+				const DHit h = ld_hit(a + first + c + lane);
+				const int rr = mab_hit2arc(h, ql, (int)(seq[h.tn] & 0x7fffffffu), p.max_hang, p.int_frac, p.min_ovlp, &t);
+				ok = rr >= 0 && h.tn != r;
+			}
+			const unsigned m = __ballot_sync(0xffffffffu, ok);
+			if (ok) {
+				const uint32_t k = n + __popc(m & ((1u << lane) - 1u));
+				key[k] = ((((uint32_t)(t.ul >> 32) & 1u) << lb | (uint32_t)t.ul) << SGW_IDX_BITS) | k;
+				pv[k] = t.v, pol[k] = t.ol_del;
+			}
+			n += __popc(m);
+		}
+		if (n == 0) continue;
+		uint32_t np = 32; while (np < n) np <<= 1;
+		__syncwarp();
+		switch (np) {
+			case 32: sub_sort_regs<1>(key, n, lane); break;
+			case 64: sub_sort_regs<2>(key, n, lane); break;
+			case 128: sub_sort_regs<4>(key, n, lane); break;
+			default: sub_sort_regs<8>(key, n, lane); break;
+		}
+		__syncwarp();
+		const uint32_t base = epos[first];
+		for (uint32_t j = lane; j < n; j += 32) {
+			const uint32_t k = key[j], src = k & ((1u << SGW_IDX_BITS) - 1u), kl = k >> SGW_IDX_BITS;
+			*reinterpret_cast<uint4*>(out + base + j) = make_uint4(kl & len_mask, r << 1 | kl >> lb, pv[src], pol[src]);
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(512)
+k_sg_sort_cta(const DHit *__restrict__ a, const uint64_t *__restrict__ grp, const uint32_t *__restrict__ epos, const uint32_t *__restrict__ seq,
+              const uint32_t *__restrict__ big_list, uint32_t n_big, HitArcParams p, DArc *__restrict__ out, unsigned long long *scal)
+{
+	extern __shared__ __align__(16) unsigned char sg_smem[];
+	uint64_t *key = reinterpret_cast<uint64_t*>(sg_smem);         // (dir << 31 | len) << 32 | arc number
+	uint32_t *pv = reinterpret_cast<uint32_t*>(key + SGC_HITS), *pol = pv + SGC_HITS;
+	__shared__ uint32_t s_n;
+	const uint32_t tid = threadIdx.x, nt = blockDim.x;
+	for (uint32_t b = blockIdx.x; b < n_big; b += gridDim.x) {
+		const uint32_t r = big_list[b];
+		const uint64_t g = grp[r];
+		const uint32_t first = (uint32_t)(g >> 32), cnt = (uint32_t)g - first;
+		if (cnt > SGC_HITS) { if (tid == 0) atomicAdd(scal + SC_AUX, 1ull); continue; }
+		if (tid == 0) s_n = 0;
+		__syncthreads();
+		const uint32_t base = epos[first];
+		const int ql = (int)(seq[r] & 0x7fffffffu);
+		for (uint32_t c = tid; c < cnt; c += nt) {
+			const DHit h = ld_hit(a + first + c);
+			DArc t;
+			t.ul = 0, t.v = 0, t.ol_del = 0;
+			const int rr = mab_hit2arc(h, ql, (int)(seq[h.tn] & 0x7fffffffu), p.max_hang, p.int_frac, p.min_ovlp, &t);
+			if (rr >= 0 && h.tn != r) {
+				const uint32_t k = epos[first + c] - base; // arcs of this read emitted before hit c
+				key[k] = (uint64_t)((((uint32_t)(t.ul >> 32) & 1u) << 31) | (uint32_t)t.ul) << 32 | k;
+				pv[k] = t.v, pol[k] = t.ol_del;
+				atomicAdd(&s_n, 1u);
+			}
+		}
+		__syncthreads();
+		const uint32_t n = s_n;
+		uint32_t np = 2; while (np < n) np <<= 1;
+		for (uint32_t i = n + tid; i < np; i += nt) key[i] = ~0ull;
+		__syncthreads();
+		for (uint32_t k = 2, lk = 1; k <= np; k <<= 1, ++lk)
+			for (uint32_t lj = lk; lj-- > 0;) {
+				const uint32_t j = 1u << lj;
+				for (uint32_t t = tid; t < np / 2; t += nt) {
+					const uint32_t lo = ((t >> lj) << (lj + 1)) | (t & (j - 1)), hi = lo + j;
+					const uint64_t x = key[lo], y = key[hi];
+					const bool asc = (lo & k) == 0;
+					if ((x > y) == asc) key[lo] = y, key[hi] = x;
+				}
+				__syncthreads();
+			}
+		for (uint32_t j = tid; j < n; j += nt) {
+			const uint64_t k = key[j];
+			const uint32_t src = (uint32_t)k, kl = (uint32_t)(k >> 32);
+			*reinterpret_cast<uint4*>(out + base + j) = make_uint4(kl & 0x7fffffffu, r << 1 | kl >> 31, pv[src], pol[src]);
+		}
+		__syncthreads();
+	}
+}
+
+// true: g.arc holds the sorted arcs.  false: nothing usable was produced, the caller runs the column sort.
+static bool sg_emit_segmented(MabDev &d, const DHits &h, const HitArcParams &p, uint32_t lb, DGraph &g)
+{
+	const size_t n = h.n;
+	const uint32_t n_seq = h.n_seq;
+	if (lb + 1 + SGW_IDX_BITS > 32 || n >= (1ull << 31)) return false;
+	uint8_t *ef = mab_alloc<uint8_t>(d, n);
+	uint32_t *epos = mab_alloc<uint32_t>(d, n), *big = mab_alloc<uint32_t>(d, n_seq);
+	uint64_t *grp = mab_alloc<uint64_t>(d, n_seq);
+	MAB_CUDA(cudaMemsetAsync(grp, 0, (size_t)n_seq * 8, d.stream));
+	d.zero_scal(SC_COUNT, 5); // SC_COUNT .. SC_AUX2
+	MAB_LAUNCH(d, k_sg_classify, mab_grid(n, 256), 256, 0, h.a, n, g.seq, p, ef, (uint32_t*)grp, d.d_scal);
+	const uint32_t n_arc = (uint32_t)d.get_scal(SC_COUNT);
+	bool ok = d.h_scal[SC_AUX2] == 0; // query ids ascend
+	if (ok) {
+		cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t*> in(ef, U8ToU32());
+		size_t tb = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tb, in, epos, (int64_t)n, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceScan::ExclusiveSum(tmp, tb, in, epos, (int64_t)n, d.stream);
+		++d.n_lib;
+		dg_reserve(d, g, n_arc ? n_arc : 1);
+		unsigned grid = (n_seq + SGW_WARPS - 1) / SGW_WARPS;
+		if (grid > 148u * 32u) grid = 148u * 32u;
+		MAB_LAUNCH(d, k_sg_sort_warp, grid, SGW_WARPS * 32, 0, h.a, grp, epos, g.seq, n_seq, p, lb, g.arc, big, d.d_scal);
+		const uint32_t n_big = (uint32_t)d.get_scal(SC_BIG);
+		if (n_big) {
+			static bool attr_set = false;
+			const size_t smem = (size_t)SGC_HITS * 16;
+			if (!attr_set) { MAB_CUDA(cudaFuncSetAttribute(k_sg_sort_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+			MAB_LAUNCH(d, k_sg_sort_cta, n_big < 148u ? n_big : 148u, 512, smem, h.a, grp, epos, g.seq, big, n_big, p, g.arc, d.d_scal);
+			if (d.get_scal(SC_AUX) != 0) ok = false; // a read with more hits than a CTA sorts
+		}
+	}
+	d.free(ef); d.free(epos); d.free(big); d.free(grp);
+	if (ok) g.len_bits = lb, g.n_arc = n_arc, g.is_srt = true, g.has_idx = false;
+	return ok;
+}
+
 void dh_sg_gen(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *del, const HitArcParams &p, DGraph &g)
 {
 	dh_sg_emit(d, h, len, del, p, g);
@@ -954,6 +1144,9 @@ void dh_sg_emit(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *d
 	const uint32_t lb = bits_for(mx);
 	if (h.n) {
 		if (h.n >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 arcs on one GPU\n"); exit(73); }
+		static const bool seg_sort = getenv("MAB_SG_SEGSORT") && atoi(getenv("MAB_SG_SEGSORT")) != 0;
+		if (seg_sort && sg_emit_segmented(d, h, p, lb, g)) return;
+		if (seg_sort) d.zero_scal(SC_COUNT); // the attempt counted the arcs already
 		const uint64_t sentinel = 1ull << (lb + bits_for((uint64_t)n_seq * 2 - 1));
 		uint64_t *ka = mab_alloc<uint64_t>(d, h.n), *kb = mab_alloc<uint64_t>(d, h.n), *va = mab_alloc<uint64_t>(d, h.n), *vb = mab_alloc<uint64_t>(d, h.n);
 		// seq lengths are read while other threads may set del bits: lengths are masked, so this is benign
