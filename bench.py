@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_1m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-gfa", action="store_true", help="e2e leg: GFA text formatted on the GPU (mab_write_gfa, experimental) instead of host structs + ma_ug_print")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -224,6 +225,8 @@ def main():
         device_steps()
         if rank != 0:                                                      # the result is replicated; rank 0 writes it
             return 0
+        if a.gpu_gfa:                                                      # experimental: GFA text formatted on the GPU, one D2H
+            return lib.mab_write_gfa(ctx, devnull)
         d, sub, ug = lib.mab_export_dict(ctx), lib.mab_export_sub(ctx), lib.mab_export_ug(ctx)   # D2H
         lib.ma_ug_print(ug, d, sub, devnull)                               # GFA text (host C writer)
         nb = 0
@@ -331,10 +334,11 @@ def main():
             "config": {"workload": wl["label"], "name": a.workload, "paf_lines_per_gpu": n_lines, "paf_bytes_per_gpu": n_bytes,
                        "l2": "inputs larger than L2 (PAF text and hit arrays are GBs; no flush needed)",
                        "parallelism": (f"read ids hash-sharded over {world} GPUs (owner = id mod {world}); NCCL all-to-all of hits, all-reduce of "
-                                       f"interval/flag tables, all-gather of names and arcs; one PAF = {world} partitions of the named shape")
+                                       f"interval/flag tables, all-gather of names and surviving arcs, neighbour slabs read from peers over NVLink; one PAF = {world} partitions of the named shape")
                        if world > 1 else "1 GPU"},
             "e2e": {"value": lines_all * a.steps / e2e_s, "unit": "PAF records/s", "ms_per_step": e2e_s / a.steps * 1e3,
-                    "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": d2h,
+                    "writer": "mab_write_gfa (text formatted on the GPU)" if a.gpu_gfa else "mab_export_* + ma_ug_print (host)"},
             "gpu_launches": launches, "lib_calls": libcalls,
             "arcs_per_sec_del_trans": n_arc_in / (dt_ms_trans * 1e-3) if dt_ms_trans else None,
             "del_trans": {"n_arc_in": n_arc_in, "inner_iters": inner, "n_vtx": n_vtx, "kernel_ms": dt_ms_trans},

@@ -180,6 +180,10 @@ ma_hit_t *mab_export_hits(mab_ctx_t *ctx, size_t *n);
 asg_t *mab_export_sg(mab_ctx_t *ctx);
 ma_ug_t *mab_export_ug(mab_ctx_t *ctx);
 float mab_coverage(const mab_ctx_t *ctx);
+/* The bytes of ma_ug_print(mab_export_ug(), mab_export_dict(), mab_export_sub(), fp) (asm.c:77-116) for a layout without
+ * unitig sequences, formatted on the GPU and written with one fwrite: no host copies of the tables.  Returns the number
+ * of bytes written, -1 before mab_unitigs.  (Experimental in round 1: the CLI uses it only with MAB_GPU_GFA=1.) */
+long mab_write_gfa(mab_ctx_t *ctx, FILE *fp);
 
 /* Hash-sharded multi-GPU run (one process per GPU, read r owned by rank r mod world, NCCL on the context's stream).
  * rank 0: mab_nccl_unique_id -> launcher broadcasts the bytes -> every rank: mab_shard_init.  Each rank loads ITS byte

@@ -156,6 +156,7 @@ _PRODUCT_ONLY = {
     "mab_export_sg": (C.POINTER(AsgT), [C.c_void_p]),
     "mab_export_ug": (C.POINTER(MaUg), [C.c_void_p]),
     "mab_coverage": (C.c_float, [C.c_void_p]),
+    "mab_write_gfa": (C.c_long, [C.c_void_p, C.c_void_p]),
     "mab_event_create": (C.c_void_p, []),
     "mab_event_record": (None, [C.c_void_p, C.c_void_p]),
     "mab_event_elapsed_ms": (C.c_float, [C.c_void_p, C.c_void_p]),

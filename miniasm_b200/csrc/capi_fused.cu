@@ -5,6 +5,7 @@
 #include "capi_util.cuh"
 #include "hit_dev.cuh"
 #include "clean_dev.cuh"
+#include "gfa_dev.cuh"
 #include "ingest_dev.cuh"
 #include "shard_comm.cuh"
 #include <cub/cub.cuh>
@@ -40,6 +41,8 @@ struct mab_ctx {
 	ShardComm sc;
 	char *name_text = nullptr;
 	std::map<std::string, void*> ipc_open;   // peer segments mapped through CUDA IPC (handle bytes -> local address)
+	char *h_gfa = nullptr;    // pinned landing buffer of mab_write_gfa (grow-only)
+	size_t h_gfa_cap = 0;
 };
 
 __global__ void k_sg_len(uint32_t n, const DSub *sub, const uint32_t *slen, const uint32_t *orig, uint32_t *len, uint8_t *del)
@@ -126,6 +129,7 @@ void mab_destroy(mab_ctx_t *c)
 	d.sync();
 	for (int i = 0; i < 2; ++i) if (c->pin[i]) MAB_CUDA(cudaFreeHost(c->pin[i]));
 	for (auto &kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
+	if (c->h_gfa) MAB_CUDA(cudaFreeHost(c->h_gfa));
 	d.destroy();
 	delete c;
 }
@@ -488,6 +492,32 @@ ma_ug_t *mab_export_ug(mab_ctx_t *c)
 }
 
 float mab_coverage(const mab_ctx_t *c) { return c->cov; }
+
+/* ma_ug_print(mab_export_ug, mab_export_dict, mab_export_sub, fp) without the host structs: the text is formatted on
+ * the GPU (gfa_dev.cu), copied down once and written with one fwrite.  Unitig sequences are not part of it ("*").
+ * Returns the number of bytes written, -1 if mab_unitigs has not run. */
+long mab_write_gfa(mab_ctx_t *c, FILE *fp)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	if (!c->have_ug) return -1;
+	MabDev &d = c->dev;
+	if (!c->ug.g.has_idx) dg_arc_index(d, c->ug.g); // the x lines print the arc counts of both unitig ends (asm.c:110-112)
+	char *d_txt = nullptr;
+	const size_t n = dg_gfa_text(d, c->ug, c->orig_id, c->names.off, c->names.nlen, c->name_text ? c->name_text : c->d_text, c->sub, &d_txt);
+	if (n) {
+		if (n > c->h_gfa_cap) {
+			if (c->h_gfa) MAB_CUDA(cudaFreeHost(c->h_gfa));
+			c->h_gfa_cap = n + (n >> 2) + (1 << 20);
+			MAB_CUDA(cudaHostAlloc((void**)&c->h_gfa, c->h_gfa_cap, cudaHostAllocDefault));
+		}
+		MAB_CUDA(cudaMemcpyAsync(c->h_gfa, d_txt, n, cudaMemcpyDeviceToHost, d.stream));
+		d.sync();
+		if (fwrite(c->h_gfa, 1, n, fp) != n) { fprintf(stderr, "[E::miniasm_b200] short write of the GFA text\n"); exit(74); }
+	}
+	d.free(d_txt);
+	d.sync();
+	return (long)n;
+}
 
 /* device-time probe used by bench.py: milliseconds between two points on the context's stream */
 void *mab_event_create(void) { cudaEvent_t e; MAB_CUDA(cudaEventCreate(&e)); return e; }

@@ -142,16 +142,21 @@ int main(int argc, char *argv[])
 		free(hit);
 	} else if (strcmp(outfmt, "ug") == 0 || strcmp(outfmt, "sg") == 0) {
 		fprintf(stderr, "[M::%s] ===> Step 4: graph cleaning <===\n", __func__);
+		const int gpu_gfa = strcmp(outfmt, "ug") == 0 && !fn_reads && (env = getenv("MAB_GPU_GFA")) != 0 && atoi(env) != 0;
 		mab_layout(ctx, &opt, stage);
-		d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
+		if (!gpu_gfa) d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
 		if (strcmp(outfmt, "ug") == 0) {
 			ma_ug_t *ug;
 			fprintf(stderr, "[M::%s] ===> Step 5: generating unitigs <===\n", __func__);
 			mab_unitigs(ctx);
-			ug = mab_export_ug(ctx);
-			if (fn_reads) ma_ug_seq(ug, d, sub, fn_reads);
-			ma_ug_print(ug, d, sub, stdout);
-			ma_ug_destroy(ug);
+			if (gpu_gfa) { /* experimental: text formatted on the GPU, no host copies of the tables */
+				mab_write_gfa(ctx, stdout);
+			} else {
+				ug = mab_export_ug(ctx);
+				if (fn_reads) ma_ug_seq(ug, d, sub, fn_reads);
+				ma_ug_print(ug, d, sub, stdout);
+				ma_ug_destroy(ug);
+			}
 		} else {
 			asg_t *sg = mab_export_sg(ctx);
 			ma_sg_print(sg, d, sub, stdout);

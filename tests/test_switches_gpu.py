@@ -23,7 +23,7 @@ SETS = {
     "deep": "-n 1500 -l 3000 -L 12000 -c 400 -j 30 -s 77",      # several hundred hits per read: the CTA-per-read kernels
 }
 VERIFIED = [{"MAB_CUB_SELECT": "1"}, {"MAB_SUB_SMEM_SORT": "1"}, {"MAB_WRITER_THREADS": "3"}]
-EXPERIMENTAL = [{"MAB_SG_SEGSORT": "1"}]
+EXPERIMENTAL = [{"MAB_SG_SEGSORT": "1"}, {"MAB_GPU_GFA": "1"}, {"MAB_SG_SEGSORT": "1", "MAB_GPU_GFA": "1"}]
 
 
 @pytest.fixture(scope="module")
