@@ -28,16 +28,16 @@ struct GfaView {
 
 struct CountSink {
 	uint32_t n;
-	__device__ __forceinline__ void c(char) { ++n; }
-	__device__ __forceinline__ void bytes(const char *, uint32_t l) { n += l; }
+	__host__ __device__ __forceinline__ void c(char) { ++n; }
+	__host__ __device__ __forceinline__ void bytes(const char *, uint32_t l) { n += l; }
 };
 struct WriteSink {
 	char *p;
-	__device__ __forceinline__ void c(char ch) { *p++ = ch; }
-	__device__ __forceinline__ void bytes(const char *s, uint32_t l) { for (uint32_t k = 0; k < l; ++k) p[k] = s[k]; p += l; }
+	__host__ __device__ __forceinline__ void c(char ch) { *p++ = ch; }
+	__host__ __device__ __forceinline__ void bytes(const char *s, uint32_t l) { for (uint32_t k = 0; k < l; ++k) p[k] = s[k]; p += l; }
 };
 
-template <class Sink> __device__ __forceinline__ void put_dec(Sink &s, uint32_t x, int min_digits)
+template <class Sink> __host__ __device__ __forceinline__ void put_dec(Sink &s, uint32_t x, int min_digits)
 {
 	char t[10];
 	int n = 0;
@@ -45,19 +45,19 @@ template <class Sink> __device__ __forceinline__ void put_dec(Sink &s, uint32_t 
 	for (int k = n; k < min_digits; ++k) s.c('0');
 	while (n) s.c(t[--n]);
 }
-template <class Sink> __device__ __forceinline__ void put_int(Sink &s, int32_t v) // "%d"
+template <class Sink> __host__ __device__ __forceinline__ void put_int(Sink &s, int32_t v) // "%d"
 {
 	uint32_t x = (uint32_t)v;
 	if (v < 0) s.c('-'), x = 0u - x;
 	put_dec(s, x, 1);
 }
-template <class Sink> __device__ __forceinline__ void put_utg(Sink &s, uint32_t i, bool circ) // "utg%.6d%c" of i + 1
+template <class Sink> __host__ __device__ __forceinline__ void put_utg(Sink &s, uint32_t i, bool circ) // "utg%.6d%c" of i + 1
 {
 	s.c('u'); s.c('t'); s.c('g');
 	put_dec(s, i + 1, 6);
 	s.c(circ ? 'c' : 'l');
 }
-template <class Sink> __device__ __forceinline__ void put_read(Sink &s, const GfaView &v, uint32_t r) // name or name:s+1-e
+template <class Sink> __host__ __device__ __forceinline__ void put_read(Sink &s, const GfaView &v, uint32_t r) // name or name:s+1-e
 {
 	const uint32_t o = v.orig ? v.orig[r] : r;
 	s.bytes(v.text + v.noff[o], v.nlen[o]);
@@ -66,9 +66,9 @@ template <class Sink> __device__ __forceinline__ void put_read(Sink &s, const Gf
 		s.c(':'); put_int(s, (int32_t)((b.s_del & 0x7fffffffu) + 1)); s.c('-'); put_int(s, (int32_t)b.e);
 	}
 }
-template <class Sink> __device__ __forceinline__ void put_lit(Sink &s, const char *lit, uint32_t l) { for (uint32_t k = 0; k < l; ++k) s.c(lit[k]); }
+template <class Sink> __host__ __device__ __forceinline__ void put_lit(Sink &s, const char *lit, uint32_t l) { for (uint32_t k = 0; k < l; ++k) s.c(lit[k]); }
 
-template <class Sink> __device__ void emit_record(const GfaView &v, uint64_t rec, Sink &s)
+template <class Sink> __host__ __device__ void emit_record(const GfaView &v, uint64_t rec, Sink &s)
 {
 	const uint64_t n_block = (uint64_t)v.n_utg + v.n_items;
 	if (rec < n_block) {
@@ -175,4 +175,37 @@ size_t dg_gfa_text(MabDev &d, const DUnitigs &ug, const uint32_t *orig, const ui
 	d.free(ioff); d.free(len); d.free(pos);
 	*d_text_out = out;
 	return bytes;
+}
+
+// ---- host probe (tests only): the same emitter compiled for the CPU, fed from the reference's host structs ------------
+// Lets the CPU test tier compare the formatter with ma_ug_print byte for byte without a GPU (tests/test_host_cpu.py).
+#include "../../include/miniasm_b200.h"
+#include <vector>
+#include <string>
+
+extern "C" size_t mab_test_gfa_host(const ma_ug_t *ug, const sdict_t *d, const ma_sub_t *sub, char *out, size_t cap)
+{
+	std::vector<DUtgMeta> meta(ug->u.n ? ug->u.n : 1);
+	std::vector<uint64_t> items;
+	for (size_t i = 0; i < ug->u.n; ++i) {
+		const ma_utg_t *p = &ug->u.a[i];
+		meta[i].len = p->len, meta[i].circ = p->circ, meta[i].start = p->start, meta[i].end = p->end, meta[i].n = p->n, meta[i].first = (uint32_t)items.size();
+		items.insert(items.end(), p->a, p->a + p->n);
+	}
+	std::vector<uint32_t> ioff(items.size() + 1, 0);
+	for (size_t k = 0; k < items.size(); ++k) ioff[k + 1] = ioff[k] + (uint32_t)items[k];
+	std::string text;
+	std::vector<uint64_t> noff(d->n_seq ? d->n_seq : 1);
+	std::vector<uint32_t> nlen(d->n_seq ? d->n_seq : 1);
+	for (uint32_t r = 0; r < d->n_seq; ++r) noff[r] = text.size(), nlen[r] = (uint32_t)strlen(d->seq[r].name), text += d->seq[r].name;
+	GfaView v{meta.data(), items.data(), ioff.data(), (uint32_t)ug->u.n, (uint64_t)items.size(),
+	          (const DArc*)ug->g->arc, ug->g->n_arc, ug->g->idx, nullptr, noff.data(), nlen.data(), text.data(), (const DSub*)sub};
+	const uint64_t n_rec = (uint64_t)v.n_utg * 2 + v.n_items + v.n_uarc;
+	size_t tot = 0;
+	for (uint64_t r = 0; r < n_rec; ++r) { CountSink s{0}; emit_record(v, r, s); tot += s.n; }
+	if (out && tot <= cap) {
+		char *p = out;
+		for (uint64_t r = 0; r < n_rec; ++r) { WriteSink s{p}; emit_record(v, r, s); p = s.p; }
+	}
+	return tot;
 }

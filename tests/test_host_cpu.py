@@ -216,3 +216,21 @@ def test_ug_writer_threads_keep_the_byte_stream(built, monkeypatch):
         for i in range(d.contents.n_seq):
             ref.sd_put(d2, d.contents.seq[i].name, d.contents.seq[i].len)
         assert ref.print_to_string("ma_ug_print", C.pointer(ug), d2, subp) == outs["0"]
+
+
+def test_device_gfa_formatter_matches_host_writer(built):
+    """gfa_dev.cu's record emitter (what mab_write_gfa runs one thread per line of) compiled for the CPU through
+    mab_test_gfa_host, against ma_ug_print on the same hand-built layout: S/L/a/x lines, circular unitigs, links."""
+    prod = capi.load_product(strict=False)
+    f = prod.dll.mab_test_gfa_host
+    f.restype = C.c_size_t
+    f.argtypes = [C.POINTER(capi.MaUg), C.POINTER(capi.Sdict), C.c_void_p, C.c_void_p, C.c_size_t]
+    for seed, with_sub in ((5, True), (6, False), (7, True)):
+        ug, d, sub, keep = _synthetic_layout(prod, 40, seed)
+        subp = C.c_void_p(sub.ctypes.data) if with_sub else None
+        want = prod.print_to_string("ma_ug_print", C.pointer(ug), d, subp)
+        n = f(C.pointer(ug), d, subp, None, 0)
+        assert n == len(want)
+        buf = C.create_string_buffer(n)
+        assert f(C.pointer(ug), d, subp, buf, n) == n
+        assert buf.raw == want
