@@ -493,9 +493,11 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 // all executed exactly once per vertex, i.e. per-vertex bookkeeping: this variant removes the run-time peer/no-peer
 // selection (template parameter), clears the table with one or two 128-bit stores instead of a general unrolled loop,
 // keeps every slab loop rolled (two entries per lane cover 64 arcs; unrolled copies were dead weight in the
-// instruction stream) and prefetches the next vertex's index/seq words, the two loads every iteration stalls on first.
+// instruction stream), prefetches the next vertex's index/seq words, the two loads every iteration stalls on first, and
+// (SORTED, i.e. whenever the graph says is_srt) uses that a slab is sorted by length: the arcs that satisfy the length
+// bound are then a prefix by themselves and the first-violation masks of the general case drop out.
 // ---------------------------------------------------------------------------------------------
-template <bool STATS, bool P2P>
+template <bool STATS, bool P2P, bool SORTED>
 __global__ void __launch_bounds__(DT_WARPS * 32, 6)
 k_del_trans_warp7(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, const uint32_t *__restrict__ seq,
                  uint32_t n_vtx, uint32_t fuzz, uint8_t *__restrict__ flag,
@@ -604,8 +606,9 @@ k_del_trans_warp7(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx
 				const bool ok0 = in0 && a0.x + li <= L, ok1 = in1 && a1.x + li <= L;
 				const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
 				// the scan of the reference stops at the first j that violates the bound: entries before it, in slab order
-				const unsigned pre0 = m0 == 0xffffffffu ? m0 : ((1u << (__ffs(~m0) - 1)) - 1);
-				const unsigned pre1 = m0 != 0xffffffffu ? 0u : (m1 == 0xffffffffu ? m1 : ((1u << (__ffs(~m1) - 1)) - 1));
+				// (SORTED: the slab is sorted by length, so the entries that pass already form that prefix)
+				const unsigned pre0 = SORTED ? m0 : (m0 == 0xffffffffu ? m0 : ((1u << (__ffs(~m0) - 1)) - 1));
+				const unsigned pre1 = SORTED ? m1 : (m0 != 0xffffffffu ? 0u : (m1 == 0xffffffffu ? m1 : ((1u << (__ffs(~m1) - 1)) - 1)));
 				if (pre0 >> lane & 1) {
 					uint32_t h = dt_hash(a0.z, mask);
 					for (;;) {
@@ -854,11 +857,11 @@ uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo
 		// the inner-iteration counter (for the roofline arithmetic) costs issue slots: only counted when asked for
 		static const bool v7 = getenv("MAB_DT_V7") && atoi(getenv("MAB_DT_V7")) != 0;
 		if (v7) {
-			const bool st = mab_del_trans_count_inner != 0, p2p = peer != nullptr;
-			if (st && p2p) MAB_LAUNCH(d, (k_del_trans_warp7<true, true>), grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, own_lo, own_hi, sv);
-			else if (st) MAB_LAUNCH(d, (k_del_trans_warp7<true, false>), grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, own_lo, own_hi, sv);
-			else if (p2p) MAB_LAUNCH(d, (k_del_trans_warp7<false, true>), grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, own_lo, own_hi, sv);
-			else MAB_LAUNCH(d, (k_del_trans_warp7<false, false>), grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, own_lo, own_hi, sv);
+			const bool st = mab_del_trans_count_inner != 0, p2p = peer != nullptr, srt = g.is_srt;
+			#define DT7(S, P, O) MAB_LAUNCH(d, (k_del_trans_warp7<S, P, O>), grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, own_lo, own_hi, sv)
+			if (st) { if (p2p) { if (srt) DT7(true, true, true); else DT7(true, true, false); } else { if (srt) DT7(true, false, true); else DT7(true, false, false); } }
+			else { if (p2p) { if (srt) DT7(false, true, true); else DT7(false, true, false); } else { if (srt) DT7(false, false, true); else DT7(false, false, false); } }
+			#undef DT7
 		} else
 		if (mab_del_trans_count_inner) MAB_LAUNCH(d, k_del_trans_warp<true>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr, own_lo, own_hi, sv);
 		else MAB_LAUNCH(d, k_del_trans_warp<false>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr, own_lo, own_hi, sv);
