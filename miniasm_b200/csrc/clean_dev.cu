@@ -274,6 +274,23 @@ __global__ void k_spec_commit(GV g, Rule rule, uint32_t lo, uint32_t hi, const u
 	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_done, (unsigned long long)cnt);
 }
 
+// Windowed rounds (experimental, MAB_SPEC_WINDOW=1): a round only looks at the vertices [lo, lo + W).  Vertices beyond
+// the window neither stamp nor commit in that round, and a stamp only ever invalidates LARGER vertices, so the prefix
+// that commits is still exactly the sequential outcome; what changes is the cost of a round, O(W) instead of
+// O(n_vtx - lo).  W shrinks towards the distance the last round advanced and grows back when a whole window commits:
+// dense conflict chains (bubbles along a contig with sorted ids advance a few vertices per round) stop paying for
+// a full-graph evaluation each time.  The kernels are unchanged: they loop to GV::n_vtx, which is set to the window end.
+struct SpecWindow {
+	bool on; uint32_t n_vtx, W;
+	explicit SpecWindow(uint32_t n) : n_vtx(n), W(n) { const char *e = getenv("MAB_SPEC_WINDOW"); on = e && atoi(e) != 0; }
+	uint32_t end(uint32_t lo) const { return !on || (uint64_t)lo + W >= n_vtx ? n_vtx : lo + W; }
+	void advanced(uint32_t lo, uint32_t hi, uint32_t end) {
+		if (!on) return;
+		if (hi >= end) W = (uint64_t)W * 4 >= n_vtx ? n_vtx : W * 4;                 // the whole window went through
+		else { const uint64_t w = 16ull * (hi - lo + 1); W = w < 4096 ? 4096 : (w < W ? (uint32_t)w : W); }
+	}
+};
+
 template <class Rule>
 static uint32_t run_spec_rounds(MabDev &d, DGraph &g, Rule rule)
 {
@@ -284,18 +301,28 @@ static uint32_t run_spec_rounds(MabDev &d, DGraph &g, Rule rule)
 	uint8_t *cand = mab_alloc<uint8_t>(d, n_vtx);
 	uint32_t *tag = mab_alloc<uint32_t>(d, g.n_seq);
 	MAB_CUDA(cudaMemsetAsync(tag, 0xff, (size_t)g.n_seq * 4, d.stream));
+	SpecWindow win(n_vtx);
 	while (lo < n_vtx) {
-		const unsigned grid = mab_grid(n_vtx - lo, 128);
+		const uint32_t end = win.end(lo);
+		GV gw = gv;
+		gw.n_vtx = end;                                              // the eval / check kernels stop at the window end
+		const unsigned grid = mab_grid(end - lo, 128);
 		d.zero_scal(SC_COUNT, 2);
 		MAB_CUDA(cudaMemsetAsync(d.d_scal + SC_MIN, 0xff, 8, d.stream));
-		MAB_LAUNCH(d, k_spec_eval<Rule>, grid, 128, 0, gv, rule, lo, cand, tag, d.d_scal + SC_COUNT);
-		if (d.get_scal(SC_COUNT) == 0) break;                      // nobody left who would act
-		MAB_LAUNCH(d, k_spec_check<Rule>, grid, 128, 0, gv, rule, lo, cand, tag, d.d_scal + SC_MIN);
+		MAB_LAUNCH(d, k_spec_eval<Rule>, grid, 128, 0, gw, rule, lo, cand, tag, d.d_scal + SC_COUNT);
+		if (d.get_scal(SC_COUNT) == 0) {                             // nobody in [lo, end) would act (and nobody stamped)
+			if (end == n_vtx) break;
+			win.advanced(lo, end, end);
+			lo = end;
+			continue;
+		}
+		MAB_LAUNCH(d, k_spec_check<Rule>, grid, 128, 0, gw, rule, lo, cand, tag, d.d_scal + SC_MIN);
 		unsigned long long xs = d.get_scal(SC_MIN);
-		uint32_t hi = xs >= n_vtx ? n_vtx : (uint32_t)xs;
+		uint32_t hi = xs >= end ? end : (uint32_t)xs;
 		MAB_LAUNCH(d, k_spec_commit<Rule>, mab_grid(hi - lo, 128), 128, 0, gv, rule, lo, hi, cand, d.d_scal + SC_NSEL);
 		MAB_CUDA(cudaMemsetAsync(tag, 0xff, (size_t)g.n_seq * 4, d.stream));
 		total += (uint32_t)d.get_scal(SC_NSEL);
+		win.advanced(lo, hi, end);
 		lo = hi;
 		++rounds;
 	}
@@ -559,12 +586,21 @@ uint64_t dg_pop_bubble(MabDev &d, DGraph &g, int max_dist)
 		uint32_t bcap = 256, n_slot = 4096;
 		bub_slots_alloc(d, sl, n_slot, bcap);
 		uint32_t lo = 0;
+		SpecWindow win(n_vtx);
 		while (lo < n_vtx) {
+			const uint32_t end = win.end(lo);
+			GV gw = gv;
+			gw.n_vtx = end;                                          // sources and own-cell checks of [lo, end) only
 			d.zero_scal(SC_COUNT, 4); // COUNT (candidates), NSEL, BIG (overflow), AUX (sources)
 			MAB_CUDA(cudaMemsetAsync(d.d_scal + SC_MIN, 0xff, 8, d.stream));
-			MAB_LAUNCH(d, k_bub_sources, mab_grid(n_vtx - lo, 256), 256, 0, gv, lo, src, d.d_scal + SC_AUX);
+			MAB_LAUNCH(d, k_bub_sources, mab_grid(end - lo, 256), 256, 0, gw, lo, src, d.d_scal + SC_AUX);
 			uint32_t n_src = (uint32_t)d.get_scal(SC_AUX);
-			if (n_src == 0) break;
+			if (n_src == 0) {
+				if (end == n_vtx) break;
+				win.advanced(lo, end, end);
+				lo = end;
+				continue;
+			}
 			const unsigned wgrid = (sl.n_slot + 63) / 64;
 			MAB_LAUNCH(d, k_bub_eval, wgrid, 64, 0, gv, (uint32_t)max_dist, sl, src, n_src, cand, tag, d.d_scal + SC_COUNT, d.d_scal + SC_BIG);
 			uint64_t n_cand = d.get_scal(SC_COUNT);
@@ -577,16 +613,22 @@ uint64_t dg_pop_bubble(MabDev &d, DGraph &g, int max_dist)
 				MAB_CUDA(cudaMemsetAsync(tag, 0xff, (size_t)g.n_seq * 4, d.stream));
 				continue;
 			}
-			if (n_cand == 0) break;
-			MAB_LAUNCH(d, k_bub_check_own, mab_grid(n_vtx - lo, 256), 256, 0, gv, lo, tag, d.d_scal + SC_MIN);
+			if (n_cand == 0) {                                       // no source of the window pops anything (nobody stamped)
+				if (end == n_vtx) break;
+				win.advanced(lo, end, end);
+				lo = end;
+				continue;
+			}
+			MAB_LAUNCH(d, k_bub_check_own, mab_grid(end - lo, 256), 256, 0, gw, lo, tag, d.d_scal + SC_MIN);
 			MAB_LAUNCH(d, k_bub_check_walk, wgrid, 64, 0, gv, (uint32_t)max_dist, sl, src, n_src, tag, d.d_scal + SC_MIN);
 			unsigned long long xs = d.get_scal(SC_MIN);
-			uint32_t hi = xs >= n_vtx ? n_vtx : (uint32_t)xs;
+			uint32_t hi = xs >= end ? end : (uint32_t)xs;
 			d.zero_scal(SC_TMP0, 2);
 			MAB_LAUNCH(d, k_bub_commit, wgrid, 64, 0, gv, (uint32_t)max_dist, sl, src, n_src, cand, hi, d.d_scal + SC_TMP0, d.d_scal + SC_TMP0 + 1);
 			MAB_CUDA(cudaMemsetAsync(tag, 0xff, (size_t)g.n_seq * 4, d.stream));
 			n_pop += d.get_scal(SC_TMP0);
 			n_tip += d.h_scal[SC_TMP0 + 1];
+			win.advanced(lo, hi, end);
 			lo = hi;
 			++rounds;
 		}

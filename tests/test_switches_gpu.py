@@ -22,10 +22,12 @@ SETS = {
     "shuffled": "shuffled",
     "deep": "-n 1500 -l 3000 -L 12000 -c 400 -j 30 -s 77",      # several hundred hits per read: the CTA-per-read kernels
     "multi": "-n 5000 -s 5 -d 200000 -j 30",                          # 20 % duplicated overlaps -> multi-arcs (shared marks in the transitive reduction)
-    "skew": "skew_small",                                          # hot spots: slabs beyond the warp kernels' limits
+    "skew": "skew_small",
+    "bubbly": "-n 60000 -l 9000 -L 11000 -j 800 -c 30 -s 21",     # thousands of bubbles/tips along sorted ids: many speculative rounds                                          # hot spots: slabs beyond the warp kernels' limits
 }
 VERIFIED = [{"MAB_CUB_SELECT": "1"}, {"MAB_SUB_SMEM_SORT": "1"}, {"MAB_WRITER_THREADS": "3"}]
-EXPERIMENTAL = [{"MAB_SG_SEGSORT": "1"}, {"MAB_GPU_GFA": "1"}, {"MAB_DT_V7": "1"}, {"MAB_SG_SEGSORT": "1", "MAB_GPU_GFA": "1", "MAB_DT_V7": "1"}]
+EXPERIMENTAL = [{"MAB_SG_SEGSORT": "1"}, {"MAB_GPU_GFA": "1"}, {"MAB_DT_V7": "1"}, {"MAB_SPEC_WINDOW": "1"},
+                {"MAB_SG_SEGSORT": "1", "MAB_GPU_GFA": "1", "MAB_DT_V7": "1", "MAB_SPEC_WINDOW": "1"}]
 
 
 @pytest.fixture(scope="module")

@@ -31,6 +31,13 @@ run_bench segsort MAB_SG_SEGSORT=1
 run_bench dtv7 MAB_DT_V7=1
 run_bench gpugfa -- --gpu-gfa
 run_bench all MAB_SG_SEGSORT=1 MAB_DT_V7=1 -- --gpu-gfa
+echo "== stage (iii) rounds on a bubble-dense set (300 K reads, jittered ends): default vs windowed =="
+python -c "from miniasm_b200 import synth; synth.generate('-n 300000 -l 9000 -L 11000 -j 800 -c 30 -s 15', '/tmp/bub.paf')"
+for w in 0 1; do
+	/usr/bin/time -f "MAB_SPEC_WINDOW=$w wall %e s" env MAB_SPEC_WINDOW=$w MAB_TRACE=1 miniasm_b200/miniasm-b200 /tmp/bub.paf > /tmp/bub_$w.gfa 2> gpurun_out/sw_bub_$w.err
+	grep -E "cleaning passes|popped|cut [0-9]+ tips" gpurun_out/sw_bub_$w.err | tail -4
+done
+cmp -s /tmp/bub_0.gfa /tmp/bub_1.gfa && echo "bubble set: same GFA" || echo "bubble set: GFA DIFFERS"
 echo "== ncu: default and v7 transitive reduction =="
 for v in 0 1; do
 	MAB_DT_V7=$v ncu --set full --clock-control none --import-source on -k regex:"k_del_trans_warp" -c 1 -o gpurun_out/sw_dt_v7_$v \
