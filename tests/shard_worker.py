@@ -1,5 +1,5 @@
 """One rank of the sharded parity run (launched by tests/test_shard_gpu.py through torch.distributed.run).
-argv: paf_path out_gfa_path"""
+argv: paf_path|gen:<n_reads>:<seed> out_gfa_path      (gen: = the PAF of a BASELINE config generated in memory on every rank)"""
 import ctypes as C
 import os
 import sys
@@ -20,7 +20,15 @@ def main():
     lib.set_verbose(0)
     ctx = lib.mab_create(local)
     sharded.init(lib, ctx, rank, world)
-    data = open(paf, "rb").read()
+    if paf.startswith("gen:"):
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+        _, n_reads, seed = paf.split(":")
+        buf, n_bytes, _, free = bench.generate(int(n_reads), int(seed))
+        data = C.string_at(buf, n_bytes)
+        free()
+    else:
+        data = open(paf, "rb").read()
     b, e = sharded.split_ranges(data, world)[rank]
     part = data[b:e]
     lib.mab_load_paf_text(ctx, part, len(part))
