@@ -619,7 +619,14 @@ uint64_t dg_pop_bubble(MabDev &d, DGraph &g, int max_dist)
 				lo = end;
 				continue;
 			}
-			MAB_LAUNCH(d, k_bub_check_own, mab_grid(end - lo, 256), 256, 0, gw, lo, tag, d.d_scal + SC_MIN);
+			// Experimental (MAB_BUB_SKIP_OWN=1): leave the non-sources out of the validity check.  Inside this pass the graph
+			// only loses arcs and vertices (a pop deletes its region and restores the path it walked, all of it live
+			// before; no multi-arcs here), so a vertex that is not a source now can never become one: it is a final no-op
+			// whatever smaller candidates do.  The sources -- candidates or not -- are all re-walked by k_bub_check_walk.
+			// With the own-cell check, a pop at source s invalidates the very next vertex id inside its own bubble, so on
+			// genome-ordered ids x* = s + 1 and every round commits a single pop.
+			static const bool skip_own = getenv("MAB_BUB_SKIP_OWN") && atoi(getenv("MAB_BUB_SKIP_OWN")) != 0;
+			if (!skip_own) MAB_LAUNCH(d, k_bub_check_own, mab_grid(end - lo, 256), 256, 0, gw, lo, tag, d.d_scal + SC_MIN);
 			MAB_LAUNCH(d, k_bub_check_walk, wgrid, 64, 0, gv, (uint32_t)max_dist, sl, src, n_src, tag, d.d_scal + SC_MIN);
 			unsigned long long xs = d.get_scal(SC_MIN);
 			uint32_t hi = xs >= end ? end : (uint32_t)xs;

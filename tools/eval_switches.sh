@@ -33,11 +33,12 @@ run_bench gpugfa -- --gpu-gfa
 run_bench all MAB_SG_SEGSORT=1 MAB_DT_V7=1 -- --gpu-gfa
 echo "== stage (iii) rounds on a bubble-dense set (300 K reads, jittered ends): default vs windowed =="
 python -c "from miniasm_b200 import synth; synth.generate('-n 300000 -l 9000 -L 11000 -j 800 -c 30 -s 15', '/tmp/bub.paf')"
-for w in 0 1; do
-	/usr/bin/time -f "MAB_SPEC_WINDOW=$w wall %e s" env MAB_SPEC_WINDOW=$w MAB_TRACE=1 miniasm_b200/miniasm-b200 /tmp/bub.paf > /tmp/bub_$w.gfa 2> gpurun_out/sw_bub_$w.err
-	grep -E "cleaning passes|popped|cut [0-9]+ tips" gpurun_out/sw_bub_$w.err | tail -4
+for w in 00 10 01 11; do
+	/usr/bin/time -f "window=${w:0:1} skip_own=${w:1:1} wall %e s" env MAB_SPEC_WINDOW=${w:0:1} MAB_BUB_SKIP_OWN=${w:1:1} MAB_TRACE=1 miniasm_b200/miniasm-b200 /tmp/bub.paf > /tmp/bub_$w.gfa 2> gpurun_out/sw_bub_$w.err
+	grep -E "cleaning passes|popped|wall" gpurun_out/sw_bub_$w.err | tail -4
+	cmp -s /tmp/bub_00.gfa /tmp/bub_$w.gfa && echo "  same GFA as default" || echo "  GFA DIFFERS from default"
 done
-cmp -s /tmp/bub_0.gfa /tmp/bub_1.gfa && echo "bubble set: same GFA" || echo "bubble set: GFA DIFFERS"
+oracle/_ref/miniasm_ref /tmp/bub.paf 2>/dev/null | cmp -s - /tmp/bub_00.gfa && echo "default GFA == reference" || echo "default GFA differs from the reference"
 echo "== ncu: default and v7 transitive reduction =="
 for v in 0 1; do
 	MAB_DT_V7=$v ncu --set full --clock-control none --import-source on -k regex:"k_del_trans_warp" -c 1 -o gpurun_out/sw_dt_v7_$v \
