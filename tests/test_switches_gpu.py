@@ -26,8 +26,8 @@ SETS = {
     "bubbly": "-n 60000 -l 9000 -L 11000 -j 800 -c 30 -s 21",     # thousands of bubbles/tips along sorted ids: many speculative rounds                                          # hot spots: slabs beyond the warp kernels' limits
 }
 VERIFIED = [{"MAB_CUB_SELECT": "1"}, {"MAB_SUB_SMEM_SORT": "1"}, {"MAB_WRITER_THREADS": "3"}]
-EXPERIMENTAL = [{"MAB_SG_SEGSORT": "1"}, {"MAB_GPU_GFA": "1"}, {"MAB_DT_V7": "1"}, {"MAB_SPEC_WINDOW": "1"}, {"MAB_BUB_SKIP_OWN": "1"},
-                {"MAB_SG_SEGSORT": "1", "MAB_GPU_GFA": "1", "MAB_DT_V7": "1", "MAB_SPEC_WINDOW": "1", "MAB_BUB_SKIP_OWN": "1"}]
+EXPERIMENTAL = [{"MAB_SG_SEGSORT": "1"}, {"MAB_GPU_GFA": "1"}, {"MAB_DT_V7": "1"}, {"MAB_SPEC_WINDOW": "1"}, {"MAB_BUB_EXCUSE": "1"},
+                {"MAB_SG_SEGSORT": "1", "MAB_GPU_GFA": "1", "MAB_DT_V7": "1", "MAB_SPEC_WINDOW": "1", "MAB_BUB_EXCUSE": "1"}]
 
 
 @pytest.fixture(scope="module")

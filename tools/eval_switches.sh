@@ -34,7 +34,7 @@ run_bench all MAB_SG_SEGSORT=1 MAB_DT_V7=1 -- --gpu-gfa
 echo "== stage (iii) rounds on a bubble-dense set (300 K reads, jittered ends): default vs windowed =="
 python -c "from miniasm_b200 import synth; synth.generate('-n 300000 -l 9000 -L 11000 -j 800 -c 30 -s 15', '/tmp/bub.paf')"
 for w in 00 10 01 11; do
-	/usr/bin/time -f "window=${w:0:1} skip_own=${w:1:1} wall %e s" env MAB_SPEC_WINDOW=${w:0:1} MAB_BUB_SKIP_OWN=${w:1:1} MAB_TRACE=1 miniasm_b200/miniasm-b200 /tmp/bub.paf > /tmp/bub_$w.gfa 2> gpurun_out/sw_bub_$w.err
+	/usr/bin/time -f "window=${w:0:1} excuse=${w:1:1} wall %e s" env MAB_SPEC_WINDOW=${w:0:1} MAB_BUB_EXCUSE=${w:1:1} MAB_TRACE=1 miniasm_b200/miniasm-b200 /tmp/bub.paf > /tmp/bub_$w.gfa 2> gpurun_out/sw_bub_$w.err
 	grep -E "cleaning passes|popped|wall" gpurun_out/sw_bub_$w.err | tail -4
 	cmp -s /tmp/bub_00.gfa /tmp/bub_$w.gfa && echo "  same GFA as default" || echo "  GFA DIFFERS from default"
 done
