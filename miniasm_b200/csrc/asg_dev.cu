@@ -507,13 +507,11 @@ k_del_trans_warp7(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx
 	__shared__ __align__(16) uint32_t s_hkey[DT_WARPS][DT_HASH];
 	__shared__ uint32_t s_tl[DT_WARPS][DT_MAXD];
 	__shared__ uint32_t s_fmin[DT_WARPS][DT_HASH];
-	__shared__ uint64_t s_ti[DT_WARPS][DT_EAGER];
 	__shared__ uint8_t  s_hmark[DT_WARPS][DT_HASH];
 	__shared__ uint8_t  s_slot[DT_WARPS][DT_MAXD];
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	uint32_t *hkey = s_hkey[warp], *tl = s_tl[warp], *fmin = s_fmin[warp];
-	uint64_t *ti = s_ti[warp];
 	uint8_t *hmark = s_hmark[warp], *slot = s_slot[warp];
 	unsigned n_red = 0;
 	unsigned long long n_inner = 0;
@@ -545,6 +543,7 @@ k_del_trans_warp7(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx
 		// stage the slab and build the target table in one sweep; every lane carries two slab entries per
 		// iteration (i and i+32), so slabs of up to 64 arcs -- nearly all of them -- take a single iteration
 		bool dup = false;
+		uint64_t my_iw = 0; // lanes 0..DT_EAGER-1: index word of the target of slab entry `lane`, fetched ahead of use
 		#pragma unroll 1
 		for (uint32_t base = 0; base < nv; base += 64) {
 			const uint32_t i0 = base + lane, i1 = i0 + 32;
@@ -554,7 +553,7 @@ k_del_trans_warp7(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx
 			if (v1) a1 = ld_arc4(arc + off + i1);
 			if (v0) {
 				tl[i0] = a0.x;
-				if (i0 < DT_EAGER) ti[i0] = __ldg(nidx + a0.z);
+				if (i0 < DT_EAGER) my_iw = __ldg(nidx + a0.z);
 				uint32_t h = dt_hash(a0.z, mask);
 				for (;;) {
 					const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a0.z);
@@ -594,7 +593,9 @@ k_del_trans_warp7(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx
 			if (nxt >= nv) break;
 			i = nxt;
 			const uint32_t w = hkey[slot[i]], li = tl[i];
-			const uint64_t iw = i < DT_EAGER ? ti[i] : __ldg(nidx + w);
+			uint64_t iw; // i is warp-uniform: the prefetched word sits in lane i's register
+			if (i < DT_EAGER) iw = (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(my_iw >> 32), i) << 32 | __shfl_sync(0xffffffffu, (uint32_t)my_iw, i);
+			else iw = __ldg(nidx + w);
 			const uint32_t nw = (uint32_t)iw;
 			const DArc *pw = (P2P ? slab_base(sv, arc, w) : arc) + (iw >> 32) + lane;
 			#pragma unroll 1
