@@ -155,6 +155,103 @@ static uint32_t spec_rounds(asg_t *g, int max_dist, int skip_own, int window, in
 	return rounds;
 }
 
+/* ------------------------------------------------------------------------------------------------------------
+ * The same for asg_cut_tip (TipRule of clean_dev.cu): a candidate stamps every cell it reads (utg_end of v and of
+ * every chain vertex: the vertex's read and its single neighbour's) or writes (read_del of each chain read: the
+ * read and every read one of its arcs points to).  excuse = 1: an invalid vertex whose read a VALID smaller candidate
+ * is going to delete does not stop the prefix -- on a deleted read the rule returns at its first test, for good.
+ * ------------------------------------------------------------------------------------------------------------ */
+static int utg_end_cells(const asg_t *g, uint32_t v, uint64_t *lw, u32v *cells)
+{
+	const asg_arc_t *av = A_A(g, v ^ 1), *aw;
+	uint32_t i, n = 0, last = 0, nv = A_N(g, v ^ 1), w, nw;
+	vpush(cells, v >> 1);
+	for (i = 0; i < nv; ++i) if (!av[i].del) last = i, ++n;
+	if (n == 0) return E_TIP;
+	if (n > 1) return E_MOUT;
+	if (lw) *lw = av[last].ul << 32 | av[last].v;
+	w = av[last].v ^ 1; aw = A_A(g, w); nw = A_N(g, w);
+	vpush(cells, w >> 1);
+	for (i = n = 0; i < nw; ++i) if (!aw[i].del) ++n;
+	return n == 1 ? E_MERGE : E_MNEI;
+}
+
+/* 1 if v cuts a tip on the current state; cells = read set (+ write set when it acts), chain = the reads it deletes */
+static int tip_eval(const asg_t *g, uint32_t v, int max_ext, u32v *cells, u32v *chain)
+{
+	int r;
+	uint64_t lw = 0;
+	uint32_t x = v, i, k;
+	cells->n = chain->n = 0;
+	if (g->seq[v >> 1].del) { vpush(cells, v >> 1); return 0; }
+	if (utg_end_cells(g, v, 0, cells) != E_TIP) return 0;
+	vpush(chain, x >> 1);
+	do {
+		r = utg_end_cells(g, x ^ 1, &lw, cells);
+		if (r != E_MERGE) break;
+		x = (uint32_t)lw; vpush(chain, x >> 1);
+	} while (--max_ext > 0);
+	if (r == E_MERGE) return 0;
+	for (i = 0; i < chain->n; ++i)                       /* write set: seq_del_cells */
+		for (vpush(cells, chain->a[i]), k = 0; k < 2; ++k) {
+			uint32_t u = chain->a[i] << 1 | k, j, nu = A_N(g, u);
+			const asg_arc_t *au = A_A(g, u);
+			for (j = 0; j < nu; ++j) vpush(cells, au[j].v >> 1);
+		}
+	return 1;
+}
+
+static uint32_t tip_rounds(asg_t *g, int max_ext, int window, int excuse, uint32_t *n_cut)
+{
+	uint32_t n_vtx = g->n_seq * 2, lo = 0, rounds = 0, W = n_vtx, v, i;
+	u32v cells = {0,0,0}, chain = {0,0,0};
+	uint32_t *tag = (uint32_t*)malloc(4 * (size_t)(g->n_seq + 1)), *dtag = (uint32_t*)malloc(4 * (size_t)(g->n_seq + 1));
+	uint8_t *cand = (uint8_t*)calloc(n_vtx + 1, 1), *valid = (uint8_t*)calloc(n_vtx + 1, 1);
+	*n_cut = 0;
+	while (lo < n_vtx) {
+		uint32_t end = (!window || (uint64_t)lo + W >= n_vtx) ? n_vtx : lo + W, xs = 0xffffffffu, hi, n_cand = 0;
+		memset(tag, 0xff, 4 * (size_t)g->n_seq); memset(dtag, 0xff, 4 * (size_t)g->n_seq);
+		for (v = lo; v < end; ++v) {                                   /* k_spec_eval */
+			cand[v] = (uint8_t)tip_eval(g, v, max_ext, &cells, &chain);
+			if (!cand[v]) continue;
+			++n_cand;
+			for (i = 0; i < cells.n; ++i) if (v < tag[cells.a[i]]) tag[cells.a[i]] = v;
+			for (i = 0; i < chain.n; ++i) if (v < dtag[chain.a[i]]) dtag[chain.a[i]] = v;
+		}
+		if (n_cand == 0) { if (end == n_vtx) break; W = (uint64_t)W * 4 >= n_vtx ? n_vtx : W * 4; lo = end; continue; }
+		for (v = lo; v < end; ++v) {                                   /* k_spec_check: smallest stamp on what v reads (+ writes) */
+			uint32_t m = 0xffffffffu;
+			tip_eval(g, v, max_ext, &cells, &chain);
+			for (i = 0; i < cells.n; ++i) if (tag[cells.a[i]] < m) m = tag[cells.a[i]];
+			valid[v] = m >= v;
+		}
+		for (v = lo; v < end; ++v) {
+			uint32_t A;
+			if (valid[v]) continue;
+			A = dtag[v >> 1];
+			if (excuse && A < v && cand[A] && valid[A]) continue;       /* its read is about to be deleted: a no-op from then on */
+			if (v < xs) xs = v;
+		}
+		hi = xs >= end ? end : xs;
+		for (v = lo; v < hi; ++v)                                      /* k_spec_commit (valid candidates only) */
+			if (cand[v] && valid[v] && tip_eval(g, v, max_ext, &cells, &chain)) {
+				u32v del = {0,0,0};
+				for (i = 0; i < chain.n; ++i) vpush(&del, chain.a[i]);
+				for (i = 0; i < del.n; ++i) read_del(g, del.a[i]);
+				free(del.a);
+				++*n_cut;
+			}
+		if (window) {
+			if (hi >= end) W = (uint64_t)W * 4 >= n_vtx ? n_vtx : W * 4;
+			else { uint64_t w = 16ull * (hi - lo + 1); W = w < 4096 ? 4096 : (w < W ? (uint32_t)w : W); }
+		}
+		lo = hi;
+		++rounds;
+	}
+	free(cells.a); free(chain.a); free(tag); free(dtag); free(cand); free(valid);
+	return rounds;
+}
+
 int main(int argc, char *argv[])
 {
 	ma_opt_t opt;
@@ -180,6 +277,27 @@ int main(int argc, char *argv[])
 	n_hits = ma_hit_contained(&opt, d, sub, n_hits, hit);
 	g = ma_sg_gen(&opt, d, sub, n_hits, hit);
 	asg_arc_del_trans(g, opt.gap_fuzz);
+	{ /* tips, on the state main.c:161 sees them */
+		state_t before = snapshot(g), seq;
+		uint32_t v, n_vtx = g->n_seq * 2, n_seq_cut = 0, i, np, *path = (uint32_t*)malloc(4 * ((size_t)opt.max_ext + 2));
+		for (v = 0; v < n_vtx; ++v) { /* cut_generic(E_TIP, E_MERGE, negate) without the cleanup */
+			if (g->seq[v >> 1].del || utg_end(g, v, 0) != E_TIP) continue;
+			if (walk(g, v, opt.max_ext, path, &np) == E_MERGE) continue;
+			for (i = 0; i < np; ++i) read_del(g, path[i] >> 1);
+			++n_seq_cut;
+		}
+		free(path);
+		seq = snapshot(g);
+		printf("tips sequential: %u cut\n", n_seq_cut);
+		for (k = 0; k < 4; ++k) {
+			uint32_t n_cut, rounds;
+			restore(g, &before);
+			rounds = tip_rounds(g, opt.max_ext, k & 1, k >> 1, &n_cut);
+			printf("tips window=%d excuse=%d: rounds %u cut %u equal %d\n", k & 1, k >> 1, rounds, n_cut, same(g, &seq));
+		}
+		restore(g, &before);
+		free(before.seq_del); free(before.arc_del); free(seq.seq_del); free(seq.arc_del);
+	}
 	asg_cut_tip(g, opt.max_ext);
 	if (!g->is_symm) asg_symm(g);
 	{

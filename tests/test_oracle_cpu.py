@@ -81,3 +81,6 @@ def test_speculative_round_model_is_exact(built, paf_dir):
         plain = [int(r[3]) for r in rows if r[:3] == ("0", "0", "0")][0]
         excuse = [int(r[3]) for r in rows if r[:3] == ("1", "0", "1")][0]
         assert excuse <= plain and (pops < 50 or excuse * 3 < plain), out
+        tips = re.findall(r"tips window=(\d) excuse=(\d): rounds (\d+) cut (\d+) equal (\d)", out)     # same model for asg_cut_tip
+        n_tip = int(re.search(r"tips sequential: (\d+) cut", out).group(1))
+        assert len(tips) == 4 and all(t[4] == "1" and int(t[3]) == n_tip for t in tips), out
