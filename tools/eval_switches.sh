@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU call that evaluates every experimental switch: parity first, then A/B bench lines, then an
 # ncu capture of the two transitive-reduction kernels.  Usage (from the repo root, under gpurun):
-#   gpurun --timeout 1500 -- 'bash tools/eval_switches.sh'
+#   gpurun --timeout 1500 -- 'bash tools/eval_switches.sh'            (FULL=1 bash tools/... adds the whole GPU tier under the switches)
 # Results land in gpurun_out/sw_*.  Nothing printed by a run under ncu is a bench value.
 set -u
 cd "$(dirname "$0")/.."
@@ -25,6 +25,13 @@ except Exception as e:
     print(n, "FAILED", e)
 PY
 }
+if [ "${FULL:-0}" = "1" ]; then
+	# the whole GPU tier with every experimental kernel switched on (the library reads the variables in-process): what has to
+	# pass before a switch becomes the default.  ~3.5 min on one GPU.
+	echo "== full -m gpu suite with the experimental kernels on =="
+	MAB_SG_SEGSORT=1 MAB_DT_V7=1 MAB_BUB_EXCUSE=1 MAB_SPEC_WINDOW=1 MAB_GPU_GFA=1 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/sw_full_suite.log 2>&1
+	echo "rc=$?"; tail -4 gpurun_out/sw_full_suite.log
+fi
 echo "== bench A/B (1 M reads / 50 M lines) =="
 run_bench default
 run_bench segsort MAB_SG_SEGSORT=1
