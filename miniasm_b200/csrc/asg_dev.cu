@@ -333,173 +333,20 @@ constexpr uint32_t DT_EMPTY = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t dt_hash(uint32_t x, uint32_t mask) { return (x * 2654435761u) >> 7 & mask; }
 
-// Shared memory per warp: hkey (target vertex per slot) | tl (arc length per slab entry) | ti (idx word of the first
-// DT_EAGER targets; reused as "lowest slab position per slot" when a slab holds multi-arcs) | hmark (mark per slot:
-// 1 = target of v, 2 = reduced) | slot (table slot of slab entry i).  The mark lives in the table, so arcs to the same
-// target share it exactly like mark[] indexed by vertex does in the reference.
-template <bool STATS>
-__global__ void __launch_bounds__(DT_WARPS * 32, 6)
-k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, const uint32_t *__restrict__ seq,
-                 uint32_t n_vtx, uint32_t fuzz, uint8_t *__restrict__ flag,
-                 uint32_t *__restrict__ big_list, unsigned long long *scal, const uint32_t *__restrict__ list, uint32_t own_lo, uint32_t own_hi,
-                 SlabView sv)
-{	// list == nullptr: every vertex 0..n_vtx-1; otherwise the n_vtx vertices named by list[]
-	// [own_lo, own_hi): arc positions this rank is responsible for (sharded runs); a vertex is processed iff its slab starts there
-	__shared__ __align__(16) uint32_t s_hkey[DT_WARPS][DT_HASH];
-	__shared__ uint32_t s_tl[DT_WARPS][DT_MAXD];
-	__shared__ uint32_t s_fmin[DT_WARPS][DT_HASH];
-	__shared__ uint64_t s_ti[DT_WARPS][DT_EAGER];
-	__shared__ uint8_t  s_hmark[DT_WARPS][DT_HASH];
-	__shared__ uint8_t  s_slot[DT_WARPS][DT_MAXD];
-
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	uint32_t *hkey = s_hkey[warp], *tl = s_tl[warp], *fmin = s_fmin[warp];
-	uint64_t *ti = s_ti[warp];
-	uint8_t *hmark = s_hmark[warp], *slot = s_slot[warp];
-	unsigned n_red = 0;
-	unsigned long long n_inner = 0;
-
-	for (uint32_t vi = blockIdx.x * DT_WARPS + warp; vi < n_vtx; vi += gridDim.x * DT_WARPS) {
-		const uint32_t v = list ? list[vi] : vi;
-		const uint64_t iv = __ldg(idx + v);
-		const uint32_t nv = (uint32_t)iv, off = (uint32_t)(iv >> 32);
-		if (nv == 0 || off < own_lo || off >= own_hi) continue;
-		if (__ldg(seq + (v >> 1)) & MAB_DEL_BIT) { // deleted read: every arc goes (asg.c:158-161)
-			for (uint32_t i = lane; i < nv; i += 32) flag[off + i] = 1;
-			if (lane == 0) n_red += nv;
-			continue;
-		}
-		if (nv > DT_MAXD) { // hand over to the CTA kernel
-			if (lane == 0) big_list[atomicAdd(scal + SC_BIG, 1ull)] = v;
-			continue;
-		}
-		const uint32_t mask = nv <= 16 ? 31u : (0xffffffffu >> __clz(2 * nv - 1)); // table = next power of two >= 2*nv, at least 32 slots
-		if (mask == 31) hkey[lane] = DT_EMPTY;
-		else for (uint32_t i = lane * 4; i <= mask; i += 128) *reinterpret_cast<uint4*>(hkey + i) = make_uint4(DT_EMPTY, DT_EMPTY, DT_EMPTY, DT_EMPTY);
-		__syncwarp();
-		// stage the slab and build the target table in one sweep; every lane carries two slab entries per
-		// iteration (i and i+32), so slabs of up to 64 arcs -- nearly all of them -- take a single iteration
-		bool dup = false;
-		for (uint32_t base = 0; base < nv; base += 64) {
-			const uint32_t i0 = base + lane, i1 = i0 + 32;
-			const bool v0 = i0 < nv, v1 = i1 < nv;
-			uint4 a0, a1;
-			if (v0) a0 = ld_arc4(arc + off + i0);       // x = len, z = target
-			if (v1) a1 = ld_arc4(arc + off + i1);
-			if (v0) {
-				tl[i0] = a0.x;
-				if (i0 < DT_EAGER) ti[i0] = __ldg((sv.peer ? sv.nidx : idx) + a0.z);
-				uint32_t h = dt_hash(a0.z, mask);
-				for (;;) {
-					const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a0.z);
-					if (prev == DT_EMPTY) { hmark[h] = 1; break; }
-					if (prev == a0.z) { dup = true; break; }
-					h = (h + 1) & mask;
-				}
-				slot[i0] = (uint8_t)h;
-			}
-			if (v1) {
-				tl[i1] = a1.x;
-				uint32_t h = dt_hash(a1.z, mask);
-				for (;;) {
-					const uint32_t prev = atomicCAS(&hkey[h], DT_EMPTY, a1.z);
-					if (prev == DT_EMPTY) { hmark[h] = 1; break; }
-					if (prev == a1.z) { dup = true; break; }
-					h = (h + 1) & mask;
-				}
-				slot[i1] = (uint8_t)h;
-			}
-		}
-		const bool has_dup = __any_sync(0xffffffffu, dup); // multi-arcs: several slab entries share one mark
-		__syncwarp();
-		const uint32_t L = tl[nv - 1] + fuzz;
-		// i ascends over the slab entries whose target still carries mark 1 (asg.c:164-168); found by ballot
-		for (uint32_t i = 0;;) {
-			uint32_t nxt = nv;
-			for (uint32_t base = i & ~63u; base < nv; base += 64) {
-				const uint32_t k0 = base + lane, k1 = k0 + 32;
-				const bool l0 = k0 >= i && k0 < nv && hmark[slot[k0]] == 1;
-				const bool l1 = k1 >= i && k1 < nv && hmark[slot[k1]] == 1;
-				const unsigned m0 = __ballot_sync(0xffffffffu, l0), m1 = __ballot_sync(0xffffffffu, l1);
-				if (m0) { nxt = base + __ffs(m0) - 1; break; }
-				if (m1) { nxt = base + 32 + __ffs(m1) - 1; break; }
-			}
-			if (nxt >= nv) break;
-			i = nxt;
-			const uint32_t w = hkey[slot[i]], li = tl[i];
-			const uint64_t iw = i < DT_EAGER ? ti[i] : __ldg((sv.peer ? sv.nidx : idx) + w);
-			const uint32_t nw = (uint32_t)iw;
-			const DArc *pw = slab_base(sv, arc, w) + (iw >> 32) + lane;
-			for (uint32_t j0 = 0; j0 < nw; j0 += 64, pw += 64) {
-				const bool in0 = j0 + lane < nw, in1 = j0 + 32 + lane < nw;
-				uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
-				if (in0) a0 = ld_arc4(pw);
-				if (in1) a1 = ld_arc4(pw + 32);
-				const bool ok0 = in0 && a0.x + li <= L, ok1 = in1 && a1.x + li <= L;
-				const unsigned m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
-				// the scan of the reference stops at the first j that violates the bound: entries before it, in slab order
-				const unsigned pre0 = m0 == 0xffffffffu ? m0 : ((1u << (__ffs(~m0) - 1)) - 1);
-				const unsigned pre1 = m0 != 0xffffffffu ? 0u : (m1 == 0xffffffffu ? m1 : ((1u << (__ffs(~m1) - 1)) - 1));
-				if (pre0 >> lane & 1) {
-					uint32_t h = dt_hash(a0.z, mask);
-					for (;;) {
-						const uint32_t kx = hkey[h];
-						if (kx == a0.z) { hmark[h] = 2; break; }
-						if (kx == DT_EMPTY) break;
-						h = (h + 1) & mask;
-					}
-				}
-				if (pre1 >> lane & 1) {
-					uint32_t h = dt_hash(a1.z, mask);
-					for (;;) {
-						const uint32_t kx = hkey[h];
-						if (kx == a1.z) { hmark[h] = 2; break; }
-						if (kx == DT_EMPTY) break;
-						h = (h + 1) & mask;
-					}
-				}
-				if (STATS && lane == 0) n_inner += __popc(pre0) + __popc(pre1);
-				if (m0 != 0xffffffffu || m1 != 0xffffffffu) break;
-			}
-			__syncwarp();
-			++i;
-		}
-		// The reference clears mark[target] right after looking at the first arc to that target
-		// (asg.c:181-184), so of several arcs to one reduced target only the lowest-index one is deleted.
-		if (has_dup) {
-			for (uint32_t i = lane; i <= mask; i += 32) fmin[i] = DT_EMPTY;
-			__syncwarp();
-			for (uint32_t i = lane; i < nv; i += 32) atomicMin(&fmin[slot[i]], i);
-			__syncwarp();
-		}
-		for (uint32_t i = lane; i < nv; i += 32) {
-			const bool r = hmark[slot[i]] == 2 && (!has_dup || fmin[slot[i]] == i);
-			flag[off + i] = r;
-			n_red += r;
-		}
-		__syncwarp();
-	}
-	n_red = __reduce_add_sync(0xffffffffu, n_red);
-	if (lane == 0) {
-		if (n_red) atomicAdd(scal + SC_COUNT, (unsigned long long)n_red);
-		if (STATS && n_inner) atomicAdd(scal + SC_AUX, n_inner);
-	}
-}
-
 // ---------------------------------------------------------------------------------------------
-// k_del_trans_warp7 -- same algorithm and shared-memory layout as k_del_trans_warp, fewer issue slots per vertex
-// (experimental, MAB_DT_V7=1; the kernel above stays the default until this one has been through the GPU test tier).
-// The ncu source page of the default kernel (profiles/r01_del_trans.md) shows ~476 warp instructions per vertex, nearly
-// all executed exactly once per vertex, i.e. per-vertex bookkeeping: this variant removes the run-time peer/no-peer
-// selection (template parameter), clears the table with one or two 128-bit stores instead of a general unrolled loop,
-// keeps every slab loop rolled (two entries per lane cover 64 arcs; unrolled copies were dead weight in the
-// instruction stream), prefetches the next vertex's index/seq words, the two loads every iteration stalls on first, and
-// (SORTED, i.e. whenever the graph says is_srt) uses that a slab is sorted by length: the arcs that satisfy the length
-// bound are then a prefix by themselves and the first-violation masks of the general case drop out.
+// k_del_trans_warp -- one warp per vertex.  Shared memory per warp: hkey (target vertex per table slot) | tl (arc length
+// per slab entry) | hmark (mark per slot: 1 = target of v, 2 = reduced) | slot (table slot of slab entry i) | fmin
+// (lowest slab position per slot, only when a slab holds multi-arcs).  The mark lives in the table, so arcs to the same
+// target share it exactly like mark[] indexed by vertex does in the reference.
+// The kernel is issue-bound (profiles/r01_del_trans.md: the round-1 version spent ~476 warp instructions per vertex,
+// nearly all of them per-vertex bookkeeping), so this version keeps the instruction stream short: peer/no-peer is a
+// template parameter, the table is cleared with one or two 128-bit stores, every slab loop stays rolled (two entries per
+// lane cover 64 arcs), the next vertex's index/seq words are prefetched, and (SORTED, i.e. whenever the graph says
+// is_srt) a slab sorted by length makes the arcs that satisfy the length bound a prefix by themselves.
 // ---------------------------------------------------------------------------------------------
 template <bool STATS, bool P2P, bool SORTED>
 __global__ void __launch_bounds__(DT_WARPS * 32, 6)
-k_del_trans_warp7(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, const uint32_t *__restrict__ seq,
+k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx, const uint32_t *__restrict__ seq,
                  uint32_t n_vtx, uint32_t fuzz, uint8_t *__restrict__ flag,
                  uint32_t *__restrict__ big_list, unsigned long long *scal, uint32_t own_lo, uint32_t own_hi, SlabView sv)
 {	// [own_lo, own_hi): arc positions this rank is responsible for (sharded runs); a vertex is processed iff its slab starts there
@@ -857,16 +704,13 @@ uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo
 		unsigned grid = (n_vtx + DT_WARPS - 1) / DT_WARPS;
 		if (grid > 148u * 64u) grid = 148u * 64u;
 		// the inner-iteration counter (for the roofline arithmetic) costs issue slots: only counted when asked for
-		static const bool v7 = getenv("MAB_DT_V7") && atoi(getenv("MAB_DT_V7")) != 0;
-		if (v7) {
+		{
 			const bool st = mab_del_trans_count_inner != 0, p2p = peer != nullptr, srt = g.is_srt;
-			#define DT7(S, P, O) MAB_LAUNCH(d, (k_del_trans_warp7<S, P, O>), grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, own_lo, own_hi, sv)
-			if (st) { if (p2p) { if (srt) DT7(true, true, true); else DT7(true, true, false); } else { if (srt) DT7(true, false, true); else DT7(true, false, false); } }
-			else { if (p2p) { if (srt) DT7(false, true, true); else DT7(false, true, false); } else { if (srt) DT7(false, false, true); else DT7(false, false, false); } }
-			#undef DT7
-		} else
-		if (mab_del_trans_count_inner) MAB_LAUNCH(d, k_del_trans_warp<true>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr, own_lo, own_hi, sv);
-		else MAB_LAUNCH(d, k_del_trans_warp<false>, grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, (const uint32_t*)nullptr, own_lo, own_hi, sv);
+			#define DT(S, P, O) MAB_LAUNCH(d, (k_del_trans_warp<S, P, O>), grid, DT_WARPS * 32, 0, g.arc, g.idx, g.seq, n_vtx, fuzz, flag, big, d.d_scal, own_lo, own_hi, sv)
+			if (st) { if (p2p) { if (srt) DT(true, true, true); else DT(true, true, false); } else { if (srt) DT(true, false, true); else DT(true, false, false); } }
+			else { if (p2p) { if (srt) DT(false, true, true); else DT(false, true, false); } else { if (srt) DT(false, false, true); else DT(false, false, false); } }
+			#undef DT
+		}
 		MAB_CUDA(cudaEventRecord(e1, d.stream));
 		uint32_t n_big = (uint32_t)d.get_scal(SC_BIG);
 		float ms = 0;

@@ -1,339 +1,122 @@
-// clean_dev.cu -- the order-dependent graph-cleaning passes of stage (iii) on the GPU, bit-exact with the
-// reference's ascending-vertex sequential loops:
-//   asg_cut_tip asg.c:238-254 | asg_cut_internal asg.c:256-272 | asg_cut_biloop asg.c:274-306 |
-//   asg_pop_bubble asg.c:412-433 (asg_bub_pop1 asg.c:360-409, asg_bub_backtrack asg.c:338-357)
+// clean_dev.cu -- stage (iii) on the GPU: the order-dependent graph-cleaning passes (asg.c:238-306, 312-433), bit-exact
+// with the reference's ascending-vertex sequential loops, and unitig construction (asm.c:121-210).
 //
-// Why this is not a plain parallel-for: iteration v reads deletion bits that iterations u < v may have
-// written (asg_seq_del, asg.h:64-77), and the survey's probe shows a decide-on-snapshot variant changes
-// the GFA.  The passes therefore run as SPECULATIVE PREFIX-COMMIT ROUNDS (DESIGN.md "sequential passes"):
-//
-//   state: everything below `lo` is final.  One round:
-//   K1  every v >= lo evaluates its decision on the current state (read only).  A vertex that would act
-//       (a "candidate") stamps every cell it reads or would write with atomicMin(tag[cell], v);
-//       a cell is one read: its seq.del bit plus the del bits of both of its out-slabs.
-//   K2  every v >= lo (candidate or not) walks its read set again (candidates: plus write set) and takes
-//       the smallest stamp; if it is < v, an earlier candidate touches what v depends on, so v may change
-//       once that candidate commits: v is "invalid".  x* = min invalid v (or infinity).
-//   K3  candidates in [lo, x*) re-evaluate and apply their action.  They are pairwise cell-disjoint (every
-//       candidate stamps all of its cells, so of two candidates sharing a cell the later one is invalid),
-//       hence order-free, and nothing earlier can change them: exactly what the sequential loop does
-//       for v < x*.  Non-candidates below x* are final no-ops.  lo = x*; repeat until no candidate is left.
-//
-// The smallest candidate is never invalid, so every round commits at least one action; on real graphs
-// candidates are sparse and local and a handful of rounds finish a pass.
+// The cleaning passes are the Jacobi iteration of clean_fix.cuh's timestamp fixed point: per sweep ONE kernel in which
+// every vertex decides under T_old and stamps T_new with atomicMin, ONE kernel that compares the two and re-arms the
+// old buffer, and one 8-byte read-back.  The sweep count is the length of the longest dependency chain of the pass
+// (2-3 for bubbles, up to a few dozen for tips on the parity sets), not the number of actions.
 #include "clean_dev.cuh"
+#include "clean_fix.cuh"
 #include <cub/cub.cuh>
 
 CleanStats g_clean_stats;
 
-#define ET_MERGEABLE 0
-#define ET_TIP       1
-#define ET_MULTI_OUT 2
-#define ET_MULTI_NEI 3
-
-constexpr uint32_t NO_TAG = 0xffffffffu;
-
-struct GV { // device view of the graph
+struct GV { // device view of the graph (unitig construction)
 	DArc *arc;
 	const uint64_t *idx;
 	uint32_t *seq;
 	uint32_t n_vtx;
 };
 
-// visitors over cells
-struct VisNone { __device__ __forceinline__ void operator()(uint32_t) const {} };
-struct VisTag {
-	uint32_t *tag, v;
-	__device__ __forceinline__ void operator()(uint32_t cell) const { atomicMin(&tag[cell], v); }
-};
-struct VisMin {
-	const uint32_t *tag; uint32_t m;
-	__device__ __forceinline__ void operator()(uint32_t cell) { uint32_t t = tag[cell]; m = t < m ? t : m; }
-};
-
-// asg_is_utg_end (asg.c:204-222): looks at the live out-arcs of v^1 and of the single neighbour
-template <class Vis>
-__device__ __forceinline__ int is_utg_end(const GV &g, uint32_t v, uint64_t *lw, Vis &vis)
-{
-	const uint64_t iv = g.idx[v ^ 1];
-	const uint32_t nv0 = (uint32_t)iv;
-	const DArc *av = g.arc + (iv >> 32);
-	uint32_t nv = 0, i0 = 0;
-	vis(v >> 1);
-	for (uint32_t i = 0; i < nv0; ++i)
-		if (!(av[i].ol_del & MAB_DEL_BIT)) i0 = i, ++nv;
-	if (nv == 0) return ET_TIP;
-	if (nv > 1) return ET_MULTI_OUT;
-	if (lw) *lw = av[i0].ul << 32 | av[i0].v;
-	const uint32_t w = av[i0].v ^ 1;
-	const uint64_t iw = g.idx[w];
-	const uint32_t nw0 = (uint32_t)iw;
-	const DArc *aw = g.arc + (iw >> 32);
-	uint32_t nw = 0;
-	vis(w >> 1);
-	for (uint32_t i = 0; i < nw0; ++i)
-		if (!(aw[i].ol_del & MAB_DEL_BIT)) ++nw;
-	return nw != 1 ? ET_MULTI_NEI : ET_MERGEABLE;
-}
-
-// asg_extend (asg.c:224-236) without materialising the path: returns the end type, the last vertex pushed
-// and the number of entries pushed (entry 0 is v itself).  `visit_chain(vertex)` sees every pushed vertex.
-template <class Vis, class ChainFn>
-__device__ __forceinline__ int extend(const GV &g, uint32_t v, int max_ext, Vis &vis, ChainFn chain, uint32_t *last)
-{
-	int ret;
-	uint64_t lw = 0;
-	chain(v);
-	*last = v;
-	do {
-		ret = is_utg_end(g, v ^ 1, &lw, vis);
-		if (ret != 0) break;
-		v = (uint32_t)lw;
-		chain(v);
-		*last = v;
-	} while (--max_ext > 0);
-	return ret;
-}
-
-// cells written by asg_seq_del(read s) (asg.h:64-77): s itself and every read one of its arcs points to
-template <class Vis>
-__device__ __forceinline__ void seq_del_cells(const GV &g, uint32_t s, Vis &vis)
-{
-	vis(s);
-	for (uint32_t k = 0; k < 2; ++k) {
-		const uint64_t iv = g.idx[s << 1 | k];
-		const DArc *av = g.arc + (iv >> 32);
-		for (uint32_t i = 0; i < (uint32_t)iv; ++i) vis(av[i].v >> 1);
-	}
-}
-
-__device__ __forceinline__ void arc_del(const GV &g, uint32_t v, uint32_t w, bool del) // asg_arc_del, asg.h:55-61
-{
-	const uint64_t iv = g.idx[v];
-	DArc *av = g.arc + (iv >> 32);
-	for (uint32_t i = 0; i < (uint32_t)iv; ++i)
-		if (av[i].v == w) av[i].ol_del = del ? (av[i].ol_del | MAB_DEL_BIT) : (av[i].ol_del & ~MAB_DEL_BIT);
-}
-
-__device__ __forceinline__ void seq_del(const GV &g, uint32_t s) // asg_seq_del, asg.h:64-77
-{
-	g.seq[s] |= MAB_DEL_BIT;
-	for (uint32_t k = 0; k < 2; ++k) {
-		const uint32_t v = s << 1 | k;
-		const uint64_t iv = g.idx[v];
-		DArc *av = g.arc + (iv >> 32);
-		for (uint32_t i = 0; i < (uint32_t)iv; ++i) {
-			av[i].ol_del |= MAB_DEL_BIT;
-			arc_del(g, av[i].v ^ 1, v ^ 1, true);
-		}
-	}
-}
-
 // ---------------------------------------------------------------------------------------------
-// The three short-unitig cutters share one skeleton; `Rule` supplies decision, cells and action.
-//   eval<Vis>(g, v, vis)   -> true if v acts on the current state; vis sees every cell read
-//   cells<Vis>(g, v, vis)  -> for an acting v: every cell its action writes
-//   apply(g, v)            -> perform the action
+// sweep machinery shared by the four passes
 // ---------------------------------------------------------------------------------------------
-struct TipRule { // asg_cut_tip
-	int max_ext;
-	template <class Vis> __device__ bool eval(const GV &g, uint32_t v, Vis &vis) const
-	{
-		if (g.seq[v >> 1] & MAB_DEL_BIT) { vis(v >> 1); return false; }
-		if (is_utg_end(g, v, nullptr, vis) != ET_TIP) return false;
-		uint32_t last;
-		return extend(g, v, max_ext, vis, [](uint32_t) {}, &last) != ET_MERGEABLE;
-	}
-	template <class Vis> __device__ void cells(const GV &g, uint32_t v, Vis &vis) const
-	{
-		VisNone none;
-		uint32_t last;
-		extend(g, v, max_ext, none, [&](uint32_t x) { seq_del_cells(g, x >> 1, vis); }, &last);
-	}
-	__device__ void apply(const GV &g, uint32_t v) const
-	{ // the chain is fixed by the (stable) state before any deletion: collect first, delete after, like the reference
-		uint32_t chain[64], n = 0, last;
-		VisNone none;
-		extend(g, v, max_ext < 63 ? max_ext : 63, none, [&](uint32_t x) { if (n < 64) chain[n++] = x; }, &last);
-		for (uint32_t i = 0; i < n; ++i) seq_del(g, chain[i] >> 1);
-	}
+struct FxBuf {
+	uint32_t *ts[2], *ta[2];
+	uint32_t n_seq, n_arc;
+	int cur;
 };
 
-struct InternalRule { // asg_cut_internal
-	int max_ext;
-	template <class Vis> __device__ bool eval(const GV &g, uint32_t v, Vis &vis) const
-	{
-		if (g.seq[v >> 1] & MAB_DEL_BIT) { vis(v >> 1); return false; }
-		if (is_utg_end(g, v, nullptr, vis) != ET_MULTI_NEI) return false;
-		uint32_t last;
-		return extend(g, v, max_ext, vis, [](uint32_t) {}, &last) == ET_MULTI_NEI;
+__global__ void k_fx_init(const DArc *arc, const uint32_t *seq, uint32_t n_arc, uint32_t n_seq, uint32_t *ts0, uint32_t *ts1, uint32_t *ta0, uint32_t *ta1)
+{
+	const uint32_t n = n_arc + n_seq;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (i < n_arc) ta0[i] = ta1[i] = arc[i].ol_del & MAB_DEL_BIT ? 0u : FX_LIVE;
+		else { const uint32_t s = i - n_arc; ts0[s] = ts1[s] = seq[s] & MAB_DEL_BIT ? 0u : FX_LIVE; }
 	}
-	template <class Vis> __device__ void cells(const GV &g, uint32_t v, Vis &vis) const
-	{
-		VisNone none;
-		uint32_t last;
-		extend(g, v, max_ext, none, [&](uint32_t x) { seq_del_cells(g, x >> 1, vis); }, &last);
-	}
-	__device__ void apply(const GV &g, uint32_t v) const
-	{
-		uint32_t chain[64], n = 0, last;
-		VisNone none;
-		extend(g, v, max_ext < 63 ? max_ext : 63, none, [&](uint32_t x) { if (n < 64) chain[n++] = x; }, &last);
-		for (uint32_t i = 0; i < n; ++i) seq_del(g, chain[i] >> 1);
-	}
-};
-
-struct BiloopRule { // asg_cut_biloop: v->...->x', w->v and w->x; drop w->x (and its complement) if it is the weaker one
-	int max_ext;
-	template <class Vis> __device__ bool find(const GV &g, uint32_t v, Vis &vis, uint32_t *w_out, uint32_t *x_out) const
-	{
-		if (g.seq[v >> 1] & MAB_DEL_BIT) { vis(v >> 1); return false; }
-		if (is_utg_end(g, v, nullptr, vis) != ET_MULTI_NEI) return false;
-		uint32_t last;
-		if (extend(g, v, max_ext, vis, [](uint32_t) {}, &last) != ET_MULTI_OUT) return false;
-		const uint32_t x = last ^ 1;
-		uint32_t w = 0xffffffffu, ov = 0, ox = 0;
-		{
-			const uint64_t iv = g.idx[v ^ 1];
-			const DArc *av = g.arc + (iv >> 32);
-			for (uint32_t i = 0; i < (uint32_t)iv; ++i)
-				if (!(av[i].ol_del & MAB_DEL_BIT)) w = av[i].v ^ 1;
-		}
-		if (w == 0xffffffffu) return false; // cannot happen: MULTI_NEI means exactly one live arc (asg.c:288 asserts it)
-		vis(w >> 1);
-		const uint64_t iw = g.idx[w];
-		const DArc *aw = g.arc + (iw >> 32);
-		for (uint32_t i = 0; i < (uint32_t)iw; ++i) {
-			if (aw[i].ol_del & MAB_DEL_BIT) continue;
-			if (aw[i].v == x) ox = aw[i].ol_del & ~MAB_DEL_BIT;
-			if (aw[i].v == v) ov = aw[i].ol_del & ~MAB_DEL_BIT;
-		}
-		if (ov == 0 && ox == 0) return false;
-		*w_out = w, *x_out = x;
-		return ov > ox;
-	}
-	template <class Vis> __device__ bool eval(const GV &g, uint32_t v, Vis &vis) const
-	{
-		uint32_t w, x;
-		return find(g, v, vis, &w, &x);
-	}
-	template <class Vis> __device__ void cells(const GV &g, uint32_t v, Vis &vis) const
-	{
-		VisNone none;
-		uint32_t w, x;
-		if (find(g, v, none, &w, &x)) vis(w >> 1), vis(x >> 1);
-	}
-	__device__ void apply(const GV &g, uint32_t v) const
-	{
-		VisNone none;
-		uint32_t w, x;
-		if (find(g, v, none, &w, &x)) arc_del(g, w, x, true), arc_del(g, x ^ 1, w ^ 1, true);
-	}
-};
+}
 
 template <class Rule>
-__global__ void k_spec_eval(GV g, Rule rule, uint32_t lo, uint8_t *cand, uint32_t *tag, unsigned long long *n_cand)
+__global__ void k_fx_sweep(FxView g, Rule rule, unsigned long long *n_act)
 {
 	unsigned cnt = 0;
-	for (uint32_t v = lo + blockIdx.x * blockDim.x + threadIdx.x; v < g.n_vtx; v += gridDim.x * blockDim.x) {
-		VisNone none;
-		bool act = rule.eval(g, v, none);
-		cand[v] = act;
-		if (act) {
-			VisTag t{tag, v};
-			rule.eval(g, v, t);
-			rule.cells(g, v, t);
-			++cnt;
-		}
-	}
+	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < g.n_vtx; v += gridDim.x * blockDim.x)
+		cnt += rule.act(g, v);
 	cnt = __reduce_add_sync(0xffffffffu, cnt);
-	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_cand, (unsigned long long)cnt);
+	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_act, (unsigned long long)cnt);
+}
+
+// changed |= T_old != T_new; T_old <- init (it is the T_new of the next sweep)
+__global__ void k_fx_diff_rearm(const DArc *arc, const uint32_t *seq, uint32_t n_arc, uint32_t n_seq, uint32_t *ts_old, const uint32_t *ts_new,
+                                uint32_t *ta_old, const uint32_t *ta_new, unsigned long long *changed)
+{
+	const uint32_t n = n_arc + n_seq;
+	bool diff = false;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (i < n_arc) { diff |= ta_old[i] != ta_new[i]; ta_old[i] = arc[i].ol_del & MAB_DEL_BIT ? 0u : FX_LIVE; }
+		else { const uint32_t s = i - n_arc; diff |= ts_old[s] != ts_new[s]; ts_old[s] = seq[s] & MAB_DEL_BIT ? 0u : FX_LIVE; }
+	}
+	if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) atomicOr(changed, 1ull);
+}
+
+__global__ void k_fx_finish(DArc *arc, uint32_t *seq, uint32_t n_arc, uint32_t n_seq, const uint32_t *ts, const uint32_t *ta)
+{
+	const uint32_t n = n_arc + n_seq;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if (i < n_arc) { if (ta[i] != FX_LIVE) arc[i].ol_del |= MAB_DEL_BIT; }
+		else { const uint32_t s = i - n_arc; if (ts[s] != FX_LIVE) seq[s] |= MAB_DEL_BIT; }
+	}
+}
+
+static void fx_alloc(MabDev &d, const DGraph &g, FxBuf &b)
+{
+	b.n_seq = g.n_seq, b.n_arc = g.n_arc, b.cur = 0;
+	for (int k = 0; k < 2; ++k) b.ts[k] = mab_alloc<uint32_t>(d, g.n_seq), b.ta[k] = mab_alloc<uint32_t>(d, g.n_arc);
+	MAB_LAUNCH(d, k_fx_init, mab_grid((size_t)g.n_arc + g.n_seq, 256), 256, 0, g.arc, g.seq, g.n_arc, g.n_seq, b.ts[0], b.ts[1], b.ta[0], b.ta[1]);
+}
+static FxView fx_view(const DGraph &g, const FxBuf &b)
+{
+	return FxView{g.arc, g.idx, b.ts[b.cur], b.ta[b.cur], b.ts[b.cur ^ 1], b.ta[b.cur ^ 1], g.n_seq * 2};
+}
+// end of a sweep: true if it changed nothing (then buffer `cur` holds the fixed point)
+static bool fx_next(MabDev &d, const DGraph &g, FxBuf &b)
+{
+	d.zero_scal(SC_AUX2);
+	MAB_LAUNCH(d, k_fx_diff_rearm, mab_grid((size_t)g.n_arc + g.n_seq, 256), 256, 0, g.arc, g.seq, g.n_arc, g.n_seq,
+	           b.ts[b.cur], b.ts[b.cur ^ 1], b.ta[b.cur], b.ta[b.cur ^ 1], d.d_scal + SC_AUX2);
+	b.cur ^= 1;
+	return d.get_scal(SC_AUX2) == 0;
+}
+static void fx_finish(MabDev &d, DGraph &g, FxBuf &b)
+{
+	MAB_LAUNCH(d, k_fx_finish, mab_grid((size_t)g.n_arc + g.n_seq, 256), 256, 0, g.arc, g.seq, g.n_arc, g.n_seq, b.ts[b.cur], b.ta[b.cur]);
+	for (int k = 0; k < 2; ++k) d.free(b.ts[k]), d.free(b.ta[k]);
 }
 
 template <class Rule>
-__global__ void k_spec_check(GV g, Rule rule, uint32_t lo, const uint8_t *cand, const uint32_t *tag, unsigned long long *xstar)
+static uint32_t run_fixpoint(MabDev &d, DGraph &g, Rule rule)
 {
-	uint32_t bad = NO_TAG;
-	for (uint32_t v = lo + blockIdx.x * blockDim.x + threadIdx.x; v < g.n_vtx; v += gridDim.x * blockDim.x) {
-		VisMin m{tag, NO_TAG};
-		rule.eval(g, v, m);
-		if (cand[v]) rule.cells(g, v, m);
-		if (m.m < v && v < bad) bad = v;
+	g_clean_stats.rounds = 0, g_clean_stats.committed = 0;
+	if (g.n_seq == 0 || g.n_arc == 0) return 0;
+	FxBuf b;
+	fx_alloc(d, g, b);
+	uint32_t sweeps = 0, cnt;
+	for (;;) {
+		d.zero_scal(SC_COUNT);
+		MAB_LAUNCH(d, k_fx_sweep<Rule>, mab_grid((size_t)g.n_seq * 2, 128), 128, 0, fx_view(g, b), rule, d.d_scal + SC_COUNT);
+		++sweeps;
+		const bool fixed = fx_next(d, g, b);
+		cnt = (uint32_t)d.h_scal[SC_COUNT];
+		if (fixed) break;       // the sweep ran on the fixed point itself: its count is the reference's
 	}
-	bad = __reduce_min_sync(0xffffffffu, bad);
-	if ((threadIdx.x & 31) == 0 && bad != NO_TAG) atomicMin(xstar, (unsigned long long)bad);
-}
-
-template <class Rule>
-__global__ void k_spec_commit(GV g, Rule rule, uint32_t lo, uint32_t hi, const uint8_t *cand, unsigned long long *n_done)
-{
-	unsigned cnt = 0;
-	for (uint32_t v = lo + blockIdx.x * blockDim.x + threadIdx.x; v < hi; v += gridDim.x * blockDim.x)
-		if (cand[v]) { rule.apply(g, v); ++cnt; }
-	cnt = __reduce_add_sync(0xffffffffu, cnt);
-	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_done, (unsigned long long)cnt);
-}
-
-// Windowed rounds (experimental, MAB_SPEC_WINDOW=1): a round only looks at the vertices [lo, lo + W).  Vertices beyond
-// the window neither stamp nor commit in that round, and a stamp only ever invalidates LARGER vertices, so the prefix
-// that commits is still exactly the sequential outcome; what changes is the cost of a round, O(W) instead of
-// O(n_vtx - lo).  W shrinks towards the distance the last round advanced and grows back when a whole window commits:
-// dense conflict chains (bubbles along a contig with sorted ids advance a few vertices per round) stop paying for
-// a full-graph evaluation each time.  The kernels are unchanged: they loop to GV::n_vtx, which is set to the window end.
-struct SpecWindow {
-	bool on; uint32_t n_vtx, W;
-	explicit SpecWindow(uint32_t n) : n_vtx(n), W(n) { const char *e = getenv("MAB_SPEC_WINDOW"); on = e && atoi(e) != 0; }
-	uint32_t end(uint32_t lo) const { return !on || (uint64_t)lo + W >= n_vtx ? n_vtx : lo + W; }
-	void advanced(uint32_t lo, uint32_t hi, uint32_t end) {
-		if (!on) return;
-		if (hi >= end) W = (uint64_t)W * 4 >= n_vtx ? n_vtx : W * 4;                 // the whole window went through
-		else { const uint64_t w = 16ull * (hi - lo + 1); W = w < 4096 ? 4096 : (w < W ? (uint32_t)w : W); }
-	}
-};
-
-template <class Rule>
-static uint32_t run_spec_rounds(MabDev &d, DGraph &g, Rule rule)
-{
-	const uint32_t n_vtx = g.n_seq * 2;
-	uint32_t lo = 0, total = 0, rounds = 0;
-	if (n_vtx == 0 || g.n_arc == 0) { g_clean_stats.rounds = 0, g_clean_stats.committed = 0; return 0; }
-	GV gv{g.arc, g.idx, g.seq, n_vtx};
-	uint8_t *cand = mab_alloc<uint8_t>(d, n_vtx);
-	uint32_t *tag = mab_alloc<uint32_t>(d, g.n_seq);
-	MAB_CUDA(cudaMemsetAsync(tag, 0xff, (size_t)g.n_seq * 4, d.stream));
-	SpecWindow win(n_vtx);
-	while (lo < n_vtx) {
-		const uint32_t end = win.end(lo);
-		GV gw = gv;
-		gw.n_vtx = end;                                              // the eval / check kernels stop at the window end
-		const unsigned grid = mab_grid(end - lo, 128);
-		d.zero_scal(SC_COUNT, 2);
-		MAB_CUDA(cudaMemsetAsync(d.d_scal + SC_MIN, 0xff, 8, d.stream));
-		MAB_LAUNCH(d, k_spec_eval<Rule>, grid, 128, 0, gw, rule, lo, cand, tag, d.d_scal + SC_COUNT);
-		if (d.get_scal(SC_COUNT) == 0) {                             // nobody in [lo, end) would act (and nobody stamped)
-			if (end == n_vtx) break;
-			win.advanced(lo, end, end);
-			lo = end;
-			continue;
-		}
-		MAB_LAUNCH(d, k_spec_check<Rule>, grid, 128, 0, gw, rule, lo, cand, tag, d.d_scal + SC_MIN);
-		unsigned long long xs = d.get_scal(SC_MIN);
-		uint32_t hi = xs >= end ? end : (uint32_t)xs;
-		MAB_LAUNCH(d, k_spec_commit<Rule>, mab_grid(hi - lo, 128), 128, 0, gv, rule, lo, hi, cand, d.d_scal + SC_NSEL);
-		MAB_CUDA(cudaMemsetAsync(tag, 0xff, (size_t)g.n_seq * 4, d.stream));
-		total += (uint32_t)d.get_scal(SC_NSEL);
-		win.advanced(lo, hi, end);
-		lo = hi;
-		++rounds;
-	}
-	d.free(cand); d.free(tag);
-	g_clean_stats.rounds = rounds, g_clean_stats.committed = total;
-	return total;
+	fx_finish(d, g, b);
+	g_clean_stats.rounds = sweeps, g_clean_stats.committed = cnt;
+	return cnt;
 }
 
 uint32_t dg_cut_tip(MabDev &d, DGraph &g, int max_ext)
 {
-	uint32_t cnt = run_spec_rounds(d, g, TipRule{max_ext});
+	uint32_t cnt = run_fixpoint(d, g, FxTip{max_ext});
 	if (cnt > 0) dg_cleanup(d, g);
 	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] cut %d tips\n", "asg_cut_tip", cnt);
 	return cnt;
@@ -341,7 +124,7 @@ uint32_t dg_cut_tip(MabDev &d, DGraph &g, int max_ext)
 
 uint32_t dg_cut_internal(MabDev &d, DGraph &g, int max_ext)
 {
-	uint32_t cnt = run_spec_rounds(d, g, InternalRule{max_ext});
+	uint32_t cnt = run_fixpoint(d, g, FxInternal{max_ext});
 	if (cnt > 0) dg_cleanup(d, g);
 	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] cut %d internal sequences\n", "asg_cut_internal", cnt);
 	return cnt;
@@ -349,275 +132,57 @@ uint32_t dg_cut_internal(MabDev &d, DGraph &g, int max_ext)
 
 uint32_t dg_cut_biloop(MabDev &d, DGraph &g, int max_ext)
 {
-	uint32_t cnt = run_spec_rounds(d, g, BiloopRule{max_ext});
+	uint32_t cnt = run_fixpoint(d, g, FxBiloop{max_ext});
 	if (cnt > 0) dg_cleanup(d, g);
 	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] cut %d small bi-loops\n", "asg_cut_biloop", cnt);
 	return cnt;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bubble popping (asg.c:312-433).  asg_bub_pop1 is a bounded Kahn-style traversal from a source v0 with
-// >= 2 live out-arcs; per visited vertex it keeps {best parent p, distance d, read count c, pending in-arcs r}.
-// The reference indexes one n_vtx-sized array by vertex and resets the touched entries afterwards; here each
-// traversal owns a small open-addressing table vertex -> {p,d,c,r} in a per-thread scratch slot, which is the
-// same map restricted to the visited set.  One thread walks one source (the walk is a LIFO-ordered pointer
-// chase); sources are independent within a round of the prefix-commit scheme above.  Cells of a traversal:
-// the source's read and the read of every visited vertex (all state read or written lives there).
+// Bubble popping (asg.c:312-433): one thread walks one source; its {p,d,c,r} map lives in a scratch slot in HBM.
+// Only vertices with >= 2 arcs in the index can ever be sources (the pass only deletes): they are listed once.
 // ---------------------------------------------------------------------------------------------
-struct BubSlots {
+struct FxSlots {
 	uint32_t *hkey, *hp, *hd, *hc, *hr;  // [n_slot][hcap]
 	uint32_t *b, *bslot, *S;             // [n_slot][bcap]
 	uint32_t *e;                         // [n_slot][ecap]
 	uint32_t bcap, ecap, hcap, n_slot;
+	__device__ FxSlot slot(uint32_t k) const
+	{
+		const size_t h = (size_t)k * hcap, q = (size_t)k * bcap, r = (size_t)k * ecap;
+		return FxSlot{hkey + h, hp + h, hd + h, hc + h, hr + h, b + q, bslot + q, S + q, e + r, bcap, ecap, hcap - 1};
+	}
 };
 
-struct BubWalk { uint32_t nb, ne, nT, sink; };
-
-constexpr uint32_t BUB_EMPTY = 0xffffffffu;
-
-__device__ __forceinline__ uint32_t bub_find(const uint32_t *hkey, uint32_t hmask, uint32_t key)
+__global__ void k_fx_bub_sources(const uint64_t *idx, const uint32_t *seq, uint32_t n_vtx, uint32_t *src, unsigned long long *n_src)
 {
-	uint32_t h = (key * 2654435761u) >> 9 & hmask;
-	while (hkey[h] != key) h = (h + 1) & hmask; // the key is known to be present
-	return h;
+	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_vtx; v += gridDim.x * blockDim.x)
+		if ((uint32_t)idx[v] >= 2 && !(seq[v >> 1] & MAB_DEL_BIT)) src[atomicAdd(n_src, 1ull)] = v;
 }
 
-// returns 1 = bubble resolved (backtrack applies), 0 = nothing to pop, -1 = scratch too small
-__device__ int bub_walk(const GV &g, uint32_t v0, uint32_t max_dist, const BubSlots &sl, uint32_t slot, BubWalk *out)
+// counts[0] pops, [1] trimmed tips, [2] scratch overflows, [3] revived-a-dead-bit (pass not deletion-only)
+__global__ void k_fx_bub_sweep(FxView g, uint32_t max_dist, FxSlots sl, const uint32_t *src, uint32_t n_src, unsigned long long *counts)
 {
-	uint32_t *hkey = sl.hkey + (size_t)slot * sl.hcap, *hp = sl.hp + (size_t)slot * sl.hcap, *hd = sl.hd + (size_t)slot * sl.hcap;
-	uint32_t *hc = sl.hc + (size_t)slot * sl.hcap, *hr = sl.hr + (size_t)slot * sl.hcap;
-	uint32_t *b = sl.b + (size_t)slot * sl.bcap, *bslot = sl.bslot + (size_t)slot * sl.bcap, *S = sl.S + (size_t)slot * sl.bcap;
-	uint32_t *e = sl.e + (size_t)slot * sl.ecap;
-	const uint32_t hmask = sl.hcap - 1;
-	uint32_t nb = 0, ne = 0, nT = 0, nS = 0, n_pending = 0;
-	int ret = 0;
-	S[nS++] = v0;
-	do {
-		const uint32_t v = S[--nS];
-		uint32_t d = 0, c = 0;
-		if (v != v0) { uint32_t h = bub_find(hkey, hmask, v); d = hd[h], c = hc[h]; }
-		const uint64_t iv = g.idx[v];
-		const uint32_t nv = (uint32_t)iv, off = (uint32_t)(iv >> 32);
-		const DArc *av = g.arc + off;
-		uint32_t i;
-		for (i = 0; i < nv; ++i) {
-			const uint32_t w = av[i].v, l = (uint32_t)av[i].ul;
-			if (w == v0) goto done;                        // a cycle through the source (tested before the del bit, asg.c:377)
-			if (av[i].ol_del & MAB_DEL_BIT) continue;
-			if (ne == sl.ecap) { ret = -1; goto done; }
-			e[ne++] = off + i;
-			if (d + l > max_dist) break;                   // too far
-			uint32_t h = (w * 2654435761u) >> 9 & hmask;
-			while (hkey[h] != BUB_EMPTY && hkey[h] != w) h = (h + 1) & hmask;
-			if (hkey[h] == BUB_EMPTY) {                    // first visit
-				if (nb == sl.bcap) { ret = -1; goto done; }
-				hkey[h] = w; bslot[nb] = h; b[nb++] = w;
-				hp[h] = v, hd[h] = d + l, hc[h] = 0;
-				uint32_t r = 0;                            // count_out(w^1): live arcs only
-				const uint64_t ix = g.idx[w ^ 1];
-				const DArc *ax = g.arc + (ix >> 32);
-				for (uint32_t k = 0; k < (uint32_t)ix; ++k) r += !(ax[k].ol_del & MAB_DEL_BIT);
-				hr[h] = r;
-				++n_pending;
-			} else {
-				if (c + 1 > hc[h] || (c + 1 == hc[h] && d + l > hd[h])) hp[h] = v;
-				if (c + 1 > hc[h]) hc[h] = c + 1;
-				if (d + l < hd[h]) hd[h] = d + l;
-			}
-			hr[h] = (hr[h] - 1) & 0x7fffffffu;
-			if (hr[h] == 0) {
-				if ((uint32_t)g.idx[w]) S[nS++] = w;       // nS <= nb + 1 <= bcap: every vertex is pushed at most once
-				else ++nT;                                 // a tip
-				--n_pending;
-			}
-		}
-		if (i < nv || nS == 0) goto done;
-	} while (nS > 1 || n_pending);
-	ret = 1;
-	out->sink = S[0];
-done:
-	out->nb = nb, out->ne = ne, out->nT = nT;
-	return ret;
-}
-
-__device__ __forceinline__ void bub_reset(const BubSlots &sl, uint32_t slot, uint32_t nb)
-{
-	uint32_t *hkey = sl.hkey + (size_t)slot * sl.hcap;
-	const uint32_t *bslot = sl.bslot + (size_t)slot * sl.bcap;
-	for (uint32_t i = 0; i < nb; ++i) hkey[bslot[i]] = BUB_EMPTY;
-}
-
-// asg_bub_backtrack (asg.c:338-357)
-__device__ void bub_backtrack(const GV &g, uint32_t v0, const BubSlots &sl, uint32_t slot, const BubWalk &w)
-{
-	const uint32_t *hkey = sl.hkey + (size_t)slot * sl.hcap, *hp = sl.hp + (size_t)slot * sl.hcap;
-	const uint32_t *b = sl.b + (size_t)slot * sl.bcap, *e = sl.e + (size_t)slot * sl.ecap;
-	for (uint32_t i = 0; i < w.nb; ++i) g.seq[b[i] >> 1] |= MAB_DEL_BIT;
-	for (uint32_t i = 0; i < w.ne; ++i) {
-		DArc *a = g.arc + e[i];
-		a->ol_del |= MAB_DEL_BIT;
-		arc_del(g, a->v ^ 1, (uint32_t)(a->ul >> 32) ^ 1, true);
-	}
-	uint32_t v = w.sink;
-	do {
-		const uint32_t u = hp[bub_find(hkey, sl.hcap - 1, v)];
-		g.seq[v >> 1] &= ~MAB_DEL_BIT;
-		arc_del(g, u, v, false);
-		arc_del(g, v ^ 1, u ^ 1, false);
-		v = u;
-	} while (v != v0);
-}
-
-// the outer-loop test of asg_pop_bubble (asg.c:420-426) plus the guards of asg_bub_pop1 (asg.c:364-365)
-__device__ __forceinline__ bool bub_is_source(const GV &g, uint32_t v)
-{
-	const uint64_t iv = g.idx[v];
-	const uint32_t nv = (uint32_t)iv;
-	if (nv < 2 || (g.seq[v >> 1] & MAB_DEL_BIT)) return false;
-	const DArc *av = g.arc + (iv >> 32);
-	uint32_t live = 0;
-	for (uint32_t i = 0; i < nv; ++i) live += !(av[i].ol_del & MAB_DEL_BIT);
-	return live > 1;
-}
-
-__global__ void k_bub_sources(GV g, uint32_t lo, uint32_t *src, unsigned long long *n_src)
-{
-	for (uint32_t v = lo + blockIdx.x * blockDim.x + threadIdx.x; v < g.n_vtx; v += gridDim.x * blockDim.x)
-		if (bub_is_source(g, v)) src[atomicAdd(n_src, 1ull)] = v;
-}
-
-__global__ void k_bub_eval(GV g, uint32_t max_dist, BubSlots sl, const uint32_t *src, uint32_t n_src, uint8_t *cand, uint32_t *tag,
-                           unsigned long long *n_cand, unsigned long long *overflow)
-{
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	if (slot >= sl.n_slot) return;
-	for (uint32_t k = slot; k < n_src; k += sl.n_slot) {
-		const uint32_t v0 = src[k];
-		BubWalk w;
-		int r = bub_walk(g, v0, max_dist, sl, slot, &w);
-		cand[v0] = r == 1;
+	const uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k0 >= sl.n_slot) return;
+	const FxSlot s = sl.slot(k0);
+	for (uint32_t k = k0; k < n_src; k += sl.n_slot) {
+		uint32_t nt = 0;
+		bool mono = true;
+		const int r = fx_bub_act(g, src[k], max_dist, s, &nt, &mono);
 		if (r == 1) {
-			const uint32_t *b = sl.b + (size_t)slot * sl.bcap;
-			atomicMin(&tag[v0 >> 1], v0);
-			for (uint32_t i = 0; i < w.nb; ++i) atomicMin(&tag[b[i] >> 1], v0);
-			atomicAdd(n_cand, 1ull);
-		} else if (r < 0) atomicAdd(overflow, 1ull);
-		bub_reset(sl, slot, w.nb);
+			atomicAdd(&counts[0], 1ull);
+			if (nt) atomicAdd(&counts[1], (unsigned long long)nt);
+			if (!mono) atomicAdd(&counts[3], 1ull);
+		} else if (r < 0) atomicAdd(&counts[2], 1ull);
 	}
 }
 
-// non-sources read only their own read's state
-__global__ void k_bub_check_own(GV g, uint32_t lo, const uint32_t *tag, unsigned long long *xstar)
-{
-	uint32_t bad = NO_TAG;
-	for (uint32_t v = lo + blockIdx.x * blockDim.x + threadIdx.x; v < g.n_vtx; v += gridDim.x * blockDim.x)
-		if (tag[v >> 1] < v && v < bad) bad = v;
-	bad = __reduce_min_sync(0xffffffffu, bad);
-	if ((threadIdx.x & 31) == 0 && bad != NO_TAG) atomicMin(xstar, (unsigned long long)bad);
-}
-
-__global__ void k_bub_check_walk(GV g, uint32_t max_dist, BubSlots sl, const uint32_t *src, uint32_t n_src, const uint32_t *tag, unsigned long long *xstar)
-{
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	if (slot >= sl.n_slot) return;
-	for (uint32_t k = slot; k < n_src; k += sl.n_slot) {
-		const uint32_t v0 = src[k];
-		BubWalk w;
-		bub_walk(g, v0, max_dist, sl, slot, &w);
-		const uint32_t *b = sl.b + (size_t)slot * sl.bcap;
-		uint32_t m = tag[v0 >> 1];
-		for (uint32_t i = 0; i < w.nb; ++i) { uint32_t t = tag[b[i] >> 1]; m = t < m ? t : m; }
-		if (m < v0) atomicMin(xstar, (unsigned long long)v0);
-		bub_reset(sl, slot, w.nb);
-	}
-}
-
-__global__ void k_bub_commit(GV g, uint32_t max_dist, BubSlots sl, const uint32_t *src, uint32_t n_src, const uint8_t *cand, uint32_t hi,
-                             unsigned long long *n_pop, unsigned long long *n_tip)
-{
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	if (slot >= sl.n_slot) return;
-	for (uint32_t k = slot; k < n_src; k += sl.n_slot) {
-		const uint32_t v0 = src[k];
-		if (v0 >= hi || !cand[v0]) continue;
-		BubWalk w;
-		if (bub_walk(g, v0, max_dist, sl, slot, &w) == 1) {
-			bub_backtrack(g, v0, sl, slot, w);
-			atomicAdd(n_pop, 1ull);
-			if (w.nT) atomicAdd(n_tip, (unsigned long long)w.nT);
-		}
-		bub_reset(sl, slot, w.nb);
-	}
-}
-
-// ---- "excuse" variant of the validity check (experimental, MAB_BUB_EXCUSE=1) ----------------------------------------
-// With the plain prefix rule every pop costs a round on genome-ordered ids: the pop at source A stamps the reads of its
-// region, the complement-strand twin of the bubble (source = sink(A)^1, a slightly larger id) finds those stamps and is
-// invalid, so x* lands right behind A.  But that twin -- like every other vertex on a read of A's walk set except A^1
-// and sink(A) -- has all of its live out-arcs (on the complement strand: the complements of all its live in-arcs)
-// inside A's region: once A has popped, at most the restored path arc is left, it is no longer a source, and in this
-// deletion-only pass (no multi-arcs, the graph is symmetric) it never becomes one again.  Such a vertex is a
-// guaranteed no-op and need not stop the prefix.  Non-sources are final no-ops for the same reason and are not
-// checked at all.  oracle/spec_sim.c is the CPU model of exactly this rule: identical final state on every parity
-// set, 3713 -> 174 rounds on a 300 K-read bubble-dense set.
-__global__ void k_bub_check_walk2(GV g, uint32_t max_dist, BubSlots sl, const uint32_t *src, uint32_t n_src, const uint32_t *tag,
-                                  uint32_t *mn, uint32_t *sink)
-{
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	if (slot >= sl.n_slot) return;
-	for (uint32_t k = slot; k < n_src; k += sl.n_slot) {
-		const uint32_t v0 = src[k];
-		BubWalk w;
-		const int r = bub_walk(g, v0, max_dist, sl, slot, &w);
-		const uint32_t *b = sl.b + (size_t)slot * sl.bcap;
-		uint32_t m = tag[v0 >> 1];
-		for (uint32_t i = 0; i < w.nb; ++i) { uint32_t t = tag[b[i] >> 1]; m = t < m ? t : m; }
-		mn[v0] = m;                                  // smallest stamp on the walk set (valid iff >= v0)
-		sink[v0] = r == 1 ? w.sink : NO_TAG;
-		bub_reset(sl, slot, w.nb);
-	}
-}
-
-__global__ void k_bub_xstar2(const uint32_t *src, uint32_t n_src, const uint32_t *tag, const uint8_t *cand, const uint32_t *mn, const uint32_t *sink,
-                             unsigned long long *xstar)
-{
-	uint32_t bad = NO_TAG;
-	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_src; k += gridDim.x * blockDim.x) {
-		const uint32_t v = src[k];
-		if (mn[v] >= v) continue;                    // valid
-		const uint32_t A = tag[v >> 1];              // smallest candidate that stamped v's own read (it is a source of this round)
-		const bool excused = A < v && cand[A] && mn[A] >= A && v != (A ^ 1) && v != sink[A];
-		if (!excused && v < bad) bad = v;
-	}
-	bad = __reduce_min_sync(0xffffffffu, bad);
-	if ((threadIdx.x & 31) == 0 && bad != NO_TAG) atomicMin(xstar, (unsigned long long)bad);
-}
-
-// commit of the excuse variant: below x* there may be invalid (excused) candidates, which must not act
-__global__ void k_bub_commit2(GV g, uint32_t max_dist, BubSlots sl, const uint32_t *src, uint32_t n_src, const uint8_t *cand, const uint32_t *mn, uint32_t hi,
-                              unsigned long long *n_pop, unsigned long long *n_tip)
-{
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	if (slot >= sl.n_slot) return;
-	for (uint32_t k = slot; k < n_src; k += sl.n_slot) {
-		const uint32_t v0 = src[k];
-		if (v0 >= hi || !cand[v0] || mn[v0] < v0) continue;
-		BubWalk w;
-		if (bub_walk(g, v0, max_dist, sl, slot, &w) == 1) {
-			bub_backtrack(g, v0, sl, slot, w);
-			atomicAdd(n_pop, 1ull);
-			if (w.nT) atomicAdd(n_tip, (unsigned long long)w.nT);
-		}
-		bub_reset(sl, slot, w.nb);
-	}
-}
-
-static void bub_slots_alloc(MabDev &d, BubSlots &sl, uint32_t n_slot, uint32_t bcap)
+static void fx_slots_alloc(MabDev &d, FxSlots &sl, uint32_t n_slot, uint32_t bcap)
 {
 	sl.n_slot = n_slot, sl.bcap = bcap, sl.ecap = bcap * 4;
 	sl.hcap = 1; while (sl.hcap < 2 * bcap) sl.hcap <<= 1;
-	size_t nh = (size_t)n_slot * sl.hcap, nb = (size_t)n_slot * sl.bcap, ne = (size_t)n_slot * sl.ecap;
+	const size_t nh = (size_t)n_slot * sl.hcap, nb = (size_t)n_slot * sl.bcap, ne = (size_t)n_slot * sl.ecap;
 	sl.hkey = mab_alloc<uint32_t>(d, nh); sl.hp = mab_alloc<uint32_t>(d, nh); sl.hd = mab_alloc<uint32_t>(d, nh);
 	sl.hc = mab_alloc<uint32_t>(d, nh); sl.hr = mab_alloc<uint32_t>(d, nh);
 	sl.b = mab_alloc<uint32_t>(d, nb); sl.bslot = mab_alloc<uint32_t>(d, nb); sl.S = mab_alloc<uint32_t>(d, nb);
@@ -625,7 +190,7 @@ static void bub_slots_alloc(MabDev &d, BubSlots &sl, uint32_t n_slot, uint32_t b
 	MAB_CUDA(cudaMemsetAsync(sl.hkey, 0xff, nh * 4, d.stream));
 }
 
-static void bub_slots_free(MabDev &d, BubSlots &sl)
+static void fx_slots_free(MabDev &d, FxSlots &sl)
 {
 	d.free(sl.hkey); d.free(sl.hp); d.free(sl.hd); d.free(sl.hc); d.free(sl.hr);
 	d.free(sl.b); d.free(sl.bslot); d.free(sl.S); d.free(sl.e);
@@ -635,77 +200,50 @@ uint64_t dg_pop_bubble(MabDev &d, DGraph &g, int max_dist)
 {
 	const uint32_t n_vtx = g.n_seq * 2;
 	uint64_t n_pop = 0, n_tip = 0;
-	uint32_t rounds = 0;
+	uint32_t sweeps = 0;
 	if (!g.is_symm) dg_symm(d, g);
 	if (n_vtx && g.n_arc) {
-		GV gv{g.arc, g.idx, g.seq, n_vtx};
-		uint8_t *cand = mab_alloc<uint8_t>(d, n_vtx);
-		uint32_t *tag = mab_alloc<uint32_t>(d, g.n_seq);
 		uint32_t *src = mab_alloc<uint32_t>(d, n_vtx);
-		MAB_CUDA(cudaMemsetAsync(tag, 0xff, (size_t)g.n_seq * 4, d.stream));
-		MAB_CUDA(cudaMemsetAsync(cand, 0, n_vtx, d.stream));
-		static const bool excuse = getenv("MAB_BUB_EXCUSE") && atoi(getenv("MAB_BUB_EXCUSE")) != 0;
-		uint32_t *mn = excuse ? mab_alloc<uint32_t>(d, n_vtx) : nullptr, *sink = excuse ? mab_alloc<uint32_t>(d, n_vtx) : nullptr;
-		BubSlots sl;
-		uint32_t bcap = 256, n_slot = 4096;
-		bub_slots_alloc(d, sl, n_slot, bcap);
-		uint32_t lo = 0;
-		SpecWindow win(n_vtx);
-		while (lo < n_vtx) {
-			const uint32_t end = win.end(lo);
-			GV gw = gv;
-			gw.n_vtx = end;                                          // sources and own-cell checks of [lo, end) only
-			d.zero_scal(SC_COUNT, 4); // COUNT (candidates), NSEL, BIG (overflow), AUX (sources)
-			MAB_CUDA(cudaMemsetAsync(d.d_scal + SC_MIN, 0xff, 8, d.stream));
-			MAB_LAUNCH(d, k_bub_sources, mab_grid(end - lo, 256), 256, 0, gw, lo, src, d.d_scal + SC_AUX);
-			uint32_t n_src = (uint32_t)d.get_scal(SC_AUX);
-			if (n_src == 0) {
-				if (end == n_vtx) break;
-				win.advanced(lo, end, end);
-				lo = end;
-				continue;
+		d.zero_scal(SC_AUX);
+		MAB_LAUNCH(d, k_fx_bub_sources, mab_grid(n_vtx, 256), 256, 0, g.idx, g.seq, n_vtx, src, d.d_scal + SC_AUX);
+		const uint32_t n_src = (uint32_t)d.get_scal(SC_AUX);
+		if (n_src) {
+			FxBuf b;
+			fx_alloc(d, g, b);
+			FxSlots sl;
+			uint32_t bcap = 64, n_slot = n_src < 16384 ? (n_src + 63) / 64 * 64 : 16384;
+			fx_slots_alloc(d, sl, n_slot, bcap);
+			for (;;) {
+				d.zero_scal(SC_TMP0, 4);
+				MAB_LAUNCH(d, k_fx_bub_sweep, (sl.n_slot + 63) / 64, 64, 0, fx_view(g, b), (uint32_t)max_dist, sl, src, n_src, d.d_scal + SC_TMP0);
+				if (d.get_scal(SC_TMP0 + 2)) { // a traversal outgrew its scratch slot: enlarge, re-arm T_new and redo the sweep
+					fx_slots_free(d, sl);
+					bcap *= 4;
+					if (n_slot > 64) n_slot /= 4;
+					if ((uint64_t)bcap > (uint64_t)n_vtx * 4) { fprintf(stderr, "[E::miniasm_b200] bubble scratch overflow\n"); exit(75); }
+					fx_slots_alloc(d, sl, n_slot, bcap);
+					MAB_LAUNCH(d, k_fx_init, mab_grid((size_t)g.n_arc + g.n_seq, 256), 256, 0, g.arc, g.seq, g.n_arc, g.n_seq,
+					           b.ts[b.cur ^ 1], b.ts[b.cur ^ 1], b.ta[b.cur ^ 1], b.ta[b.cur ^ 1]);
+					continue;
+				}
+				++sweeps;
+				const bool fixed = fx_next(d, g, b);
+				n_pop = d.h_scal[SC_TMP0], n_tip = d.h_scal[SC_TMP0 + 1];
+				if (fixed) {
+					if (d.h_scal[SC_TMP0 + 3]) { // asg_bub_backtrack would revive a bit deleted earlier: impossible on the symmetric,
+						// multi-arc-free graph asg_pop_bubble works on; refuse rather than return a different graph
+						fprintf(stderr, "[E::miniasm_b200] asg_pop_bubble: the graph is not symmetric (best path over a deleted arc)\n");
+						exit(76);
+					}
+					break;
+				}
 			}
-			const unsigned wgrid = (sl.n_slot + 63) / 64;
-			MAB_LAUNCH(d, k_bub_eval, wgrid, 64, 0, gv, (uint32_t)max_dist, sl, src, n_src, cand, tag, d.d_scal + SC_COUNT, d.d_scal + SC_BIG);
-			uint64_t n_cand = d.get_scal(SC_COUNT);
-			if (d.h_scal[SC_BIG]) { // a traversal outgrew its scratch slot: enlarge and redo the round
-				bub_slots_free(d, sl);
-				bcap *= 4;
-				if (n_slot > 64) n_slot /= 4;
-				if ((uint64_t)bcap > (uint64_t)n_vtx * 4) { fprintf(stderr, "[E::miniasm_b200] bubble scratch overflow\n"); exit(75); }
-				bub_slots_alloc(d, sl, n_slot, bcap);
-				MAB_CUDA(cudaMemsetAsync(tag, 0xff, (size_t)g.n_seq * 4, d.stream));
-				continue;
-			}
-			if (n_cand == 0) {                                       // no source of the window pops anything (nobody stamped)
-				if (end == n_vtx) break;
-				win.advanced(lo, end, end);
-				lo = end;
-				continue;
-			}
-			if (excuse) { // non-sources unchecked, excusable invalid sources do not stop the prefix (see k_bub_check_walk2)
-				MAB_LAUNCH(d, k_bub_check_walk2, wgrid, 64, 0, gv, (uint32_t)max_dist, sl, src, n_src, tag, mn, sink);
-				MAB_LAUNCH(d, k_bub_xstar2, mab_grid(n_src, 256), 256, 0, src, n_src, tag, cand, mn, sink, d.d_scal + SC_MIN);
-			} else {
-				MAB_LAUNCH(d, k_bub_check_own, mab_grid(end - lo, 256), 256, 0, gw, lo, tag, d.d_scal + SC_MIN);
-				MAB_LAUNCH(d, k_bub_check_walk, wgrid, 64, 0, gv, (uint32_t)max_dist, sl, src, n_src, tag, d.d_scal + SC_MIN);
-			}
-			unsigned long long xs = d.get_scal(SC_MIN);
-			uint32_t hi = xs >= end ? end : (uint32_t)xs;
-			d.zero_scal(SC_TMP0, 2);
-			if (excuse) MAB_LAUNCH(d, k_bub_commit2, wgrid, 64, 0, gv, (uint32_t)max_dist, sl, src, n_src, cand, mn, hi, d.d_scal + SC_TMP0, d.d_scal + SC_TMP0 + 1);
-			else MAB_LAUNCH(d, k_bub_commit, wgrid, 64, 0, gv, (uint32_t)max_dist, sl, src, n_src, cand, hi, d.d_scal + SC_TMP0, d.d_scal + SC_TMP0 + 1);
-			MAB_CUDA(cudaMemsetAsync(tag, 0xff, (size_t)g.n_seq * 4, d.stream));
-			n_pop += d.get_scal(SC_TMP0);
-			n_tip += d.h_scal[SC_TMP0 + 1];
-			win.advanced(lo, hi, end);
-			lo = hi;
-			++rounds;
+			fx_slots_free(d, sl);
+			fx_finish(d, g, b);
 		}
-		bub_slots_free(d, sl);
-		d.free(cand); d.free(tag); d.free(src); d.free(mn); d.free(sink);
+		d.free(src);
 	}
-	g_clean_stats.rounds = rounds, g_clean_stats.committed = (uint32_t)n_pop;
+	g_clean_stats.rounds = sweeps, g_clean_stats.committed = (uint32_t)n_pop;
 	if (n_pop) dg_cleanup(d, g);
 	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] popped %d bubbles and trimmed %d tips\n", "asg_pop_bubble", (uint32_t)n_pop, (uint32_t)n_tip);
 	return (n_pop & 0xffffffffull) | n_tip << 32;

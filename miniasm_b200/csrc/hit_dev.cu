@@ -1144,7 +1144,7 @@ void dh_sg_emit(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *d
 	const uint32_t lb = bits_for(mx);
 	if (h.n) {
 		if (h.n >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 arcs on one GPU\n"); exit(73); }
-		static const bool seg_sort = getenv("MAB_SG_SEGSORT") && atoi(getenv("MAB_SG_SEGSORT")) != 0;
+		static const bool seg_sort = !(getenv("MAB_SG_SEGSORT") && atoi(getenv("MAB_SG_SEGSORT")) == 0); // default on; 0 = device-wide column sort
 		if (seg_sort && sg_emit_segmented(d, h, p, lb, g)) return;
 		if (seg_sort) d.zero_scal(SC_COUNT); // the attempt counted the arcs already
 		const uint64_t sentinel = 1ull << (lb + bits_for((uint64_t)n_seq * 2 - 1));

@@ -142,14 +142,15 @@ int main(int argc, char *argv[])
 		free(hit);
 	} else if (strcmp(outfmt, "ug") == 0 || strcmp(outfmt, "sg") == 0) {
 		fprintf(stderr, "[M::%s] ===> Step 4: graph cleaning <===\n", __func__);
-		const int gpu_gfa = strcmp(outfmt, "ug") == 0 && !fn_reads && (env = getenv("MAB_GPU_GFA")) != 0 && atoi(env) != 0;
+		/* no -f: the GFA text is formatted on the GPU and copied down once (MAB_GPU_GFA=0: host structs + ma_ug_print) */
+		const int gpu_gfa = strcmp(outfmt, "ug") == 0 && !fn_reads && !((env = getenv("MAB_GPU_GFA")) != 0 && atoi(env) == 0);
 		mab_layout(ctx, &opt, stage);
 		if (!gpu_gfa) d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
 		if (strcmp(outfmt, "ug") == 0) {
 			ma_ug_t *ug;
 			fprintf(stderr, "[M::%s] ===> Step 5: generating unitigs <===\n", __func__);
 			mab_unitigs(ctx);
-			if (gpu_gfa) { /* experimental: text formatted on the GPU, no host copies of the tables */
+			if (gpu_gfa) {
 				mab_write_gfa(ctx, stdout);
 			} else {
 				ug = mab_export_ug(ctx);
