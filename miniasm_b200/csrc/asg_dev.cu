@@ -15,8 +15,9 @@
 #include <cub/cub.cuh>
 
 int mab_verbose = 3;
+thread_local int mab_mute = 0;
 int mab_del_trans_count_inner = 0;
-DelTransStats g_del_trans_stats;
+thread_local DelTransStats g_del_trans_stats;
 
 // ---------------------------------------------------------------------------------------------
 // small helpers
@@ -286,7 +287,7 @@ uint32_t dg_del_multi(MabDev &d, DGraph &g)
 		n_multi = (uint32_t)d.get_scal(SC_COUNT);
 	}
 	if (n_multi) dg_cleanup(d, g);
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] removed %d multi-arcs\n", "asg_arc_del_multi", n_multi);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] removed %d multi-arcs\n", "asg_arc_del_multi", n_multi);
 	return n_multi;
 }
 
@@ -299,7 +300,7 @@ uint32_t dg_del_asymm(MabDev &d, DGraph &g)
 		n_asymm = (uint32_t)d.get_scal(SC_COUNT);
 	}
 	if (n_asymm) dg_cleanup(d, g);
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] removed %d asymmetric arcs\n", "asg_arc_del_asymm", n_asymm);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] removed %d asymmetric arcs\n", "asg_arc_del_asymm", n_asymm);
 	return n_asymm;
 }
 
@@ -673,7 +674,7 @@ uint32_t dg_del_trans(MabDev &d, DGraph &g, uint32_t fuzz)
 {
 	uint8_t *flag = nullptr;
 	uint32_t n_reduced = dg_del_trans_flags(d, g, fuzz, 0, 0xffffffffu, &flag, nullptr, nullptr, nullptr, 1);
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] transitively reduced %d arcs\n", "asg_arc_del_trans", n_reduced);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] transitively reduced %d arcs\n", "asg_arc_del_trans", n_reduced);
 	if (n_reduced) {
 		dg_cleanup(d, g, flag);
 		dg_symm(d, g);
@@ -718,11 +719,7 @@ uint32_t dg_del_trans_flags(MabDev &d, DGraph &g, uint32_t fuzz, uint32_t own_lo
 		g_del_trans_stats.kernel_ms = ms;
 		MAB_CUDA(cudaEventDestroy(e0)); MAB_CUDA(cudaEventDestroy(e1));
 		if (n_big) {
-			static bool attr_set = false;
-			if (!attr_set) {
-				MAB_CUDA(cudaFuncSetAttribute(k_del_trans_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DT_BIG_SMEM));
-				attr_set = true;
-			}
+			MAB_CUDA(cudaFuncSetAttribute(k_del_trans_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DT_BIG_SMEM)); // per device: set on every use
 			uint32_t *huge = mab_alloc<uint32_t>(d, n_big);
 			MAB_LAUNCH(d, k_del_trans_cta, n_big < 148u * 2 ? n_big : 148u * 2, 256, DT_BIG_SMEM, g.arc, g.idx, fuzz, flag, big, n_big, huge, d.d_scal, sv);
 			uint32_t n_huge = (uint32_t)d.get_scal(SC_AUX2);
@@ -780,6 +777,6 @@ uint32_t dg_del_short(MabDev &d, DGraph &g, float ratio)
 		dg_cleanup(d, g);
 		dg_symm(d, g);
 	}
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] removed %d short overlaps\n", "asg_arc_del_short", n_short);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] removed %d short overlaps\n", "asg_arc_del_short", n_short);
 	return n_short;
 }

@@ -36,7 +36,9 @@ uint32_t dg_del_short(MabDev &d, DGraph &g, float ratio);    // asg.c:83-101
 
 // statistics of the last dg_del_trans call (for the roofline arithmetic in bench.py)
 struct DelTransStats { uint64_t n_arc_in, n_vtx, inner_iters, n_reduced, n_big; float kernel_ms; };
-extern DelTransStats g_del_trans_stats;
+extern thread_local DelTransStats g_del_trans_stats; // of the calling thread's last call (one thread drives one GPU)
 
 extern int mab_del_trans_count_inner; // 1: asg_arc_del_trans also counts its inner-loop iterations (slower kernel variant)
+extern thread_local int mab_mute; // 1: this thread is a non-zero rank of a multi-GPU run and prints no [M::...] lines
+#define MAB_V(level) (!mab_mute && mab_verbose >= (level))
 extern int mab_verbose;   // mirrors ma_verbose (common.c:3): >=3 prints the reference's [M::...] lines

@@ -220,7 +220,7 @@ int mab_ingest(mab_ctx_t *c, int min_span, int min_match, int bi_dir)
 	ingest_paf(d, c->d_text, c->text_len, min_span, min_match, bi_dir, c->hits, c->names, c->ist);
 	c->n_seq = c->names.n_seq;
 	c->stats.n_lines = c->ist.n_parsed, c->stats.n_hits_stored = c->ist.n_hits, c->stats.n_seq_in = c->ist.n_seq;
-	if (ma_verbose >= 3)
+	if (!mab_mute && ma_verbose >= 3)
 		fprintf(stderr, "[M::%s::%s] read %ld hits; stored %ld hits and %d sequences (%ld bp)\n", "ma_hit_read", sys_timestamp(),
 				(long)c->ist.n_parsed, (long)c->ist.n_hits, (int)c->ist.n_seq, (long)c->ist.tot_len);
 	return 0;
@@ -352,7 +352,7 @@ int mab_layout(mab_ctx_t *c, const ma_opt_t *opt, int stage)
 	DGraph &g = c->sg;
 	c->stats.n_arc_sg = g.n_arc;
 	if (stage >= 6) {
-		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.1: transitive reduction <===\n");
+		if (!mab_mute && ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.1: transitive reduction <===\n");
 		dg_del_trans(d, g, (uint32_t)opt->gap_fuzz);
 		c->stats.n_arc_trans_in = g_del_trans_stats.n_arc_in, c->stats.n_reduced = g_del_trans_stats.n_reduced;
 		c->stats.trans_inner = g_del_trans_stats.inner_iters, c->stats.ms_del_trans_kernel = g_del_trans_stats.kernel_ms;
@@ -368,12 +368,12 @@ static void layout_tail(mab_ctx *c, const ma_opt_t *opt, int stage)
 	MabDev &d = c->dev;
 	DGraph &g = c->sg;
 	if (stage >= 7) {
-		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.2: initial tip cutting and bubble popping <===\n");
+		if (!mab_mute && ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.2: initial tip cutting and bubble popping <===\n");
 		dg_cut_tip(d, g, opt->max_ext);
 		dg_pop_bubble(d, g, opt->bub_dist);
 	}
 	if (stage >= 9) {
-		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.3: cutting short overlaps (%d rounds in total) <===\n", opt->n_rounds + 1);
+		if (!mab_mute && ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.3: cutting short overlaps (%d rounds in total) <===\n", opt->n_rounds + 1);
 		for (int i = 0; i <= opt->n_rounds; ++i) {
 			float r = opt->min_ovlp_drop_ratio + (opt->max_ovlp_drop_ratio - opt->min_ovlp_drop_ratio) / opt->n_rounds * i;
 			if (dg_del_short(d, g, r) != 0) {
@@ -383,14 +383,14 @@ static void layout_tail(mab_ctx *c, const ma_opt_t *opt, int stage)
 		}
 	}
 	if (stage >= 10) {
-		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.4: removing short internal sequences and bi-loops <===\n");
+		if (!mab_mute && ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.4: removing short internal sequences and bi-loops <===\n");
 		dg_cut_internal(d, g, 1);
 		dg_cut_biloop(d, g, opt->max_ext);
 		dg_cut_tip(d, g, opt->max_ext);
 		dg_pop_bubble(d, g, opt->bub_dist);
 	}
 	if (stage >= 11) {
-		if (ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.5: aggressively cutting short overlaps <===\n");
+		if (!mab_mute && ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.5: aggressively cutting short overlaps <===\n");
 		if (dg_del_short(d, g, opt->final_ovlp_drop_ratio) != 0) {
 			dg_cut_tip(d, g, opt->max_ext);
 			dg_pop_bubble(d, g, opt->bub_dist);
@@ -565,7 +565,7 @@ int mab_ingest_sharded(mab_ctx_t *c, int min_span, int min_match, int bi_dir)
 	ingest_paf_sharded(d, c->sc, c->d_text, c->text_len, min_span, min_match, bi_dir, c->hits, c->names, &c->name_text, c->ist);
 	c->n_seq = c->names.n_seq;
 	c->stats.n_lines = c->ist.n_parsed, c->stats.n_hits_stored = c->ist.n_hits, c->stats.n_seq_in = c->ist.n_seq;
-	if (ma_verbose >= 3 && c->sc.rank == 0)
+	if (!mab_mute && ma_verbose >= 3 && c->sc.rank == 0)
 		fprintf(stderr, "[M::%s::%s] read %ld hits; stored %ld hits and %d sequences (%ld bp)\n", "ma_hit_read", sys_timestamp(),
 				(long)c->ist.n_parsed, (long)c->ist.n_hits, (int)c->ist.n_seq, (long)c->ist.tot_len);
 	return 0;
@@ -580,8 +580,8 @@ int mab_select_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	ShardComm &sc = c->sc;
 	PhaseTimer pt(d, &c->stats.ms_select, "mab_select_sharded");
 	ctx_drop_graphs(c);
-	const int vsave = ma_verbose;
-	if (sc.rank != 0) ma_verbose = 0; // counts in the log lines are per rank: only rank 0 talks
+	const int msave = mab_mute;
+	if (sc.rank != 0) mab_mute = 1; // counts in the log lines are per rank: only rank 0 talks (thread-local: ranks may be threads of one process)
 	const uint32_t n = c->n_seq;
 	d.free(c->sub);
 	c->sub = mab_alloc<DSub>(d, n);
@@ -608,7 +608,7 @@ int mab_select_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	c->orig_id = orig_new;
 	c->n_seq = h.n_seq;
 	d.free(map); d.free(cut2);
-	ma_verbose = vsave;
+	mab_mute = msave;
 	c->stats.n_hits_final = h.n, c->stats.n_seq_final = c->n_seq;
 	d.sync();
 	return 0;
@@ -628,8 +628,8 @@ int mab_layout_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	const int G = sc.world;
 	PhaseTimer pt(d, &c->stats.ms_layout, "mab_layout_sharded");
 	ctx_drop_graphs(c);
-	const int vsave = ma_verbose, mvsave = mab_verbose;
-	if (sc.rank != 0) ma_verbose = 0, mab_verbose = 0;
+	const int msave = mab_mute;
+	if (sc.rank != 0) mab_mute = 1;
 	const uint32_t n = c->n_seq;
 	uint32_t *len = mab_alloc<uint32_t>(d, n);
 	uint8_t *del = mab_alloc<uint8_t>(d, n);
@@ -649,14 +649,17 @@ int mab_layout_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	for (int r = 0; r < G; ++r) tot += cnt[r];
 	if (tot >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 arcs in the graph\n"); exit(73); }
 	c->stats.n_arc_sg = tot;
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", (int)tot);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", (int)tot);
 	// ---- neighbour slabs: peer access over NVLink (CUDA IPC) when every rank can offer it, else an all-gather of all arcs
-	struct PeerInfo { cudaIpcMemHandle_t h; uint64_t off, ok; };
+	// (ranks that are threads of ONE process -- the CLI's MINIASM_B200_GPUS mode -- share an address space: there the raw
+	// pointer is used after cudaDeviceEnablePeerAccess; an IPC handle cannot be opened by the process that exported it)
+	struct PeerInfo { cudaIpcMemHandle_t h; uint64_t off, ok, pid, ptr, dev; };
 	PeerInfo mine;
 	memset(&mine, 0, sizeof(mine));
 	{
 		char *base; size_t off;
 		const char *env = getenv("MAB_SHARD_P2P");
+		mine.pid = (uint64_t)getpid(), mine.ptr = (uint64_t)(uintptr_t)loc.arc, mine.dev = (uint64_t)d.device;
 		if (!(env && atoi(env) == 0) && d.arena.segment_of(loc.arc, &base, &off) && cudaIpcGetMemHandle(&mine.h, base) == cudaSuccess) mine.off = off, mine.ok = 1;
 		else cudaGetLastError();
 	}
@@ -675,6 +678,15 @@ int mab_layout_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	for (int r = 0; r < G && p2p; ++r) {
 		if (!peers[r].ok) { p2p = false; break; }
 		if (r == sc.rank) { peer_ptr[r] = loc.arc; continue; }
+		if (peers[r].pid == mine.pid) { // same process: direct peer access
+			int can = 0;
+			if (cudaDeviceCanAccessPeer(&can, d.device, (int)peers[r].dev) != cudaSuccess || !can) { cudaGetLastError(); p2p = false; break; }
+			cudaError_t e = cudaDeviceEnablePeerAccess((int)peers[r].dev, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); p2p = false; break; }
+			cudaGetLastError();
+			peer_ptr[r] = (const DArc*)(uintptr_t)peers[r].ptr;
+			continue;
+		}
 		std::string key((const char*)&peers[r].h, sizeof(cudaIpcMemHandle_t));
 		auto it = c->ipc_open.find(key);
 		void *base = nullptr;
@@ -754,7 +766,7 @@ int mab_layout_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	d.free(flag);
 	}
 	c->stats.n_reduced = n_red_all;
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] transitively reduced %d arcs\n", "asg_arc_del_trans", (int)n_red_all);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] transitively reduced %d arcs\n", "asg_arc_del_trans", (int)n_red_all);
 	// survivors -> all ranks; their stable sort by (vertex, length) is the single-GPU arc array
 	std::vector<uint64_t> bytes(G);
 	std::vector<uint64_t> kc = sc_allgather_u64(d, sc, n_keep);
@@ -771,7 +783,7 @@ int mab_layout_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	if (n_red_all) dg_symm(d, g);                           // asg.c:188-191
 	dg_free(d, loc);
 	layout_tail(c, opt, 100);
-	ma_verbose = vsave, mab_verbose = mvsave;
+	mab_mute = msave;
 	return 0;
 }
 }

@@ -9,7 +9,7 @@
 #include "clean_fix.cuh"
 #include <cub/cub.cuh>
 
-CleanStats g_clean_stats;
+thread_local CleanStats g_clean_stats;
 
 struct GV { // device view of the graph (unitig construction)
 	DArc *arc;
@@ -118,7 +118,7 @@ uint32_t dg_cut_tip(MabDev &d, DGraph &g, int max_ext)
 {
 	uint32_t cnt = run_fixpoint(d, g, FxTip{max_ext});
 	if (cnt > 0) dg_cleanup(d, g);
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] cut %d tips\n", "asg_cut_tip", cnt);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] cut %d tips\n", "asg_cut_tip", cnt);
 	return cnt;
 }
 
@@ -126,7 +126,7 @@ uint32_t dg_cut_internal(MabDev &d, DGraph &g, int max_ext)
 {
 	uint32_t cnt = run_fixpoint(d, g, FxInternal{max_ext});
 	if (cnt > 0) dg_cleanup(d, g);
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] cut %d internal sequences\n", "asg_cut_internal", cnt);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] cut %d internal sequences\n", "asg_cut_internal", cnt);
 	return cnt;
 }
 
@@ -134,7 +134,7 @@ uint32_t dg_cut_biloop(MabDev &d, DGraph &g, int max_ext)
 {
 	uint32_t cnt = run_fixpoint(d, g, FxBiloop{max_ext});
 	if (cnt > 0) dg_cleanup(d, g);
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] cut %d small bi-loops\n", "asg_cut_biloop", cnt);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] cut %d small bi-loops\n", "asg_cut_biloop", cnt);
 	return cnt;
 }
 
@@ -245,7 +245,7 @@ uint64_t dg_pop_bubble(MabDev &d, DGraph &g, int max_dist)
 	}
 	g_clean_stats.rounds = sweeps, g_clean_stats.committed = (uint32_t)n_pop;
 	if (n_pop) dg_cleanup(d, g);
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] popped %d bubbles and trimmed %d tips\n", "asg_pop_bubble", (uint32_t)n_pop, (uint32_t)n_tip);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] popped %d bubbles and trimmed %d tips\n", "asg_pop_bubble", (uint32_t)n_pop, (uint32_t)n_tip);
 	return (n_pop & 0xffffffffull) | n_tip << 32;
 }
 

@@ -10,7 +10,7 @@ uint64_t dg_pop_bubble(MabDev &d, DGraph &g, int max_dist);    // asg.c:312-433 
 
 // statistics of the speculative rounds (DESIGN.md "sequential passes"): rounds and candidates of the last call
 struct CleanStats { uint32_t rounds, committed; };
-extern CleanStats g_clean_stats;
+extern thread_local CleanStats g_clean_stats;
 
 // Unitigs (asm.c:121-210).  Device result, flattened:
 //   utg_meta[i] = {len, circ, start, end, n, first}   items[first .. first+n) = vertex<<32 | length

@@ -8,7 +8,7 @@
 
 extern "C" int ma_verbose;              // hit.c prints its [M::fn::timestamp] lines only when ma_verbose >= 3
 extern "C" const char *sys_timestamp(void);
-#define ma_verbose_dev ma_verbose
+#define ma_verbose_dev (mab_mute ? 0 : ma_verbose)
 
 __device__ __forceinline__ DHit ld_hit(const DHit *p)
 {
@@ -525,9 +525,8 @@ uint64_t dh_sub(MabDev &d, const DHits &h, int min_dp, float min_iden, int end_c
 	MAB_LAUNCH(d, k_sub_warp, grid, SUBW_WARPS * 32, 0, h.a, grp, n_seq, min_dp, min_iden, (uint32_t)end_clip, sub_out, big, d.d_scal, smem_sort);
 	uint32_t n_big = (uint32_t)d.get_scal(SC_BIG);
 	if (n_big) {
-		static bool attr_set = false;
 		const size_t smem = (size_t)SUBC_HITS * 2 * 4;
-		if (!attr_set) { MAB_CUDA(cudaFuncSetAttribute(k_sub_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+		MAB_CUDA(cudaFuncSetAttribute(k_sub_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); // per device: set on every use
 		uint32_t *huge = mab_alloc<uint32_t>(d, n_big);
 		MAB_LAUNCH(d, k_sub_cta, n_big < 148u * 2 ? n_big : 148u * 2, 512, smem, h.a, grp, big, n_big, min_dp, min_iden, (uint32_t)end_clip, sub_out, huge, d.d_scal);
 		uint32_t n_huge = (uint32_t)d.get_scal(SC_AUX2);
@@ -1112,9 +1111,8 @@ static bool sg_emit_segmented(MabDev &d, const DHits &h, const HitArcParams &p, 
 		MAB_LAUNCH(d, k_sg_sort_warp, grid, SGW_WARPS * 32, 0, h.a, grp, epos, g.seq, n_seq, p, lb, g.arc, big, d.d_scal);
 		const uint32_t n_big = (uint32_t)d.get_scal(SC_BIG);
 		if (n_big) {
-			static bool attr_set = false;
-			const size_t smem = (size_t)SGC_HITS * 16;
-			if (!attr_set) { MAB_CUDA(cudaFuncSetAttribute(k_sg_sort_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+				const size_t smem = (size_t)SGC_HITS * 16;
+			MAB_CUDA(cudaFuncSetAttribute(k_sg_sort_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 			MAB_LAUNCH(d, k_sg_sort_cta, n_big < 148u ? n_big : 148u, 512, smem, h.a, grp, epos, g.seq, big, n_big, p, g.arc, d.d_scal);
 			if (d.get_scal(SC_AUX) != 0) ok = false; // a read with more hits than a CTA sorts
 		}
@@ -1128,7 +1126,7 @@ void dh_sg_gen(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *de
 {
 	dh_sg_emit(d, h, len, del, p, g);
 	dg_cleanup(d, g);
-	if (mab_verbose >= 1) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", g.n_arc);
+	if (MAB_V(1)) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", g.n_arc);
 }
 
 void dh_sg_emit(MabDev &d, const DHits &h, const uint32_t *len, const uint8_t *del, const HitArcParams &p, DGraph &g)

@@ -379,6 +379,10 @@ int ma_ug_seq(ma_ug_t *g, const sdict_t *d, const ma_sub_t *sub, const char *fn)
 		memset(u->s, 'N', u->len);
 		for (j = 0; j < u->n; ++j) {
 			utg_slot_t *t = &slot[u->a[j] >> 33];
+			if (t->len != 0) { /* asm.c:246 asserts it: a read lies on one unitig, once */
+				fprintf(stderr, "[E::%s] read %u is placed twice in the layout\n", __func__, (uint32_t)(u->a[j] >> 33));
+				abort();
+			}
 			t->utg = i, t->ori = u->a[j] >> 32 & 1, t->start = off, t->len = (uint32_t)u->a[j];
 			off += t->len;
 		}
@@ -392,6 +396,13 @@ int ma_ug_seq(ma_ug_t *g, const sdict_t *d, const ma_sub_t *sub, const char *fn)
 		if (id < 0 || slot[id].len == 0) continue;
 		t = &slot[id];
 		dst = g->u.a[t->utg].s + t->start;
+		/* asm.c:263 asserts that the record covers the kept interval; a reads file that does not belong to the PAF must not
+		 * make us read outside the record (without `sub` the reference would: we refuse there too) */
+		if (sub ? sub[id].e > f.seq.l : t->len > f.seq.l) {
+			fprintf(stderr, "[E::%s] sequence '%s' has %ld bases, the layout needs %u: wrong reads file?\n", __func__, f.name.s, (long)f.seq.l,
+					sub ? sub[id].e : t->len);
+			abort();
+		}
 		if (sub) src += sub[id].s, sl = sub[id].e - sub[id].s;
 		if (!t->ori) memcpy(dst, src, t->len);
 		else for (i = 0; i < t->len; ++i) dst[i] = (char)comp[(unsigned char)src[sl - 1 - i]];

@@ -1,11 +1,18 @@
 /* main.c -- the miniasm-b200 command line: same options, step order, stderr chatter and output formats as
  * the reference driver (main.c:32-211), with every step of the hot path running on the GPU through the fused
  * C ABI (include/miniasm_b200.h).  Usage: miniasm-b200 [options] <in.paf>
- * Extra environment: MINIASM_B200_DEVICE=<cuda ordinal>. */
+ * Extra environment: MINIASM_B200_DEVICE=<cuda ordinal> (first device), MINIASM_B200_GPUS=<N>: the default pipeline
+ * (no -R/-1/-2/-S/-f, -p ug|sg) hash-sharded over N GPUs of this node -- one thread and one context per GPU, the PAF cut
+ * into N byte ranges at line ends, NCCL inside the library.  Same bytes on stdout as with one GPU. */
 #include <unistd.h>
 #include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
+#include <pthread.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <zlib.h>
 #include "miniasm_b200.h"
 
 #define MAB_VERSION "0.3-r179"   /* tracks the reference release whose output it reproduces */
@@ -60,10 +67,100 @@ static void usage(const ma_opt_t *o, const char *outfmt)
 	fprintf(stderr, "\nSee miniasm.1 of the reference for a detailed description of the command-line options.\n");
 }
 
+/* ---- MINIASM_B200_GPUS=N: one thread per GPU ------------------------------------------------------------------ */
+typedef struct {
+	int rank, world, device, bi_dir;
+	const ma_opt_t *opt;
+	const char *text;            /* this rank's byte range of the PAF */
+	size_t len;
+	const void *nccl_id;
+	mab_ctx_t *ctx;
+} rank_job_t;
+
+static void *rank_main(void *p)
+{
+	rank_job_t *j = (rank_job_t*)p;
+	j->ctx = mab_create(j->device);
+	mab_shard_init(j->ctx, j->rank, j->world, j->nccl_id);
+	mab_load_paf_text(j->ctx, j->text, j->len);
+	mab_ingest_sharded(j->ctx, j->opt->min_span, j->opt->min_match, j->bi_dir);
+	mab_select_sharded(j->ctx, j->opt);
+	mab_layout_sharded(j->ctx, j->opt);
+	return 0;
+}
+
+/* the whole PAF in host memory: plain files are mapped, gzip / stdin are inflated into a heap buffer */
+static char *slurp(const char *fn, size_t *len, int *mapped)
+{
+	unsigned char magic[2] = {0, 0};
+	int fd = strcmp(fn, "-") ? open(fn, O_RDONLY) : -1;
+	struct stat sb;
+	*mapped = 0;
+	if (fd >= 0 && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0 && pread(fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b)) {
+		char *m = (char*)mmap(0, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+		close(fd);
+		if (m != MAP_FAILED) { *len = (size_t)sb.st_size, *mapped = 1; return m; }
+		fd = -1;
+	}
+	if (fd >= 0) close(fd);
+	{
+		gzFile fp = strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(fileno(stdin), "r");
+		size_t n = 0, m = 1 << 24;
+		char *buf;
+		int r;
+		if (fp == 0) return 0;
+		gzbuffer(fp, 1 << 20);
+		buf = (char*)malloc(m);
+		while ((r = gzread(fp, buf + n, (unsigned)(m - n < (1u << 30) ? m - n : (1u << 30)))) > 0) {
+			n += (size_t)r;
+			if (n == m) buf = (char*)realloc(buf, m <<= 1);
+		}
+		gzclose(fp);
+		*len = n;
+		return buf;
+	}
+}
+
+/* steps 1-4 on `world` GPUs; returns rank 0's context (holding the same reduced graph a single GPU would) */
+static mab_ctx_t *run_sharded(const char *fn, const ma_opt_t *opt, int bi_dir, int world, int device0)
+{
+	char id[128];
+	size_t len = 0, cut[65];
+	int r, mapped = 0;
+	char *text = slurp(fn, &len, &mapped);
+	pthread_t tid[64];
+	rank_job_t job[64];
+	mab_ctx_t *ctx0;
+	if (text == 0) {
+		fprintf(stderr, "[E::%s] could not open PAF file %s\n", "ma_hit_read", fn);
+		exit(1);
+	}
+	cut[0] = 0;
+	for (r = 1; r < world; ++r) { /* byte ranges in rank order, each ending after a newline */
+		size_t p = len / world * r;
+		const char *q;
+		if (p < cut[r - 1]) p = cut[r - 1];
+		q = p < len ? (const char*)memchr(text + p, '\n', len - p) : 0;
+		cut[r] = q ? (size_t)(q - text) + 1 : len;
+	}
+	cut[world] = len;
+	mab_nccl_unique_id(id);
+	for (r = 0; r < world; ++r) {
+		job[r].rank = r, job[r].world = world, job[r].device = device0 + r, job[r].bi_dir = bi_dir, job[r].opt = opt;
+		job[r].text = text + cut[r], job[r].len = cut[r + 1] - cut[r], job[r].nccl_id = id, job[r].ctx = 0;
+		pthread_create(&tid[r], 0, rank_main, &job[r]);
+	}
+	for (r = 0; r < world; ++r) pthread_join(tid[r], 0);
+	if (mapped) munmap(text, len); else free(text);
+	ctx0 = job[0].ctx;
+	for (r = 1; r < world; ++r) mab_destroy(job[r].ctx);
+	return ctx0;
+}
+
 int main(int argc, char *argv[])
 {
 	ma_opt_t opt;
-	int i, c, stage = 100, no_first = 0, no_second = 0, bi_dir = 1, o_set = 0, no_cont = 0, device = 0;
+	int i, c, stage = 100, no_first = 0, no_second = 0, bi_dir = 1, o_set = 0, no_cont = 0, device = 0, n_gpus = 1, sharded_done = 0;
 	const char *fn_reads = 0, *outfmt = "ug", *env;
 	mab_ctx_t *ctx;
 	sdict_t *d = 0;
@@ -105,9 +202,23 @@ int main(int argc, char *argv[])
 
 	sys_init();
 	if ((env = getenv("MINIASM_B200_DEVICE")) != 0) device = atoi(env);
-	ctx = mab_create(device);
+	if ((env = getenv("MINIASM_B200_GPUS")) != 0) n_gpus = atoi(env);
+	if (n_gpus > 64) n_gpus = 64;
+	if (n_gpus > 1 && (no_cont || no_first || no_second || stage < 100 || fn_reads || (strcmp(outfmt, "ug") && strcmp(outfmt, "sg")))) {
+		fprintf(stderr, "[W::%s] MINIASM_B200_GPUS=%d covers the default pipeline (-p ug|sg without -R/-1/-2/-S/-f): running on one GPU\n", __func__, n_gpus);
+		n_gpus = 1;
+	}
+	if (n_gpus > 1) { /* steps 1-4 sharded; what follows (unitigs, output) runs on rank 0's context as in a single-GPU run */
+		fprintf(stderr, "[M::%s] ===> Step 1: reading read mappings <===\n", __func__);
+		fprintf(stderr, "[M::%s] ===> Step 2: 1-pass (crude) read selection <===\n", __func__);
+		fprintf(stderr, "[M::%s] ===> Step 3: 2-pass (fine) read selection <===\n", __func__);
+		fprintf(stderr, "[M::%s] ===> Step 4: graph cleaning <===\n", __func__);
+		ctx = run_sharded(argv[optind], &opt, bi_dir, n_gpus, device);
+		sharded_done = 1;
+	} else ctx = mab_create(device);
 
-	if (no_cont) { /* -R: the exclusion list is a host-side streaming pass; hits then come in through ma_hit_read */
+	if (sharded_done) {
+	} else if (no_cont) { /* -R: the exclusion list is a host-side streaming pass; hits then come in through ma_hit_read */
 		sdict_t *excl, *d0;
 		ma_hit_t *hit;
 		size_t n_hits;
@@ -127,9 +238,11 @@ int main(int argc, char *argv[])
 		mab_ingest(ctx, opt.min_span, opt.min_match, bi_dir);
 	}
 
-	if (!no_first) fprintf(stderr, "[M::%s] ===> Step 2: 1-pass (crude) read selection <===\n", __func__);
-	if (!no_second) fprintf(stderr, "[M::%s] ===> Step 3: 2-pass (fine) read selection <===\n", __func__);
-	mab_select(ctx, &opt, no_first, no_second, stage);
+	if (!sharded_done) {
+		if (!no_first) fprintf(stderr, "[M::%s] ===> Step 2: 1-pass (crude) read selection <===\n", __func__);
+		if (!no_second) fprintf(stderr, "[M::%s] ===> Step 3: 2-pass (fine) read selection <===\n", __func__);
+		mab_select(ctx, &opt, no_first, no_second, stage);
+	}
 
 	if (strcmp(outfmt, "bed") == 0) {
 		d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
@@ -141,10 +254,12 @@ int main(int argc, char *argv[])
 		if (sub) write_paf(n_hits, hit, d, sub);
 		free(hit);
 	} else if (strcmp(outfmt, "ug") == 0 || strcmp(outfmt, "sg") == 0) {
-		fprintf(stderr, "[M::%s] ===> Step 4: graph cleaning <===\n", __func__);
 		/* no -f: the GFA text is formatted on the GPU and copied down once (MAB_GPU_GFA=0: host structs + ma_ug_print) */
 		const int gpu_gfa = strcmp(outfmt, "ug") == 0 && !fn_reads && !((env = getenv("MAB_GPU_GFA")) != 0 && atoi(env) == 0);
-		mab_layout(ctx, &opt, stage);
+		if (!sharded_done) {
+			fprintf(stderr, "[M::%s] ===> Step 4: graph cleaning <===\n", __func__);
+			mab_layout(ctx, &opt, stage);
+		}
 		if (!gpu_gfa) d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
 		if (strcmp(outfmt, "ug") == 0) {
 			ma_ug_t *ug;

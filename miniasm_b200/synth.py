@@ -17,7 +17,9 @@ CONFIGS = {
     "c2_100k": "-n 100000 -s 2",
     "c3_1m": "-n 1000000 -s 3",
     "c4_4m": "-n 4000000 -s 4",
-    "c5_8m_skew": "-n 7750000 -s 5 -H 100 -R 2500 -W 8000",
+    # config 5: 8 M reads / 400 M overlaps, skewed: 7.98 M reads at 46.9x (~300 M lines) + 2 hot loci of 10 000 reads each
+    # (2 x 50 M pairwise lines; those reads have ~10 000 hits and slabs of ~5 000 arcs per vertex)
+    "c5_8m_skew": "-n 7980000 -c 46.9 -s 5 -H 2 -R 10000 -W 8000",
     # E. coli-shaped stand-in for config 1 (4.6 Mb, ~30x, variable read length, noisy ends)
     "c1_ecoli_like": "-n 13800 -l 4000 -L 16000 -c 30 -j 200 -s 1",
     # small parity sets: exact, jittered, containment-heavy, tips+bubbles, everything at once

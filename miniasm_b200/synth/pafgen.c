@@ -29,6 +29,9 @@ typedef struct {
 	uint32_t shuffle;        /* shuffle line order */
 	uint32_t flip_ppm;       /* per-million chance to swap q/t role is fixed at 50%; this adds CR line ends */
 	uint32_t name_base;      /* added to every read number: disjoint names for the partitions of a multi-GPU run */
+	uint32_t part, n_parts;  /* n_parts > 1: emit only part `part` of the PAF -- the lines whose first read (in genomic order) has index
+	                          * in [n*part/n_parts, n*(part+1)/n_parts).  The parts, concatenated in order, are the bytes of the whole
+	                          * PAF: the random stream does not depend on what is emitted.  Not with `shuffle`. */
 } pafgen_opt_t;
 
 typedef struct { uint64_t n_lines, n_bytes, genome_len; uint32_t n_reads_total; } pafgen_stat_t;
@@ -93,7 +96,7 @@ static void emit(sbuf_t *b, const rd_t *q, const rd_t *t, uint32_t qs, uint32_t 
 size_t pafgen_generate(const pafgen_opt_t *o, char **out, pafgen_stat_t *st)
 {
 	uint64_t rng = o->seed * 0x2545F4914F6CDD1DULL + 0x1234567ULL, G;
-	uint32_t n = o->n_reads + o->n_hot * o->hot_reads, i, j, k;
+	uint32_t n = o->n_reads + o->n_hot * o->hot_reads, i, j, k, part_lo, part_hi;
 	double mean_len = 0.5 * ((double)o->len_min + o->len_max);
 	rd_t *r = (rd_t*)malloc((size_t)n * sizeof(rd_t));
 	uint32_t *perm = (uint32_t*)malloc((size_t)n * 4);
@@ -123,14 +126,21 @@ size_t pafgen_generate(const pafgen_opt_t *o, char **out, pafgen_stat_t *st)
 	free(perm);
 	qsort(r, n, sizeof(rd_t), cmp_rd);
 
+	if (o->n_parts > 1) part_lo = (uint32_t)((uint64_t)n * o->part / o->n_parts), part_hi = (uint32_t)((uint64_t)n * (o->part + 1) / o->n_parts);
+	else part_lo = 0, part_hi = n;
 	for (i = 0; i < n; ++i) {
 		uint64_t ei = r[i].start + r[i].len;
+		const int mine = i >= part_lo && i < part_hi;
+		if (i >= part_hi && !o->shuffle) break; /* nothing of the later reads belongs to this part */
 		if (o->self_ppm && rnd_below(&rng, 1000000) < o->self_ppm) { /* self hit: a palindromic-looking or shifted one */
 			uint32_t w = r[i].len / 2;
-			if (o->shuffle) { if (n_lines == line_m) { line_m = line_m ? line_m * 2 : 1024; line_off = (uint64_t*)realloc(line_off, line_m * 8); } line_off[n_lines] = b.l; }
-			if (sm64(&rng) & 1) { rd_t t = r[i]; t.rev = !t.rev; emit(&b, &r[i], &t, 100, 100 + w, 100, 100 + w, 0, 0); }
-			else emit(&b, &r[i], &r[i], 0, w, r[i].len - w, r[i].len, 0, 0);
-			++n_lines;
+			const int pal = sm64(&rng) & 1;
+			if (mine) {
+				if (o->shuffle) { if (n_lines == line_m) { line_m = line_m ? line_m * 2 : 1024; line_off = (uint64_t*)realloc(line_off, line_m * 8); } line_off[n_lines] = b.l; }
+				if (pal) { rd_t t = r[i]; t.rev = !t.rev; emit(&b, &r[i], &t, 100, 100 + w, 100, 100 + w, 0, 0); }
+				else emit(&b, &r[i], &r[i], 0, w, r[i].len - w, r[i].len, 0, 0);
+				++n_lines;
+			}
 		}
 		for (j = i + 1; j < n && r[j].start + o->min_olap <= ei; ++j) {
 			uint64_t a = r[j].start, e = ei < r[j].start + r[j].len ? ei : r[j].start + r[j].len;
@@ -153,8 +163,10 @@ size_t pafgen_generate(const pafgen_opt_t *o, char **out, pafgen_stat_t *st)
 			else to_local(q, a2, e2, &qs, &qe), to_local(t, a1, e1, &ts, &te);
 			dup = (o->dup_ppm && rnd_below(&rng, 1000000) < o->dup_ppm) ? 2 : 1;
 			while (dup--) {
+				const int cr = o->flip_ppm && rnd_below(&rng, 1000000) < o->flip_ppm;
+				if (!mine) continue;
 				if (o->shuffle) { if (n_lines == line_m) { line_m = line_m ? line_m * 2 : 1024; line_off = (uint64_t*)realloc(line_off, line_m * 8); } line_off[n_lines] = b.l; }
-				emit(&b, q, t, qs, qe, ts, te, lowid, o->flip_ppm && rnd_below(&rng, 1000000) < o->flip_ppm);
+				emit(&b, q, t, qs, qe, ts, te, lowid, cr);
 				++n_lines;
 			}
 		}
@@ -195,7 +207,7 @@ int main(int argc, char *argv[])
 	size_t len;
 	int c;
 	pafgen_defaults(&o);
-	while ((c = getopt(argc, argv, "n:l:L:c:m:j:s:H:R:W:d:S:I:D:xC:B:")) >= 0) {
+	while ((c = getopt(argc, argv, "n:l:L:c:m:j:s:H:R:W:d:S:I:D:xC:B:P:")) >= 0) {
 		if (c == 'n') o.n_reads = strtoul(optarg, 0, 10);
 		else if (c == 'l') o.len_min = atoi(optarg);
 		else if (c == 'L') o.len_max = atoi(optarg);
@@ -213,8 +225,10 @@ int main(int argc, char *argv[])
 		else if (c == 'C') o.flip_ppm = atoi(optarg);
 		else if (c == 'x') o.shuffle = 1;
 		else if (c == 'B') o.name_base = strtoul(optarg, 0, 10);
+		else if (c == 'P') { char *e; o.part = strtoul(optarg, &e, 10); o.n_parts = *e == '/' ? strtoul(e + 1, 0, 10) : 1; }
 	}
 	if (o.len_max < o.len_min) o.len_max = o.len_min;
+	if (o.n_parts > 1 && (o.shuffle || o.part >= o.n_parts)) { fprintf(stderr, "pafgen: -P part/parts needs part < parts and no -x\n"); return 1; }
 	len = pafgen_generate(&o, &buf, &st);
 	fwrite(buf, 1, len, stdout);
 	fprintf(stderr, "[pafgen] reads=%u genome=%lu lines=%lu bytes=%lu\n", st.n_reads_total, (unsigned long)st.genome_len,

@@ -4,7 +4,7 @@
 tests/golden/configs.json.  The inputs are not stored (GBs): (pafgen options, sha256 of the PAF) identify them, and
 the GPU tests regenerate the same bytes in memory (tests/test_configs_gpu.py).
 
-usage: python tests/golden/make_golden_configs.py [c2_100k c3_1m c4_4m]      (c3 needs ~10 GB RAM / 2 min, c4 ~45 GB / 10 min)
+usage: python tests/golden/make_golden_configs.py [c2_100k c3_1m c4_4m]      (c3 needs ~10 GB RAM / 2 min, c4 ~25 GB / 7 min, c5 ~45 GB / 20 min)
 """
 import hashlib
 import json

@@ -1,5 +1,6 @@
 """One rank of the sharded parity run (launched by tests/test_shard_gpu.py through torch.distributed.run).
-argv: paf_path|gen:<n_reads>:<seed> out_gfa_path      (gen: = the PAF of a BASELINE config generated in memory on every rank)"""
+argv: paf_path|gen:<workload name of bench.WORKLOADS> out_gfa_path
+(gen: = ONE PAF of a BASELINE config cut into `world` parts in file order; every rank generates only its own part)"""
 import ctypes as C
 import os
 import sys
@@ -21,24 +22,29 @@ def main():
     ctx = lib.mab_create(local)
     sharded.init(lib, ctx, rank, world)
     if paf.startswith("gen:"):
-        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         import bench
-        _, n_reads, seed = paf.split(":")
-        buf, n_bytes, _, free = bench.generate(int(n_reads), int(seed))
-        data = C.string_at(buf, n_bytes)
+        buf, n_bytes, _, free = bench.generate_args(bench.WORKLOADS[paf[4:]]["args"], rank, world)
+        lib.mab_load_paf_text(ctx, buf, n_bytes)           # (synchronises: the host copy can go)
         free()
     else:
         data = open(paf, "rb").read()
-    b, e = sharded.split_ranges(data, world)[rank]
-    part = data[b:e]
-    lib.mab_load_paf_text(ctx, part, len(part))
+        b, e = sharded.split_ranges(data, world)[rank]
+        part = data[b:e]
+        lib.mab_load_paf_text(ctx, part, len(part))
     opt = lib.default_opt()
     sharded.run(lib, ctx, opt)
     if rank == 0:
-        d, sub, ug = lib.mab_export_dict(ctx), lib.mab_export_sub(ctx), lib.mab_export_ug(ctx)
-        text = lib.print_to_string("ma_ug_print", ug, d, sub)
-        with open(out, "wb") as f:
-            f.write(text)
+        st = lib.mab_stats(ctx).contents
+        print(f"[shard_worker] world {world}: {st.n_lines} lines on rank 0, {st.n_seq_final} reads kept, {st.n_reduced} arcs reduced, {st.n_utg} unitigs", flush=True)
+        if os.environ.get("MAB_GPU_GFA") == "0":           # host structs + the host writer
+            d, sub, ug = lib.mab_export_dict(ctx), lib.mab_export_sub(ctx), lib.mab_export_ug(ctx)
+            text = lib.print_to_string("ma_ug_print", ug, d, sub)
+            with open(out, "wb") as f:
+                f.write(text)
+        else:                                              # the GFA text formatted on the GPU (what the CLI prints)
+            fp = capi._libc.fopen(out.encode(), b"w")
+            lib.mab_write_gfa(ctx, fp)
+            capi._libc.fclose(fp)
     dist.barrier()
     lib.mab_destroy(ctx)
     dist.destroy_process_group()

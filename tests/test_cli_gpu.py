@@ -85,6 +85,39 @@ def test_gzip_and_stdin(pafs, paf_dir):
     assert rc == 0 and out == plain
 
 
+def _counters(err):
+    """The reference's [M::...] progress lines with the timestamps masked (sys_timestamp: "::<real>*<cpu ratio>")."""
+    import re
+    out = []
+    for ln in err.decode().splitlines():
+        if not ln.startswith("[M::") or ln.startswith(("[M::main] Version", "[M::main] CMD", "[M::main] Real time")):
+            continue
+        out.append(re.sub(r"::\d+\.\d+\*\d+\.\d+\]", "]", ln))
+    return out
+
+
+@pytest.mark.parametrize("name", ["chaos_small", "chaos", "bubbles800", "tiny_exact"])
+@pytest.mark.parametrize("opts", [[], ["-c", "2", "-e", "2"], ["-R"]], ids=["default", "c2e2", "R"])
+def test_stderr_counters(name, opts, pafs):
+    """SURVEY.md section 5: the [M::...] lines carry the counts of every step (hits stored, reads kept, arcs reduced, tips cut,
+    bubbles popped ...) and are reproduced verbatim."""
+    _, _, err_r = run(REF, opts + [pafs[name]])
+    _, _, err_c = run(CLI, opts + [pafs[name]])
+    assert _counters(err_c) == _counters(err_r)
+
+
+def test_bubble_dense_300k(paf_dir):
+    """300 K reads with jittered ends: 3 713 bubbles popped along genome-ordered ids (the set on which one-commit-per-round
+    schemes crawl); output bytes and every stderr counter against the reference."""
+    paf = synth.generate("-n 300000 -l 9000 -L 11000 -j 800 -c 30 -s 15", os.path.join(paf_dir, "bub300k.paf"))
+    rc_r, out_r, err_r = run(REF, [paf])
+    rc_c, out_c, err_c = run(CLI, [paf])
+    assert rc_c == rc_r == 0, err_c.decode()[-2000:]
+    assert out_c == out_r
+    assert _counters(err_c) == _counters(err_r)
+    assert any("popped 3713 bubbles" in x for x in _counters(err_c))
+
+
 def test_version_usage_and_missing_file(pafs):
     assert run(CLI, ["-V"])[:2] == run(REF, ["-V"])[:2]
     rc, out, err = run(CLI, [])

@@ -8,6 +8,8 @@ import pytest
 from miniasm_b200 import capi, synth
 from miniasm_b200.pipeline import Pipeline
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 class PafRec(C.Structure):                                   # paf_rec_t, paf.h:20-24
     _fields_ = [("qn", C.c_char_p), ("tn", C.c_char_p), ("ql", C.c_uint32), ("qs", C.c_uint32), ("qe", C.c_uint32),
@@ -93,6 +95,36 @@ def test_writers_and_ug_seq_against_reference(built, ref, paf_dir):
         assert prod.print_to_string("ma_sg_print", b.sg, b.d, b.sub) == a.sg_text()
         assert prod.print_to_string("ma_sg_print", b.sg, b.d, None) == ref.print_to_string("ma_sg_print", a.sg, a.d, None)
         a.free(), b.free()
+
+
+@pytest.mark.skipif(not os.path.exists(capi.REFERENCE_SO), reason="oracle/_ref not built")
+def test_ug_seq_refuses_a_short_record(built, paf_dir):
+    """asm.c:263 asserts that a record covers the interval the layout keeps; ours must not read past a shorter record either
+    (a reads file that does not belong to the PAF): message + abort, in a child process."""
+    import subprocess
+    import sys
+    code = f"""
+import sys, os
+sys.path.insert(0, {ROOT!r})
+from miniasm_b200 import capi, synth
+from miniasm_b200.pipeline import Pipeline
+ref = capi.load_reference(); ref.set_verbose(0)
+prod = capi.load_product(); prod.set_verbose(0)
+paf = synth.generate("tiny_exact", {paf_dir!r} + "/short.paf")
+b = Pipeline(ref, paf).read().select().sg_gen().clean().ug_gen()
+names = b.names()
+with open({paf_dir!r} + "/short.fa", "w") as f:
+    for nm in names:
+        f.write(">" + nm.decode() + "\\nACGTACGTAC\\n")          # 10 bases where the layout needs thousands
+d2 = prod.sd_init()
+for i, nm in enumerate(names):
+    prod.sd_put(d2, nm, b.d.contents.seq[i].len)
+prod.ma_ug_seq(b.ug, d2, b.sub, ({paf_dir!r} + "/short.fa").encode())
+print("survived")
+"""
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode != 0 and "survived" not in r.stdout
+    assert "[E::ma_ug_seq]" in r.stderr and "wrong reads file" in r.stderr
 
 
 @pytest.mark.skipif(not os.path.exists(capi.REFERENCE_SO), reason="oracle/_ref not built")

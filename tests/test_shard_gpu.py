@@ -38,12 +38,14 @@ def test_sharded_gfa_equals_reference(name, world, built, paf_dir):
     assert open(out, "rb").read() == want
 
 
+FULL = [("c3_1m", 2), ("c3_1m", 8), ("c4_4m", 2), ("c4_4m", 4), ("c5_8m_skew", 8)]
+
+
 @pytest.mark.skipif(n_gpus() < 2 or os.environ.get("MAB_TEST_FULL") != "1", reason="needs >= 2 GPUs and MAB_TEST_FULL=1 (minutes)")
-@pytest.mark.parametrize("name,n_reads,seed", [("c3_1m", 1_000_000, 3), ("c4_4m", 4_000_000, 4)])
-@pytest.mark.parametrize("world", [w for w in (2, 4, 8) if w <= n_gpus()] or [2])
-def test_sharded_full_config_digest(name, n_reads, seed, world, built, paf_dir):
-    """BASELINE configs 3 / 4 (1 M / 4 M reads) hash-sharded over `world` GPUs: the GFA must have the sha256 of the
-    reference's GFA for the same PAF (tests/golden/configs.json)."""
+@pytest.mark.parametrize("name,world", [c for c in FULL if c[1] <= max(n_gpus(), 2)])
+def test_sharded_full_config_digest(name, world, built, paf_dir):
+    """BASELINE configs 3 / 4 / 5 (1 M / 4 M / 8 M reads, the last one skewed) as ONE PAF cut into `world` parts, hash-sharded
+    over `world` GPUs: the GFA must have the sha256 of the reference's GFA for the same PAF (tests/golden/configs.json)."""
     import hashlib
     import json
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "configs.json")))
@@ -51,9 +53,13 @@ def test_sharded_full_config_digest(name, n_reads, seed, world, built, paf_dir):
         pytest.skip(f"no golden digest for {name}")
     out = f"{paf_dir}/shfull_{name}_{world}.gfa"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29534", os.path.join(ROOT, "tests", "shard_worker.py"), f"gen:{n_reads}:{seed}", out]
+           "--master-port", "29534", os.path.join(ROOT, "tests", "shard_worker.py"), f"gen:{name}", out]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1800)
     assert r.returncode == 0, r.stdout[-3000:]
-    got = open(out, "rb").read()
+    h = hashlib.sha256()
+    with open(out, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 24), b""):
+            h.update(blk)
+    size = os.path.getsize(out)
     os.unlink(out)
-    assert len(got) == gold[name]["gfa_bytes"] and hashlib.sha256(got).hexdigest() == gold[name]["gfa_sha256"]
+    assert size == gold[name]["gfa_bytes"] and h.hexdigest() == gold[name]["gfa_sha256"]
