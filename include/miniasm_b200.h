@@ -163,7 +163,9 @@ const mab_stats_t *mab_stats(const mab_ctx_t *ctx);
 int mab_load_paf_text(mab_ctx_t *ctx, const char *text, size_t len);
 int mab_load_paf_file(mab_ctx_t *ctx, const char *fn);  /* -1 if the file cannot be opened */
 int mab_ingest(mab_ctx_t *ctx, int min_span, int min_match, int bi_dir);
-/* alternative to load+ingest: hits and dictionary produced by ma_hit_read (needed for the -R exclusion list) */
+/* -R: ma_hit_no_cont (hit.c:38-68) + ma_hit_read with its exclusion list (hit.c:86) as one pass over the resident text */
+int mab_ingest_nocont(mab_ctx_t *ctx, int min_span, int min_match, int bi_dir, int max_hang, float int_frac);
+/* alternative to load+ingest: hits and dictionary produced by the drop-in ma_hit_read (host arrays) */
 int mab_load_hits(mab_ctx_t *ctx, const ma_hit_t *a, size_t n, const sdict_t *dict);
 
 /* Steps 2-3, main.c:119-142 (ma_hit_sub/cut/flt/sub_merge/contained).  stage = the reference's -S. */
@@ -184,6 +186,14 @@ float mab_coverage(const mab_ctx_t *ctx);
  * unitig sequences, formatted on the GPU and written with one fwrite: no host copies of the tables.  Returns the number
  * of bytes written, -1 before mab_unitigs.  (Experimental in round 1: the CLI uses it only with MAB_GPU_GFA=1.) */
 long mab_write_gfa(mab_ctx_t *ctx, FILE *fp);
+/* -f reads: ma_ug_seq (asm.c:236-290) + ma_ug_print on the GPU.  mab_reads_prefetch starts streaming the FASTA/FASTQ file (plain
+ * or gzip, "-" = stdin) into HBM on a thread and stream of its own -- call it before mab_ingest and the copy hides behind the
+ * graph stages.  mab_write_gfa_reads indexes the records in HBM (line starts, headers, a name table of the layout's reads),
+ * gathers / reverse-complements the bases straight into the S lines of the GFA text and writes it.  Returns the bytes written;
+ * -1 before mab_unitigs; -2 (nothing written) when the file is neither FASTA-like nor 4-line FASTQ -- multi-line FASTQ cannot be
+ * cut into records in parallel -- in which case the caller uses mab_export_* + ma_ug_seq + ma_ug_print. */
+int mab_reads_prefetch(mab_ctx_t *ctx, const char *fn);
+long mab_write_gfa_reads(mab_ctx_t *ctx, FILE *fp, const char *fn_reads);
 
 /* Hash-sharded multi-GPU run (one process per GPU, read r owned by rank r mod world, NCCL on the context's stream).
  * rank 0: mab_nccl_unique_id -> launcher broadcasts the bytes -> every rank: mab_shard_init.  Each rank loads ITS byte

@@ -146,6 +146,7 @@ _PRODUCT_ONLY = {
     "mab_load_paf_text": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mab_load_paf_file": (C.c_int, [C.c_void_p, C.c_char_p]),
     "mab_ingest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mab_ingest_nocont": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "mab_load_hits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Sdict)]),
     "mab_select": (C.c_int, [C.c_void_p, C.POINTER(MaOpt), C.c_int, C.c_int, C.c_int]),
     "mab_layout": (C.c_int, [C.c_void_p, C.POINTER(MaOpt), C.c_int]),
@@ -157,6 +158,8 @@ _PRODUCT_ONLY = {
     "mab_export_ug": (C.POINTER(MaUg), [C.c_void_p]),
     "mab_coverage": (C.c_float, [C.c_void_p]),
     "mab_write_gfa": (C.c_long, [C.c_void_p, C.c_void_p]),
+    "mab_reads_prefetch": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mab_write_gfa_reads": (C.c_long, [C.c_void_p, C.c_void_p, C.c_char_p]),
     "mab_event_create": (C.c_void_p, []),
     "mab_event_record": (None, [C.c_void_p, C.c_void_p]),
     "mab_event_elapsed_ms": (C.c_float, [C.c_void_p, C.c_void_p]),

@@ -6,6 +6,8 @@
 #include "hit_dev.cuh"
 #include "clean_dev.cuh"
 #include "gfa_dev.cuh"
+#include "ugseq_dev.cuh"
+#include <pthread.h>
 #include "ingest_dev.cuh"
 #include "shard_comm.cuh"
 #include <cub/cub.cuh>
@@ -43,6 +45,14 @@ struct mab_ctx {
 	std::map<std::string, void*> ipc_open;   // peer segments mapped through CUDA IPC (handle bytes -> local address)
 	char *h_gfa = nullptr;    // pinned landing buffer of mab_write_gfa (grow-only)
 	size_t h_gfa_cap = 0;
+	// -f reads: the file streams into HBM on its own thread and stream while the graph stages run (mab_reads_prefetch)
+	struct ReadsLoad {
+		pthread_t tid; bool started = false, joined = false;
+		std::string fn;
+		int device = 0, rc = 0;
+		char *d_text = nullptr;  // cudaMalloc'd by the loader thread (not the arena: that one belongs to the context's own thread)
+		size_t len = 0, cap = 0;
+	} rl;
 };
 
 __global__ void k_sg_len(uint32_t n, const DSub *sub, const uint32_t *slen, const uint32_t *orig, uint32_t *len, uint8_t *del)
@@ -88,6 +98,7 @@ struct PhaseTimer { // CUDA-event stopwatch around one step of the fused API (+ 
 };
 
 extern "C" { static void layout_tail(mab_ctx *c, const ma_opt_t *opt, int stage); }
+extern "C" { static void reads_drop(mab_ctx *c); }
 
 static void ctx_drop_graphs(mab_ctx *c)
 {
@@ -130,6 +141,7 @@ void mab_destroy(mab_ctx_t *c)
 	for (int i = 0; i < 2; ++i) if (c->pin[i]) MAB_CUDA(cudaFreeHost(c->pin[i]));
 	for (auto &kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
 	if (c->h_gfa) MAB_CUDA(cudaFreeHost(c->h_gfa));
+	reads_drop(c);
 	d.destroy();
 	delete c;
 }
@@ -226,6 +238,26 @@ int mab_ingest(mab_ctx_t *c, int min_span, int min_match, int bi_dir)
 	return 0;
 }
 
+/* -R (main.c:110-113 + hit.c:38-68,86): Step 0 and Step 1 in one pass over the text that is already in HBM.  Prints the
+ * reference's two log lines and its Step-1 banner in the reference's order. */
+int mab_ingest_nocont(mab_ctx_t *c, int min_span, int min_match, int bi_dir, int max_hang, float int_frac)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	PhaseTimer pt(d, &c->stats.ms_ingest, "mab_ingest_nocont");
+	ctx_reset_reads(c);
+	NoContParams nc = { max_hang, int_frac };
+	ingest_paf(d, c->d_text, c->text_len, min_span, min_match, bi_dir, c->hits, c->names, c->ist, &nc);
+	c->n_seq = c->names.n_seq;
+	c->stats.n_lines = c->ist.n_parsed, c->stats.n_hits_stored = c->ist.n_hits, c->stats.n_seq_in = c->ist.n_seq;
+	if (!mab_mute && ma_verbose >= 3) fprintf(stderr, "[M::%s::%s] dropped %d contained reads\n", "ma_hit_no_cont", sys_timestamp(), (int)c->ist.n_dropped);
+	if (!mab_mute) fprintf(stderr, "[M::main] ===> Step 1: reading read mappings <===\n");
+	if (!mab_mute && ma_verbose >= 3)
+		fprintf(stderr, "[M::%s::%s] read %ld hits; stored %ld hits and %d sequences (%ld bp)\n", "ma_hit_read", sys_timestamp(),
+				(long)c->ist.n_parsed, (long)c->ist.n_hits, (int)c->ist.n_seq, (long)c->ist.tot_len);
+	return 0;
+}
+
 /* Alternative to mab_ingest: hits parsed elsewhere (e.g. ma_hit_read with an exclusion dictionary, -R) */
 int mab_load_hits(mab_ctx_t *c, const ma_hit_t *a, size_t n, const sdict_t *dict)
 {
@@ -275,6 +307,7 @@ int mab_select(mab_ctx_t *c, const ma_opt_t *opt, int no_first, int no_second, i
 	PhaseTimer pt(d, &c->stats.ms_select, "mab_select");
 	ctx_drop_graphs(c);
 	if (!no_first) {
+		if (!mab_mute && ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 2: 1-pass (crude) read selection <===\n");
 		if (stage >= 2) {
 			d.free(c->sub);
 			c->sub = mab_alloc<DSub>(d, c->n_seq);
@@ -287,6 +320,7 @@ int mab_select(mab_ctx_t *c, const ma_opt_t *opt, int no_first, int no_second, i
 		}
 	}
 	if (!no_second) {
+		if (!mab_mute && ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 3: 2-pass (fine) read selection <===\n");
 		if (stage >= 4) {
 			DSub *sub2 = mab_alloc<DSub>(d, c->n_seq);
 			d.trace("select:flt");
@@ -516,6 +550,117 @@ long mab_write_gfa(mab_ctx_t *c, FILE *fp)
 	}
 	d.free(d_txt);
 	d.sync();
+	return (long)n;
+}
+
+/* ---- -f reads (ma_ug_seq, asm.c:236-290) ------------------------------------------------------------------------------- */
+static void *reads_loader(void *p) // file -> pinned double buffer -> HBM, on a stream of its own
+{
+	mab_ctx::ReadsLoad *rl = (mab_ctx::ReadsLoad*)p;
+	const size_t CH = 32u << 20;
+	cudaStream_t st;
+	char *pin[2];
+	cudaEvent_t ev[2];
+	MAB_CUDA(cudaSetDevice(rl->device));
+	gzFile fp = rl->fn != "-" ? gzopen(rl->fn.c_str(), "r") : gzdopen(fileno(stdin), "r");
+	if (fp == 0) { rl->rc = -1; return 0; }
+	gzbuffer(fp, 1 << 20);
+	MAB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; ++i) { MAB_CUDA(cudaMallocHost(&pin[i], CH)); MAB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
+	struct stat sb;
+	size_t guess = 0;
+	if (rl->fn != "-" && stat(rl->fn.c_str(), &sb) == 0) guess = (size_t)sb.st_size;
+	rl->cap = (guess ? guess : CH) + 4096;
+	MAB_CUDA(cudaMalloc(&rl->d_text, rl->cap));
+	for (int k = 0;; k ^= 1) {
+		MAB_CUDA(cudaEventSynchronize(ev[k]));
+		size_t got = 0;
+		while (got < CH) {
+			int r = gzread(fp, pin[k] + got, (unsigned)(CH - got));
+			if (r <= 0) break;
+			got += (size_t)r;
+		}
+		if (got == 0) break;
+		if (rl->len + got + 64 > rl->cap) { // compressed input: grow, keeping what is there
+			size_t ncap = (rl->len + got) * 2 + 4096;
+			char *nt;
+			MAB_CUDA(cudaStreamSynchronize(st));
+			MAB_CUDA(cudaMalloc(&nt, ncap));
+			if (rl->len) MAB_CUDA(cudaMemcpyAsync(nt, rl->d_text, rl->len, cudaMemcpyDeviceToDevice, st));
+			MAB_CUDA(cudaStreamSynchronize(st));
+			MAB_CUDA(cudaFree(rl->d_text));
+			rl->d_text = nt, rl->cap = ncap;
+		}
+		MAB_CUDA(cudaMemcpyAsync(rl->d_text + rl->len, pin[k], got, cudaMemcpyHostToDevice, st));
+		MAB_CUDA(cudaEventRecord(ev[k], st));
+		rl->len += got;
+		if (got < CH) break;
+	}
+	MAB_CUDA(cudaStreamSynchronize(st));
+	gzclose(fp);
+	for (int i = 0; i < 2; ++i) { MAB_CUDA(cudaFreeHost(pin[i])); MAB_CUDA(cudaEventDestroy(ev[i])); }
+	MAB_CUDA(cudaStreamDestroy(st));
+	return 0;
+}
+
+static void reads_drop(mab_ctx *c)
+{
+	if (c->rl.started && !c->rl.joined) pthread_join(c->rl.tid, 0);
+	if (c->rl.d_text) cudaFree(c->rl.d_text);
+	c->rl = mab_ctx::ReadsLoad();
+}
+
+/* Start streaming the reads file (FASTA/FASTQ, plain or gzip, "-" = stdin) into HBM in the background; call it before
+ * mab_ingest so that the copy hides behind the graph stages.  Optional: mab_write_gfa_reads loads the file itself otherwise. */
+int mab_reads_prefetch(mab_ctx_t *c, const char *fn)
+{
+	reads_drop(c);
+	c->rl.fn = fn, c->rl.device = c->dev.device;
+	if (pthread_create(&c->rl.tid, 0, reads_loader, &c->rl) != 0) return -1;
+	c->rl.started = true;
+	return 0;
+}
+
+/* ma_ug_seq + ma_ug_print (asm.c:236-290, 77-116): the GFA with unitig sequences, formatted and filled on the GPU.  Returns the
+ * bytes written; -1 before mab_unitigs; -2 when the reads file is not in a layout the parallel parser proves (nothing is
+ * written: the caller falls back to mab_export_* + ma_ug_seq + ma_ug_print).  A file that cannot be opened gives the GFA
+ * without sequences, as the reference does (main.c:193 ignores the return value). */
+long mab_write_gfa_reads(mab_ctx_t *c, FILE *fp, const char *fn_reads)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	if (!c->have_ug) return -1;
+	MabDev &d = c->dev;
+	if (!c->rl.started || c->rl.fn != fn_reads) mab_reads_prefetch(c, fn_reads);
+	if (!c->rl.joined) { pthread_join(c->rl.tid, 0); c->rl.joined = true; }
+	if (c->rl.rc < 0) { reads_drop(c); return mab_write_gfa(c, fp); }
+	DReadsIndex ix;
+	const int rc = dg_reads_index(d, c->rl.d_text, c->rl.len, ix);
+	if (rc == UGSEQ_UNSUPPORTED) { dg_reads_free(d, ix); reads_drop(c); return -2; }
+	if (!c->ug.g.has_idx) dg_arc_index(d, c->ug.g);
+	uint64_t *seq_pos = mab_alloc<uint64_t>(d, c->ug.n_utg);
+	uint32_t *ioff = nullptr;
+	char *d_txt = nullptr;
+	const char *ntext = c->name_text ? c->name_text : c->d_text;
+	const size_t n = dg_gfa_text(d, c->ug, c->orig_id, c->names.off, c->names.nlen, ntext, c->sub, &d_txt, seq_pos, &ioff);
+	if (n) {
+		const int gr = dg_ugseq_fill(d, c->rl.d_text, c->rl.len, ix, c->ug, ioff, c->n_seq, c->orig_id, c->names.off, c->names.nlen, ntext, c->sub, seq_pos, d_txt);
+		if (gr == UGSEQ_SHORT_RECORD) { // asm.c:263 asserts it
+			fprintf(stderr, "[E::ma_ug_seq] a record of '%s' is shorter than the interval the layout keeps of it: wrong reads file?\n", fn_reads);
+			abort();
+		}
+		if (n > c->h_gfa_cap) {
+			if (c->h_gfa) MAB_CUDA(cudaFreeHost(c->h_gfa));
+			c->h_gfa_cap = n + (n >> 2) + (1 << 20);
+			MAB_CUDA(cudaHostAlloc((void**)&c->h_gfa, c->h_gfa_cap, cudaHostAllocDefault));
+		}
+		MAB_CUDA(cudaMemcpyAsync(c->h_gfa, d_txt, n, cudaMemcpyDeviceToHost, d.stream));
+		d.sync();
+		if (fwrite(c->h_gfa, 1, n, fp) != n) { fprintf(stderr, "[E::miniasm_b200] short write of the GFA text\n"); exit(74); }
+	}
+	d.free(d_txt); d.free(ioff); d.free(seq_pos);
+	dg_reads_free(d, ix);
+	d.sync();
+	reads_drop(c);
 	return (long)n;
 }
 

@@ -24,17 +24,21 @@ struct GfaView {
 	uint32_t n_utg; uint64_t n_items;
 	const DArc *uarc; uint32_t n_uarc; const uint64_t *uidx;
 	const uint32_t *orig; const uint64_t *noff; const uint32_t *nlen; const char *text; const DSub *sub;
+	uint64_t *seq_pos;             // non-null: S lines reserve `len` bytes for the unitig sequence; seq_pos[i] = where (filled by the write pass)
+	const char *out_base;
 };
 
 struct CountSink {
 	uint32_t n;
 	__host__ __device__ __forceinline__ void c(char) { ++n; }
 	__host__ __device__ __forceinline__ void bytes(const char *, uint32_t l) { n += l; }
+	__host__ __device__ __forceinline__ void hole(uint32_t l, uint64_t *, const char *) { n += l; }
 };
 struct WriteSink {
 	char *p;
 	__host__ __device__ __forceinline__ void c(char ch) { *p++ = ch; }
 	__host__ __device__ __forceinline__ void bytes(const char *s, uint32_t l) { for (uint32_t k = 0; k < l; ++k) p[k] = s[k]; p += l; }
+	__host__ __device__ __forceinline__ void hole(uint32_t l, uint64_t *where, const char *base) { *where = (uint64_t)(p - base); p += l; } // left as the buffer was pre-filled
 };
 
 template <class Sink> __host__ __device__ __forceinline__ void put_dec(Sink &s, uint32_t x, int min_digits)
@@ -82,7 +86,9 @@ template <class Sink> __host__ __device__ void emit_record(const GfaView &v, uin
 		const DUtgMeta m = v.meta[i];
 		const uint64_t j = rec - ((uint64_t)i + m.first);
 		if (j == 0) {
-			s.c('S'); s.c('\t'); put_utg(s, i, m.circ != 0); s.c('\t'); s.c('*'); put_lit(s, "\tLN:i:", 6); put_int(s, (int32_t)m.len); s.c('\n');
+			s.c('S'); s.c('\t'); put_utg(s, i, m.circ != 0); s.c('\t');
+			if (v.seq_pos) s.hole(m.len, v.seq_pos + i, v.out_base); else s.c('*');       // asm.c:83: u->s or "*"
+			put_lit(s, "\tLN:i:", 6); put_int(s, (int32_t)m.len); s.c('\n');
 			if (m.circ)
 				for (int k = 0; k < 2; ++k) {
 					s.c('L'); s.c('\t'); put_utg(s, i, true); s.c('\t'); s.c(k ? '-' : '+'); s.c('\t');
@@ -128,6 +134,7 @@ __global__ void k_gfa_count(GfaView v, uint64_t n_rec, uint32_t *len)
 
 __global__ void k_gfa_write(GfaView v, uint64_t n_rec, const uint64_t *pos, char *out)
 {
+	v.out_base = out;
 	for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n_rec; r += (uint64_t)gridDim.x * blockDim.x) {
 		WriteSink s{out + pos[r]};
 		emit_record(v, r, s);
@@ -139,9 +146,10 @@ struct U32ToU64 { __host__ __device__ __forceinline__ uint64_t operator()(uint32
 
 // Formats the GFA into a fresh device buffer (*d_text_out, caller frees through d.free); returns its size in bytes.
 size_t dg_gfa_text(MabDev &d, const DUnitigs &ug, const uint32_t *orig, const uint64_t *noff, const uint32_t *nlen, const char *name_text,
-                   const DSub *sub, char **d_text_out)
+                   const DSub *sub, char **d_text_out, uint64_t *seq_pos, uint32_t **ioff_out)
 {
 	*d_text_out = nullptr;
+	if (ioff_out) *ioff_out = nullptr;
 	const uint64_t n_rec = (uint64_t)ug.n_utg * 2 + ug.n_items + ug.g.n_arc;
 	if (n_rec == 0) return 0;
 	if (ug.n_items >= (1ull << 32)) { fprintf(stderr, "[E::miniasm_b200] more than 2^32 layout entries\n"); exit(73); }
@@ -155,7 +163,7 @@ size_t dg_gfa_text(MabDev &d, const DUnitigs &ug, const uint32_t *orig, const ui
 		cub::DeviceScan::ExclusiveSum(tmp, tb, in, ioff, (int64_t)ug.n_items, d.stream);
 		++d.n_lib;
 	}
-	GfaView v{ug.meta, ug.items, ioff, ug.n_utg, ug.n_items, ug.g.arc, ug.g.n_arc, ug.g.idx, orig, noff, nlen, name_text, sub};
+	GfaView v{ug.meta, ug.items, ioff, ug.n_utg, ug.n_items, ug.g.arc, ug.g.n_arc, ug.g.idx, orig, noff, nlen, name_text, sub, seq_pos, nullptr};
 	uint32_t *len = mab_alloc<uint32_t>(d, n_rec);
 	uint64_t *pos = mab_alloc<uint64_t>(d, n_rec + 1);
 	MAB_LAUNCH(d, k_gfa_count, mab_grid(n_rec, 256), 256, 0, v, n_rec, len);
@@ -171,8 +179,10 @@ size_t dg_gfa_text(MabDev &d, const DUnitigs &ug, const uint32_t *orig, const ui
 	d.sync();
 	const size_t bytes = (size_t)(last_pos + last_len);
 	char *out = (char*)d.alloc(bytes ? bytes : 1);
+	if (seq_pos && bytes) MAB_CUDA(cudaMemsetAsync(out, 'N', bytes, d.stream)); // asm.c:249: a unitig starts as N's; the gather overwrites what the reads file holds
 	MAB_LAUNCH(d, k_gfa_write, mab_grid(n_rec, 256), 256, 0, v, n_rec, pos, out);
-	d.free(ioff); d.free(len); d.free(pos);
+	if (ioff_out) *ioff_out = ioff; else d.free(ioff);
+	d.free(len); d.free(pos);
 	*d_text_out = out;
 	return bytes;
 }
@@ -199,7 +209,7 @@ extern "C" size_t mab_test_gfa_host(const ma_ug_t *ug, const sdict_t *d, const m
 	std::vector<uint32_t> nlen(d->n_seq ? d->n_seq : 1);
 	for (uint32_t r = 0; r < d->n_seq; ++r) noff[r] = text.size(), nlen[r] = (uint32_t)strlen(d->seq[r].name), text += d->seq[r].name;
 	GfaView v{meta.data(), items.data(), ioff.data(), (uint32_t)ug->u.n, (uint64_t)items.size(),
-	          (const DArc*)ug->g->arc, ug->g->n_arc, ug->g->idx, nullptr, noff.data(), nlen.data(), text.data(), (const DSub*)sub};
+	          (const DArc*)ug->g->arc, ug->g->n_arc, ug->g->idx, nullptr, noff.data(), nlen.data(), text.data(), (const DSub*)sub, nullptr, nullptr};
 	const uint64_t n_rec = (uint64_t)v.n_utg * 2 + v.n_items + v.n_uarc;
 	size_t tot = 0;
 	for (uint64_t r = 0; r < n_rec; ++r) { CountSink s{0}; emit_record(v, r, s); tot += s.n; }

@@ -160,7 +160,7 @@ static mab_ctx_t *run_sharded(const char *fn, const ma_opt_t *opt, int bi_dir, i
 int main(int argc, char *argv[])
 {
 	ma_opt_t opt;
-	int i, c, stage = 100, no_first = 0, no_second = 0, bi_dir = 1, o_set = 0, no_cont = 0, device = 0, n_gpus = 1, sharded_done = 0;
+	int i, c, stage = 100, no_first = 0, no_second = 0, bi_dir = 1, o_set = 0, no_cont = 0, device = 0, n_gpus = 1, sharded_done = 0, gpu_seq = 0;
 	const char *fn_reads = 0, *outfmt = "ug", *env;
 	mab_ctx_t *ctx;
 	sdict_t *d = 0;
@@ -216,19 +216,17 @@ int main(int argc, char *argv[])
 		ctx = run_sharded(argv[optind], &opt, bi_dir, n_gpus, device);
 		sharded_done = 1;
 	} else ctx = mab_create(device);
+	/* -f: the reads file starts streaming into HBM now, on its own thread and stream, behind the graph stages */
+	if (fn_reads && strcmp(outfmt, "ug") == 0 && !((env = getenv("MAB_GPU_SEQ")) != 0 && atoi(env) == 0)) mab_reads_prefetch(ctx, fn_reads), gpu_seq = 1;
 
 	if (sharded_done) {
-	} else if (no_cont) { /* -R: the exclusion list is a host-side streaming pass; hits then come in through ma_hit_read */
-		sdict_t *excl, *d0;
-		ma_hit_t *hit;
-		size_t n_hits;
+	} else if (no_cont) { /* -R: Step 0 (contained-read prefilter) and Step 1 share one pass over the text in HBM */
 		fprintf(stderr, "[M::%s] ===> Step 0: removing contained reads <===\n", __func__);
-		excl = ma_hit_no_cont(argv[optind], opt.min_span, opt.min_match, opt.max_hang, opt.int_frac);
-		fprintf(stderr, "[M::%s] ===> Step 1: reading read mappings <===\n", __func__);
-		d0 = sd_init();
-		hit = ma_hit_read(argv[optind], opt.min_span, opt.min_match, d0, &n_hits, bi_dir, excl);
-		mab_load_hits(ctx, hit, n_hits, d0);
-		free(hit); sd_destroy(d0); sd_destroy(excl);
+		if (mab_load_paf_file(ctx, argv[optind]) < 0) {
+			fprintf(stderr, "[E::%s] could not open PAF file %s\n", "ma_hit_no_cont", argv[optind]);
+			exit(1);
+		}
+		mab_ingest_nocont(ctx, opt.min_span, opt.min_match, bi_dir, opt.max_hang, opt.int_frac);
 	} else {
 		fprintf(stderr, "[M::%s] ===> Step 1: reading read mappings <===\n", __func__);
 		if (mab_load_paf_file(ctx, argv[optind]) < 0) {
@@ -238,11 +236,7 @@ int main(int argc, char *argv[])
 		mab_ingest(ctx, opt.min_span, opt.min_match, bi_dir);
 	}
 
-	if (!sharded_done) {
-		if (!no_first) fprintf(stderr, "[M::%s] ===> Step 2: 1-pass (crude) read selection <===\n", __func__);
-		if (!no_second) fprintf(stderr, "[M::%s] ===> Step 3: 2-pass (fine) read selection <===\n", __func__);
-		mab_select(ctx, &opt, no_first, no_second, stage);
-	}
+	if (!sharded_done) mab_select(ctx, &opt, no_first, no_second, stage); /* prints the Step 2 / Step 3 banners where the reference does */
 
 	if (strcmp(outfmt, "bed") == 0) {
 		d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
@@ -260,14 +254,16 @@ int main(int argc, char *argv[])
 			fprintf(stderr, "[M::%s] ===> Step 4: graph cleaning <===\n", __func__);
 			mab_layout(ctx, &opt, stage);
 		}
-		if (!gpu_gfa) d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
 		if (strcmp(outfmt, "ug") == 0) {
 			ma_ug_t *ug;
 			fprintf(stderr, "[M::%s] ===> Step 5: generating unitigs <===\n", __func__);
 			mab_unitigs(ctx);
 			if (gpu_gfa) {
 				mab_write_gfa(ctx, stdout);
+			} else if (gpu_seq && mab_write_gfa_reads(ctx, stdout, fn_reads) != -2) {
+				/* ma_ug_seq + ma_ug_print on the GPU (MAB_GPU_SEQ=0, or a reads file that is neither FASTA-like nor 4-line FASTQ: host path below) */
 			} else {
+				d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
 				ug = mab_export_ug(ctx);
 				if (fn_reads) ma_ug_seq(ug, d, sub, fn_reads);
 				ma_ug_print(ug, d, sub, stdout);
@@ -275,6 +271,7 @@ int main(int argc, char *argv[])
 			}
 		} else {
 			asg_t *sg = mab_export_sg(ctx);
+			d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
 			ma_sg_print(sg, d, sub, stdout);
 			asg_destroy(sg);
 		}

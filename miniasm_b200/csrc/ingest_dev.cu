@@ -96,12 +96,6 @@ struct IsLineStart {
 	__device__ __forceinline__ bool operator()(uint64_t p) const { return p == 0 || text[p - 1] == '\n'; }
 };
 
-__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t k)
-{
-	k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
-	return k;
-}
-
 // strtol(field, 0, 10) narrowed to uint32, on the byte range [p, e).  Up to 18 significant digits cannot
 // overflow a long, so the common path is one multiply-add per digit; only longer digit strings take the clamping
 // path (LONG_MAX / LONG_MIN, then truncation to 32 bits, as the reference's assignment does).
@@ -150,14 +144,6 @@ __host__ __device__ __forceinline__ uint32_t num_field(const char *p, uint32_t s
 		v = v * 10 + dgt;
 	}
 	return plain ? v : field_to_u32(p + s, p + t);
-}
-
-__host__ __device__ __forceinline__ uint64_t name_hash(const char *p, uint32_t s, uint32_t t, uint64_t seed)
-{
-	uint64_t h = 1469598103934665603ULL ^ seed;
-	for (uint32_t i = s; i < t; ++i) h = (h ^ (uint8_t)p[i]) * 1099511628211ULL;
-	h = fmix64(h);
-	return h ? h : 1;
 }
 
 // Parse one line [p, e) (no terminator, '\r' already dropped), one thread per line.
@@ -343,10 +329,49 @@ __global__ void k_dict_verify(const char *text, const uint64_t *start, const PLi
 	}
 }
 
-struct SlotUsed {
-	const unsigned long long *key;
-	__device__ __forceinline__ bool operator()(uint64_t s) const { return key[s] != 0; }
+struct SlotUsed { // a name is in the dictionary iff some stored line carries it (after -R: iff such a line is left)
+	const unsigned long long *first;
+	__device__ __forceinline__ bool operator()(uint64_t s) const { return first[s] != ~0ull; }
 };
+
+// ---- -R: ma_hit_no_cont (hit.c:38-68) as two passes over the parsed lines -----------------------------------------
+// A read is dropped when some stored line shows it clearly inside a read at least twice as long; every line that
+// names a dropped read is skipped BEFORE ids are given out (hit.c:86), so first appearances are taken again afterwards.
+__global__ void k_nocont_mark(const PLine *ln, uint64_t n_lines, int max_hang, float int_frac, uint8_t *excl)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+		const PLine r = ln[i];
+		if (!r.pass) continue;
+		const bool rev = r.ml_rev >> 31;
+		const int l5 = (int)(rev ? r.tl - r.te : r.ts), l3 = (int)(rev ? r.ts : r.tl - r.te);
+		if (r.ql >> 1 > r.tl) { // query at least twice as long: is the target inside it?
+			if (l5 > max_hang >> 2 || l3 > max_hang >> 2 || (float)(r.te - r.ts) < __fmul_rn((float)r.tl, int_frac)) continue; // internal match
+			if ((int)r.qs - l5 > max_hang << 1 && (int)(r.ql - r.qe) - l3 > max_hang << 1) excl[r.slot_t] = 1;
+		} else if (r.ql < r.tl >> 1) {
+			if (r.qs > (uint32_t)(max_hang >> 2) || r.ql - r.qe > (uint32_t)(max_hang >> 2) || (float)(r.qe - r.qs) < __fmul_rn((float)r.ql, int_frac)) continue;
+			if (l5 - (int)r.qs > max_hang << 1 && l3 - (int)(r.ql - r.qe) > max_hang << 1) excl[r.slot_q] = 1;
+		}
+	}
+}
+
+__global__ void k_nocont_drop(PLine *ln, uint64_t n_lines, const uint8_t *excl, NameTab t)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+		if (!ln[i].pass) continue;
+		const uint64_t sq = ln[i].slot_q, st = ln[i].slot_t;
+		if (excl[sq] || excl[st]) { ln[i].pass = 0; continue; }
+		if (t.first[sq] > 2 * i) atomicMin(&t.first[sq], (unsigned long long)(2 * i));
+		if (t.first[st] > 2 * i + 1) atomicMin(&t.first[st], (unsigned long long)(2 * i + 1));
+	}
+}
+
+__global__ void k_count_u8(const uint8_t *a, uint64_t n, unsigned long long *out)
+{
+	unsigned c = 0;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += a[i] != 0;
+	c = __reduce_add_sync(0xffffffffu, c);
+	if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
 
 __global__ void k_dict_pairs(const uint64_t *slots, uint32_t n, NameTab t, unsigned long long *first_out)
 {
@@ -403,6 +428,30 @@ __global__ void k_hit_emit(const PLine *ln, uint64_t n_lines, const uint32_t *cn
 	if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_qs, mx);
 }
 
+// start[i] = byte offset of line i (a line starts at byte 0 and after every '\n' that is not the last byte); len > 0
+uint64_t *dev_line_starts(MabDev &d, const char *d_text, size_t len, uint64_t *n_lines_out)
+{
+	const uint64_t n_tile = (len + NL_TILE - 1) / NL_TILE;
+	uint64_t *cnt = mab_alloc<uint64_t>(d, n_tile + 1);
+	uint64_t *base = mab_alloc<uint64_t>(d, n_tile + 1);
+	MAB_LAUNCH(d, k_nl_count, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, cnt);
+	size_t tb = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, base, (int64_t)(n_tile + 1), d.stream);
+	void *tmp = d.tmp(tb);
+	cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, base, (int64_t)(n_tile + 1), d.stream);
+	++d.n_lib;
+	uint64_t n_nl;
+	MAB_CUDA(cudaMemcpyAsync(&n_nl, base + n_tile, 8, cudaMemcpyDeviceToHost, d.stream));
+	d.sync();
+	const uint64_t n_lines = n_nl + 1; // newlines that are followed by at least one byte, plus the first line
+	uint64_t *start = mab_alloc<uint64_t>(d, n_lines + 1);
+	MAB_CUDA(cudaMemsetAsync(start, 0, 8, d.stream));
+	MAB_LAUNCH(d, k_nl_write, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, base, start + 1);
+	d.free(cnt); d.free(base);
+	*n_lines_out = n_lines;
+	return start;
+}
+
 void names_free(MabDev &d, DNames &n)
 {
 	d.free(n.off); d.free(n.nlen); d.free(n.slen);
@@ -411,7 +460,8 @@ void names_free(MabDev &d, DNames &n)
 
 static inline uint32_t bits_for(uint64_t x) { uint32_t b = 0; while (x) ++b, x >>= 1; return b ? b : 1; }
 
-void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min_match, int bi_dir, DHits &h, DNames &names, IngestStats &st)
+void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min_match, int bi_dir, DHits &h, DNames &names, IngestStats &st,
+                const NoContParams *nocont)
 {
 	memset(&st, 0, sizeof(st));
 	names = DNames();
@@ -420,27 +470,8 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 
 	d.trace("ingest:begin");
 	// (1) line starts: count newlines per 16 KB tile, scan the tile counts, write the positions
-	uint64_t *start = nullptr;
 	uint64_t n_lines;
-	{
-		const uint64_t n_tile = (len + NL_TILE - 1) / NL_TILE;
-		uint64_t *cnt = mab_alloc<uint64_t>(d, n_tile + 1);
-		uint64_t *base = mab_alloc<uint64_t>(d, n_tile + 1);
-		MAB_LAUNCH(d, k_nl_count, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, cnt);
-		size_t tb = 0;
-		cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, base, (int64_t)(n_tile + 1), d.stream);
-		void *tmp = d.tmp(tb);
-		cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, base, (int64_t)(n_tile + 1), d.stream);
-		++d.n_lib;
-		uint64_t n_nl;
-		MAB_CUDA(cudaMemcpyAsync(&n_nl, base + n_tile, 8, cudaMemcpyDeviceToHost, d.stream));
-		d.sync();
-		n_lines = n_nl + 1; // newlines that are followed by at least one byte, plus the first line
-		start = mab_alloc<uint64_t>(d, n_lines + 1);
-		MAB_CUDA(cudaMemsetAsync(start, 0, 8, d.stream));
-		MAB_LAUNCH(d, k_nl_write, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, base, start + 1);
-		d.free(cnt); d.free(base);
-	}
+	uint64_t *start = dev_line_starts(d, d_text, len, &n_lines);
 	st.n_lines = n_lines;
 	d.trace("ingest:line_starts");
 
@@ -484,12 +515,24 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 	}
 
 	d.trace("ingest:dictionary");
+	if (nocont) { // -R: mark the contained reads, drop every line that names one, take the first appearances again
+		uint8_t *excl = mab_alloc<uint8_t>(d, cap);
+		MAB_CUDA(cudaMemsetAsync(excl, 0, cap, d.stream));
+		MAB_LAUNCH(d, k_nocont_mark, mab_grid(n_lines, 256), 256, 0, ln, n_lines, nocont->max_hang, nocont->int_frac, excl);
+		d.zero_scal(SC_AUX, 1);
+		MAB_LAUNCH(d, k_count_u8, mab_grid(cap, 256), 256, 0, excl, cap, d.d_scal + SC_AUX);
+		MAB_CUDA(cudaMemsetAsync(tab.first, 0xff, cap * 8, d.stream));
+		MAB_LAUNCH(d, k_nocont_drop, mab_grid(n_lines, 256), 256, 0, ln, n_lines, excl, tab);
+		st.n_dropped = d.get_scal(SC_AUX);
+		d.free(excl);
+		d.trace("ingest:-R prefilter");
+	}
 	// (4) ids = rank of the first occurrence
 	uint64_t *slots = mab_alloc<uint64_t>(d, cap);
 	uint32_t n_seq;
 	{
 		cub::CountingInputIterator<uint64_t> pos(0);
-		SlotUsed used{tab.key};
+		SlotUsed used{tab.first};
 		size_t tb = 0;
 		unsigned long long *d_n = d.d_scal + SC_NSEL;
 		cub::DeviceSelect::If(nullptr, tb, pos, slots, d_n, (int64_t)cap, used, d.stream);
@@ -834,7 +877,7 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		uint64_t *slots = mab_alloc<uint64_t>(d, cap);
 		if (!bad) {
 			cub::CountingInputIterator<uint64_t> pos(0);
-			SlotUsed used{tab.key};
+			SlotUsed used{tab.first};
 			size_t tb = 0;
 			unsigned long long *d_n = d.d_scal + SC_NSEL;
 			cub::DeviceSelect::If(nullptr, tb, pos, slots, d_n, (int64_t)cap, used, d.stream);

@@ -118,6 +118,23 @@ def test_bubble_dense_300k(paf_dir):
     assert any("popped 3713 bubbles" in x for x in _counters(err_c))
 
 
+@pytest.mark.parametrize("args", ["-n 4000 -l 2000 -L 30000 -c 30 -j 100 -s 41", "-n 20000 -l 1500 -L 40000 -c 40 -j 300 -s 42 -d 20000"])
+def test_R_prefilter_on_the_gpu(args, paf_dir):
+    """-R (ma_hit_no_cont, hit.c:38-68): read lengths spread over a factor of 20, so hundreds of reads are clearly contained in a
+    read twice as long; ids are first appearances among the lines that survive the exclusion.  Output and counters vs the reference."""
+    paf = synth.generate(args, os.path.join(paf_dir, "nocont_cli.paf"))
+    for extra in ([], ["-b"], ["-c", "2"]):
+        rc_r, out_r, err_r = run(REF, ["-R"] + extra + [paf])
+        rc_c, out_c, err_c = run(CLI, ["-R"] + extra + [paf])
+        assert rc_c == rc_r == 0, err_c.decode()[-2000:]
+        assert out_c == out_r
+        assert _counters(err_c) == _counters(err_r)
+        dropped = [x for x in _counters(err_r) if "dropped" in x]
+        assert dropped and int(dropped[0].split("dropped")[1].split()[0]) > 50
+    same(["-R", "-S", "2", "-p", "paf", paf], exact=False)
+    same(["-R", "-p", "bed", paf])
+
+
 def test_version_usage_and_missing_file(pafs):
     assert run(CLI, ["-V"])[:2] == run(REF, ["-V"])[:2]
     rc, out, err = run(CLI, [])
@@ -132,6 +149,105 @@ def test_with_reads(pafs, paf_dir):
     reads = _write_reads(pafs["chaos_small"], os.path.join(paf_dir, "cli_reads.fa"))
     out = same(["-f", reads, pafs["chaos_small"]])
     assert b"\t*\tLN" not in out
+
+
+def _read_lengths(paf):
+    lens = {}
+    with open(paf) as f:
+        for line in f:
+            t = line.split("\t")
+            lens[t[0]] = int(t[1]); lens[t[5]] = int(t[6])
+    return lens
+
+
+def _reads_file(paf, path, style, seed=7):
+    """A reads file for `paf` in one of the layouts ma_ug_seq (asm.c:236-290, kseq.h:163-211) must cope with."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    lens = _read_lengths(paf)
+    alphabet = np.frombuffer(b"ACGTNacgtnRYKMBDHVUuWSrykm", dtype=np.uint8)
+    names = sorted(lens)
+    rng.shuffle(names)
+    op = gzip.open if path.endswith(".gz") else open
+    eol = b"\r\n" if "crlf" in style else b"\n"
+    with op(path, "wb") as f:
+        def record(nm, seq):
+            if style.startswith("fq"):
+                qual = bytes(rng.integers(33, 74, len(seq), dtype=np.uint8))       # includes '@' (64) and '>' (62) and '+' (43) as first bytes now and then
+                if "multi" in style:                                               # multi-line FASTQ: only a sequential reader can cut it
+                    h = len(seq) // 2
+                    f.write(b"@" + nm + b" c" + eol + seq[:h] + eol + seq[h:] + eol + b"+" + eol + qual[:h] + eol + qual[h:] + eol)
+                else:
+                    f.write(b"@" + nm + b"\tx=1" + eol + seq + eol + b"+" + nm + eol + qual + eol)
+            else:
+                w = 70 if "wrap" in style else (len(seq) if "one" in style else int(rng.integers(40, 200)))
+                f.write(b">" + nm + (b" some comment" if rng.random() < .5 else b"") + eol)
+                for i in range(0, len(seq), w):
+                    f.write(seq[i:i + w] + eol)
+                    if "gaps" in style and rng.random() < .05:
+                        f.write(eol)                                               # empty lines are skipped (kseq.h:181)
+        for k, nm in enumerate(names):
+            if "missing" in style and k % 9 == 0:
+                continue                                                           # reads that are not in the file stay N's
+            seq = bytes(alphabet[rng.integers(0, len(alphabet), lens[nm])])
+            record(nm.encode(), seq)
+            if "dups" in style and k % 7 == 0:                                     # same name again with other bases: the later record wins
+                record(nm.encode(), bytes(alphabet[rng.integers(0, len(alphabet), lens[nm])]))
+            if "extra" in style and k % 5 == 0:
+                record(b"not_in_the_layout_%d" % k, b"ACGT" * 50)
+    return path
+
+
+@pytest.mark.parametrize("style,ext", [("fa_wrap", "fa"), ("fa_one_crlf", "fa"), ("fa_var_gaps_extra_dups_missing", "fa"), ("fa_wrap", "fa.gz"),
+                                       ("fq", "fq"), ("fq_crlf_extra_dups", "fq"), ("fq_missing", "fq.gz"), ("fq_multi", "fq")])
+@pytest.mark.parametrize("name", ["chaos_small", "bubbles800"])
+def test_reads_on_the_gpu(style, ext, name, pafs, paf_dir):
+    """-f reads: the record index, name table and base gather of ma_ug_seq on the GPU (or, for multi-line FASTQ, the host reader it
+    falls back to) against the reference, for FASTA/FASTQ layouts, line ends, compression, missing / foreign / repeated records."""
+    reads = _reads_file(pafs[name], os.path.join(paf_dir, f"r_{name}_{style}.{ext}"), style)
+    out = same(["-f", reads, pafs[name]])
+    assert b"\t*\tLN" not in out
+    same(["-f", reads, "-c", "2", "-e", "2", pafs[name]])
+
+
+def test_reads_wrong_file_is_refused(pafs, paf_dir):
+    """asm.c:263 asserts that a record covers the kept interval: a reads file with shorter records aborts with a message."""
+    lens = _read_lengths(pafs["chaos_small"])
+    path = os.path.join(paf_dir, "short_reads.fa")
+    with open(path, "w") as f:
+        for nm in lens:
+            f.write(f">{nm}\nACGTACGT\n")
+    rc, out, err = run(CLI, ["-f", path, pafs["chaos_small"]])
+    assert rc != 0 and b"[E::ma_ug_seq]" in err
+    rc, out, err = run(CLI, ["-f", "/nonexistent.fa", pafs["chaos_small"]])       # unreadable file: GFA without sequences, like the reference
+    rc_r, out_r, _ = run(REF, ["-f", "/nonexistent.fa", pafs["chaos_small"]])
+    assert rc == rc_r == 0 and out == out_r and b"\t*\tLN" in out
+
+
+def test_reads_c2_size(paf_dir):
+    """BASELINE config 2 (100 K reads / 5 M overlaps) with its 1 GB reads file: -f parity at size, and the wall clocks."""
+    import time
+    import numpy as np
+    paf = synth.generate("c2_100k", os.path.join(paf_dir, "c2.paf"))
+    lens = _read_lengths(paf)
+    reads = os.path.join(paf_dir, "c2_reads.fa")
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    with open(reads, "wb") as f:
+        for nm, ln in lens.items():
+            seq = acgt[rng.integers(0, 4, ln)]
+            lines = np.full((ln + 69) // 70 * 71, 10, dtype=np.uint8)
+            body = lines.reshape(-1, 71)
+            flat = np.concatenate([seq, np.zeros(body.shape[0] * 70 - ln, dtype=np.uint8)]).reshape(-1, 70)
+            body[:, :70] = flat
+            txt = body.tobytes().replace(b"\x00", b"")
+            f.write(b">" + nm.encode() + b"\n" + txt)
+    t0 = time.time(); rc_r, out_r, _ = run(REF, ["-f", reads, paf]); t_ref = time.time() - t0
+    t0 = time.time(); rc_c, out_c, err_c = run(CLI, ["-f", reads, paf]); t_cli = time.time() - t0
+    assert rc_c == rc_r == 0, err_c.decode()[-2000:]
+    assert out_c == out_r
+    print(f"c2 with -f: reference {t_ref:.2f} s, miniasm-b200 {t_cli:.2f} s ({os.path.getsize(reads) / 1e9:.2f} GB of reads)")
+    os.unlink(reads)
 
 
 def test_weird_lines(paf_dir):

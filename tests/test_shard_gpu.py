@@ -63,3 +63,29 @@ def test_sharded_full_config_digest(name, world, built, paf_dir):
     size = os.path.getsize(out)
     os.unlink(out)
     assert size == gold[name]["gfa_bytes"] and h.hexdigest() == gold[name]["gfa_sha256"]
+
+
+CLI = os.path.join(ROOT, "miniasm_b200", "miniasm-b200")
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("name", ["chaos_small", "chaos", "bubbles800", "tiny_exact"])
+@pytest.mark.parametrize("world", WORLDS or [2])
+@pytest.mark.parametrize("extra", [[], ["-p", "sg"]], ids=["ug", "sg"])
+def test_cli_multi_gpu(name, world, extra, built, paf_dir):
+    """The drop-in command line with MINIASM_B200_GPUS=N (threads of one process, NCCL + peer access inside the library):
+    same bytes on stdout as the reference, same counts on stderr."""
+    import re
+    paf = synth.generate(name, f"{paf_dir}/sh_{name}.paf")
+    want = subprocess.run([REF] + extra + [paf], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    for p2p in ("1", "0"):
+        got = subprocess.run([CLI] + extra + [paf], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600,
+                             env={**os.environ, "MINIASM_B200_GPUS": str(world), "MAB_SHARD_P2P": p2p})
+        assert got.returncode == 0, got.stderr.decode()[-3000:]
+        if extra:   # raw-graph dumps: arcs of equal (vertex, length) print in the order the reference's unstable sort left them
+            assert sorted(got.stdout.splitlines()) == sorted(want.stdout.splitlines())
+        else:
+            assert got.stdout == want.stdout
+        cnt = lambda err: [re.sub(r"::\d+\.\d+\*\d+\.\d+\]", "]", x) for x in err.decode().splitlines()
+                           if x.startswith("[M::") and "::main]" not in x and any(k in x for k in ("ma_hit_read", "ma_hit_contained", "ma_sg_gen", "asg_")) and "===>" not in x]
+        assert cnt(got.stderr) == cnt(want.stderr)
