@@ -45,7 +45,7 @@ from miniasm_b200 import synth  # noqa: E402
 WORKLOADS = {
     "c2_100k": dict(args=synth.CONFIGS["c2_100k"], label="Synthetic PAF: 100K reads / 5M overlaps"),
     "c3_1m": dict(args=synth.CONFIGS["c3_1m"], label="Synthetic PAF: 1M reads / 50M overlaps (C. elegans-scale)"),
-    "c3_2m": dict(args="-n 2000000 -s 4", label="Synthetic PAF: 2M reads / 100M overlaps (config 3's law)"),
+    "c3_2m": dict(args=synth.CONFIGS["c3_2m"], label="Synthetic PAF: 2M reads / 100M overlaps (config 3's law)"),
     "c4_4m": dict(args=synth.CONFIGS["c4_4m"], label="Synthetic PAF: 4M reads / 200M overlaps"),
     "c5_8m_skew": dict(args=synth.CONFIGS["c5_8m_skew"], label="Synthetic PAF: 8M reads / 400M overlaps, skewed degree (hot loci of 10 000 reads)"),
     "noisy_600k": dict(args="-n 600000 -l 9000 -L 11000 -j 800 -c 30 -s 15", label="Synthetic PAF: 600K reads U[9k,11k] / 30x / ends jittered by U[0,800] (tips and bubbles)"),

@@ -1,12 +1,7 @@
 """ctypes view of the miniasm C ABI (include/miniasm_b200.h).
 
-The same bindings drive two shared libraries, because the product keeps the reference's ABI:
-
-* ``load_product()``  -> ``miniasm_b200/libminiasm_b200.so`` (CUDA, sm_100a)
-* ``load_reference()`` -> ``oracle/_ref/libminiasm_ref.so`` (the unmodified reference, test oracle only)
-* ``load_oracle_port()`` -> ``oracle/libma_oracle.so`` (our CPU restatement, test oracle only)
-
-Only tests, ``__graft_entry__.smoke`` and the CPU-baseline leg of ``bench.py`` may load the last two.
+``load_product()`` -> ``miniasm_b200/libminiasm_b200.so`` (CUDA, sm_100a).  ``Lib`` works for any library that exports the
+reference's C API, which is how the test oracles are driven too -- but their loaders live in ``oracle/loaders.py``, not here.
 """
 import ctypes as C
 import os
@@ -15,8 +10,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PRODUCT_SO = os.path.join(ROOT, "miniasm_b200", "libminiasm_b200.so")
-REFERENCE_SO = os.path.join(ROOT, "oracle", "_ref", "libminiasm_ref.so")
-ORACLE_SO = os.path.join(ROOT, "oracle", "libma_oracle.so")
 
 HIT_DT = np.dtype([("qns", "<u8"), ("qe", "<u4"), ("tn", "<u4"), ("ts", "<u4"), ("te", "<u4"),
                    ("ml_rev", "<u4"), ("bl_del", "<u4")])          # ma_hit_t, miniasm.h:29-34
@@ -270,10 +263,3 @@ class Lib:
 def load_product(strict=True):
     return Lib(PRODUCT_SO, product=True, strict=strict)
 
-
-def load_reference():
-    return Lib(REFERENCE_SO, product=False, strict=True)
-
-
-def load_oracle_port():
-    return Lib(ORACLE_SO, product=False, strict=False)

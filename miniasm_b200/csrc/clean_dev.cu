@@ -36,8 +36,8 @@ __global__ void k_fx_init(const DArc *arc, const uint32_t *seq, uint32_t n_arc, 
 	}
 }
 
-template <class Rule>
-__global__ void k_fx_sweep(FxView g, Rule rule, unsigned long long *n_act)
+template <class View, class Rule>
+__global__ void k_fx_sweep(View g, Rule rule, unsigned long long *n_act)
 {
 	unsigned cnt = 0;
 	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < g.n_vtx; v += gridDim.x * blockDim.x)
@@ -97,20 +97,25 @@ template <class Rule>
 static uint32_t run_fixpoint(MabDev &d, DGraph &g, Rule rule)
 {
 	g_clean_stats.rounds = 0, g_clean_stats.committed = 0;
-	if (g.n_seq == 0 || g.n_arc == 0) return 0;
+	if (g.n_seq == 0) return 0;                        // (a graph WITHOUT arcs still has work: every live read is a tip, asg.c:243-249)
+	// probe: the first sweep straight on the deletion bits, stamping nothing.  Nobody acts -> the pass is over.
+	d.zero_scal(SC_COUNT);
+	MAB_LAUNCH(d, (k_fx_sweep<FxProbe, Rule>), mab_grid((size_t)g.n_seq * 2, 128), 128, 0, FxProbe{g.arc, g.idx, g.seq, g.n_seq * 2}, rule, d.d_scal + SC_COUNT);
+	g_clean_stats.rounds = 1;
+	if (d.get_scal(SC_COUNT) == 0) return 0;
 	FxBuf b;
 	fx_alloc(d, g, b);
 	uint32_t sweeps = 0, cnt;
 	for (;;) {
 		d.zero_scal(SC_COUNT);
-		MAB_LAUNCH(d, k_fx_sweep<Rule>, mab_grid((size_t)g.n_seq * 2, 128), 128, 0, fx_view(g, b), rule, d.d_scal + SC_COUNT);
+		MAB_LAUNCH(d, (k_fx_sweep<FxView, Rule>), mab_grid((size_t)g.n_seq * 2, 128), 128, 0, fx_view(g, b), rule, d.d_scal + SC_COUNT);
 		++sweeps;
 		const bool fixed = fx_next(d, g, b);
 		cnt = (uint32_t)d.h_scal[SC_COUNT];
 		if (fixed) break;       // the sweep ran on the fixed point itself: its count is the reference's
 	}
 	fx_finish(d, g, b);
-	g_clean_stats.rounds = sweeps, g_clean_stats.committed = cnt;
+	g_clean_stats.rounds = sweeps + 1, g_clean_stats.committed = cnt;
 	return cnt;
 }
 

@@ -42,14 +42,6 @@
 
 constexpr uint32_t FX_LIVE = 0xffffffffu;
 
-struct FxView {
-	const DArc *arc;            // structure: never written during the sweeps
-	const uint64_t *idx;
-	const uint32_t *ts, *ta;    // T_old: per read / per arc
-	uint32_t *ns, *na;          // T_new
-	uint32_t n_vtx;
-};
-
 FX_HD void fx_stamp(uint32_t *p, uint32_t t)
 {
 #if defined(__CUDA_ARCH__)
@@ -59,14 +51,41 @@ FX_HD void fx_stamp(uint32_t *p, uint32_t t)
 #endif
 }
 
+// The graph as a sweep sees it: T_old to read, T_new to stamp.
+struct FxView {
+	const DArc *arc;            // structure: never written during the sweeps
+	const uint64_t *idx;
+	const uint32_t *ts, *ta;    // T_old: per read / per arc
+	uint32_t *ns, *na;          // T_new
+	uint32_t n_vtx;
+	FX_MEMBER uint32_t at(uint32_t i) const { return ta[i]; }
+	FX_MEMBER uint32_t st(uint32_t s) const { return ts[s]; }
+	FX_MEMBER void stamp_a(uint32_t i, uint32_t t) const { fx_stamp(&na[i], t); }
+	FX_MEMBER void stamp_s(uint32_t s, uint32_t t) const { fx_stamp(&ns[s], t); }
+};
+
+// The same interface straight on the deletion bits, stamping nothing: the PROBE sweep that opens every pass.  T_init is
+// "0 where the bit is set, LIVE elsewhere", so deciding on the bits IS the first Jacobi sweep; if nobody acts in it the
+// pass is over (the reference's loop would not have changed anything either) and no timestamp array was ever touched.
+struct FxProbe {
+	const DArc *arc;
+	const uint64_t *idx;
+	const uint32_t *seq;
+	uint32_t n_vtx;
+	FX_MEMBER uint32_t at(uint32_t i) const { return arc[i].ol_del & MAB_DEL_BIT ? 0u : FX_LIVE; }
+	FX_MEMBER uint32_t st(uint32_t s) const { return seq[s] & MAB_DEL_BIT ? 0u : FX_LIVE; }
+	FX_MEMBER void stamp_a(uint32_t, uint32_t) const {}
+	FX_MEMBER void stamp_s(uint32_t, uint32_t) const {}
+};
+
 // asg_is_utg_end (asg.c:204-222) as iteration `me` sees it
-FX_HD int fx_utg_end(const FxView &g, uint32_t me, uint32_t v, uint64_t *lw)
+template <class V> FX_HD int fx_utg_end(const V &g, uint32_t me, uint32_t v, uint64_t *lw)
 {
 	const uint64_t iv = g.idx[v ^ 1];
 	const uint32_t nv0 = (uint32_t)iv, off = (uint32_t)(iv >> 32);
 	uint32_t nv = 0, i0 = 0;
 	for (uint32_t i = 0; i < nv0; ++i)
-		if (g.ta[off + i] > me) i0 = off + i, ++nv;
+		if (g.at(off + i) > me) i0 = off + i, ++nv;
 	if (nv == 0) return FX_ET_TIP;
 	if (nv > 1) return FX_ET_MULTI_OUT;
 	const DArc a = g.arc[i0];
@@ -75,13 +94,13 @@ FX_HD int fx_utg_end(const FxView &g, uint32_t me, uint32_t v, uint64_t *lw)
 	const uint32_t nw0 = (uint32_t)iw, offw = (uint32_t)(iw >> 32);
 	uint32_t nw = 0;
 	for (uint32_t i = 0; i < nw0; ++i)
-		if (g.ta[offw + i] > me) ++nw;
+		if (g.at(offw + i) > me) ++nw;
 	return nw != 1 ? FX_ET_MULTI_NEI : FX_ET_MERGEABLE;
 }
 
 // asg_extend (asg.c:224-236) without materialising the path: `chain(vertex)` sees every vertex the reference pushes
-template <class ChainFn>
-FX_HD int fx_extend(const FxView &g, uint32_t me, uint32_t v, int max_ext, ChainFn chain, uint32_t *last)
+template <class V, class ChainFn>
+FX_HD int fx_extend(const V &g, uint32_t me, uint32_t v, int max_ext, ChainFn chain, uint32_t *last)
 {
 	int ret;
 	uint64_t lw = 0;
@@ -98,24 +117,24 @@ FX_HD int fx_extend(const FxView &g, uint32_t me, uint32_t v, int max_ext, Chain
 }
 
 // asg_arc_del(g, v, w, 1) (asg.h:55-61): every arc v->w
-FX_HD void fx_arc_del(const FxView &g, uint32_t v, uint32_t w, uint32_t t)
+template <class V> FX_HD void fx_arc_del(const V &g, uint32_t v, uint32_t w, uint32_t t)
 {
 	const uint64_t iv = g.idx[v];
 	const uint32_t off = (uint32_t)(iv >> 32);
 	for (uint32_t i = 0; i < (uint32_t)iv; ++i)
-		if (g.arc[off + i].v == w) fx_stamp(&g.na[off + i], t);
+		if (g.arc[off + i].v == w) g.stamp_a(off + i, t);
 }
 
 // asg_seq_del (asg.h:64-77): the read, all arcs of both strands and their complements
-FX_HD void fx_seq_del(const FxView &g, uint32_t s, uint32_t t)
+template <class V> FX_HD void fx_seq_del(const V &g, uint32_t s, uint32_t t)
 {
-	fx_stamp(&g.ns[s], t);
+	g.stamp_s(s, t);
 	for (uint32_t k = 0; k < 2; ++k) {
 		const uint32_t v = s << 1 | k;
 		const uint64_t iv = g.idx[v];
 		const uint32_t off = (uint32_t)(iv >> 32);
 		for (uint32_t i = 0; i < (uint32_t)iv; ++i) {
-			fx_stamp(&g.na[off + i], t);
+			g.stamp_a(off + i, t);
 			fx_arc_del(g, g.arc[off + i].v ^ 1, v ^ 1, t);
 		}
 	}
@@ -124,9 +143,9 @@ FX_HD void fx_seq_del(const FxView &g, uint32_t s, uint32_t t)
 // ---- the three short-unitig cutters: act(g, v) decides under T_old and stamps T_new; true if v acts ----
 struct FxTip { // asg_cut_tip
 	int max_ext;
-	FX_MEMBER bool act(const FxView &g, uint32_t v) const
+	template <class V> FX_MEMBER bool act(const V &g, uint32_t v) const
 	{
-		if (g.ts[v >> 1] <= v) return false;
+		if (g.st(v >> 1) <= v) return false;
 		if (fx_utg_end(g, v, v, nullptr) != FX_ET_TIP) return false;
 		uint32_t last;
 		if (fx_extend(g, v, v, max_ext, [](uint32_t) {}, &last) == FX_ET_MERGEABLE) return false;
@@ -138,9 +157,9 @@ struct FxTip { // asg_cut_tip
 
 struct FxInternal { // asg_cut_internal
 	int max_ext;
-	FX_MEMBER bool act(const FxView &g, uint32_t v) const
+	template <class V> FX_MEMBER bool act(const V &g, uint32_t v) const
 	{
-		if (g.ts[v >> 1] <= v) return false;
+		if (g.st(v >> 1) <= v) return false;
 		if (fx_utg_end(g, v, v, nullptr) != FX_ET_MULTI_NEI) return false;
 		uint32_t last;
 		if (fx_extend(g, v, v, max_ext, [](uint32_t) {}, &last) != FX_ET_MULTI_NEI) return false;
@@ -151,9 +170,9 @@ struct FxInternal { // asg_cut_internal
 
 struct FxBiloop { // asg_cut_biloop: v->...->x', w->v and w->x; drop w->x (and its complement) if it is the weaker one
 	int max_ext;
-	FX_MEMBER bool act(const FxView &g, uint32_t v) const
+	template <class V> FX_MEMBER bool act(const V &g, uint32_t v) const
 	{
-		if (g.ts[v >> 1] <= v) return false;
+		if (g.st(v >> 1) <= v) return false;
 		if (fx_utg_end(g, v, v, nullptr) != FX_ET_MULTI_NEI) return false;
 		uint32_t last;
 		if (fx_extend(g, v, v, max_ext, [](uint32_t) {}, &last) != FX_ET_MULTI_OUT) return false;
@@ -163,13 +182,13 @@ struct FxBiloop { // asg_cut_biloop: v->...->x', w->v and w->x; drop w->x (and i
 			const uint64_t iv = g.idx[v ^ 1];
 			const uint32_t off = (uint32_t)(iv >> 32);
 			for (uint32_t i = 0; i < (uint32_t)iv; ++i)
-				if (g.ta[off + i] > v) w = g.arc[off + i].v ^ 1;
+				if (g.at(off + i) > v) w = g.arc[off + i].v ^ 1;
 		}
 		if (w == 0xffffffffu) return false; // cannot happen: MULTI_NEI means exactly one live arc (asg.c:288 asserts it)
 		const uint64_t iw = g.idx[w];
 		const uint32_t offw = (uint32_t)(iw >> 32);
 		for (uint32_t i = 0; i < (uint32_t)iw; ++i) {
-			if (g.ta[offw + i] <= v) continue;
+			if (g.at(offw + i) <= v) continue;
 			const DArc a = g.arc[offw + i];
 			if (a.v == x) ox = a.ol_del & ~MAB_DEL_BIT;
 			if (a.v == v) ov = a.ol_del & ~MAB_DEL_BIT;
@@ -213,18 +232,18 @@ FX_HD uint32_t fx_lookup(const FxSlot &sl, uint32_t key)
 	return h;
 }
 
-FX_HD bool fx_is_source(const FxView &g, uint32_t v)
+template <class V> FX_HD bool fx_is_source(const V &g, uint32_t v)
 {
 	const uint64_t iv = g.idx[v];
 	const uint32_t nv = (uint32_t)iv, off = (uint32_t)(iv >> 32);
-	if (nv < 2 || g.ts[v >> 1] <= v) return false;
+	if (nv < 2 || g.st(v >> 1) <= v) return false;
 	uint32_t live = 0;
-	for (uint32_t i = 0; i < nv; ++i) live += g.ta[off + i] > v;
+	for (uint32_t i = 0; i < nv; ++i) live += g.at(off + i) > v;
 	return live > 1;
 }
 
 // the traversal of asg_bub_pop1 as iteration v0 sees the graph: 1 = bubble resolved, 0 = nothing to pop, -1 = scratch too small
-FX_HD_NOINL int fx_bub_walk(const FxView &g, uint32_t v0, uint32_t max_dist, const FxSlot &sl, FxBubRes *out)
+template <class V> FX_HD_NOINL int fx_bub_walk(const V &g, uint32_t v0, uint32_t max_dist, const FxSlot &sl, FxBubRes *out)
 {
 	uint32_t nb = 0, ne = 0, nT = 0, nS = 0, n_pending = 0;
 	int ret = 0;
@@ -240,7 +259,7 @@ FX_HD_NOINL int fx_bub_walk(const FxView &g, uint32_t v0, uint32_t max_dist, con
 			const DArc a = g.arc[off + i];
 			const uint32_t w = a.v, l = (uint32_t)a.ul;
 			if (w == v0) goto done;                            // a cycle through the source (tested before the del bit, asg.c:377)
-			if (g.ta[off + i] <= v0) continue;
+			if (g.at(off + i) <= v0) continue;
 			if (ne == sl.ecap) { ret = -1; goto done; }
 			sl.e[ne++] = off + i;
 			if (d + l > max_dist) break;                       // too far
@@ -253,7 +272,7 @@ FX_HD_NOINL int fx_bub_walk(const FxView &g, uint32_t v0, uint32_t max_dist, con
 				uint32_t r = 0;                                // count_out(w^1): live arcs only
 				const uint64_t ix = g.idx[w ^ 1];
 				const uint32_t offx = (uint32_t)(ix >> 32);
-				for (uint32_t k = 0; k < (uint32_t)ix; ++k) r += g.ta[offx + k] > v0;
+				for (uint32_t k = 0; k < (uint32_t)ix; ++k) r += g.at(offx + k) > v0;
 				sl.hr[h] = r;
 				++n_pending;
 			} else {
@@ -294,7 +313,7 @@ FX_HD bool fx_revived(const FxSlot &sl, uint32_t s, uint32_t t)
 // asg_bub_backtrack (asg.c:338-357) as NET deletions: everything visited goes, except what the best path revives.
 // Returns false if the backtrack would revive a bit that was already deleted when v0 looked (never on a symmetric
 // graph without multi-arcs, which is what asg_pop_bubble works on): the pass would not be deletion-only.
-FX_HD_NOINL bool fx_bub_backtrack(const FxView &g, uint32_t v0, const FxSlot &sl, const FxBubRes &w)
+template <class V> FX_HD_NOINL bool fx_bub_backtrack(const V &g, uint32_t v0, const FxSlot &sl, const FxBubRes &w)
 {
 	bool mono = true;
 	const uint32_t t = v0 + 1;
@@ -302,12 +321,12 @@ FX_HD_NOINL bool fx_bub_backtrack(const FxView &g, uint32_t v0, const FxSlot &sl
 	do { // mark the best path sink -> ... -> child of v0
 		const uint32_t h = fx_lookup(sl, v), u = sl.hp[h];
 		sl.hr[h] |= FX_ON_PATH;
-		if (g.ts[v >> 1] <= v0) mono = false;
+		if (g.st(v >> 1) <= v0) mono = false;
 		{ // revived arcs u->v and v'->u' must have been live
 			const uint64_t iu = g.idx[u]; const uint32_t off = (uint32_t)(iu >> 32);
-			for (uint32_t i = 0; i < (uint32_t)iu; ++i) if (g.arc[off + i].v == v && g.ta[off + i] <= v0) mono = false;
+			for (uint32_t i = 0; i < (uint32_t)iu; ++i) if (g.arc[off + i].v == v && g.at(off + i) <= v0) mono = false;
 			const uint64_t ic = g.idx[v ^ 1]; const uint32_t offc = (uint32_t)(ic >> 32);
-			for (uint32_t i = 0; i < (uint32_t)ic; ++i) if (g.arc[offc + i].v == (u ^ 1) && g.ta[offc + i] <= v0) mono = false;
+			for (uint32_t i = 0; i < (uint32_t)ic; ++i) if (g.arc[offc + i].v == (u ^ 1) && g.at(offc + i) <= v0) mono = false;
 		}
 		v = u;
 	} while (v != v0);
@@ -316,19 +335,19 @@ FX_HD_NOINL bool fx_bub_backtrack(const FxView &g, uint32_t v0, const FxSlot &sl
 		if (sl.hr[sl.bslot[i]] & FX_ON_PATH) continue;
 		const uint32_t h = fx_lookup(sl, x ^ 1);
 		if (h != FX_EMPTY && (sl.hr[h] & FX_ON_PATH)) continue;
-		fx_stamp(&g.ns[x >> 1], t);
+		g.stamp_s(x >> 1, t);
 	}
 	for (uint32_t i = 0; i < w.ne; ++i) { // arcs and their complements
 		const DArc a = g.arc[sl.e[i]];
 		const uint32_t u = (uint32_t)(a.ul >> 32), x = a.v;
-		if (!fx_revived(sl, u, x)) fx_stamp(&g.na[sl.e[i]], t);
+		if (!fx_revived(sl, u, x)) g.stamp_a(sl.e[i], t);
 		if (!fx_revived(sl, x ^ 1, u ^ 1)) fx_arc_del(g, x ^ 1, u ^ 1, t);
 	}
 	return mono;
 }
 
 // one source of asg_pop_bubble's loop (asg.c:420-426): returns 1 = popped, 0 = nothing, -1 = scratch too small
-FX_HD int fx_bub_act(const FxView &g, uint32_t v0, uint32_t max_dist, const FxSlot &sl, uint32_t *n_tip, bool *mono)
+template <class V> FX_HD int fx_bub_act(const V &g, uint32_t v0, uint32_t max_dist, const FxSlot &sl, uint32_t *n_tip, bool *mono)
 {
 	if (!fx_is_source(g, v0)) return 0;
 	FxBubRes w;

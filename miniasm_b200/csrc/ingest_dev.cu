@@ -21,17 +21,22 @@
 #include "shard_comm.cuh"
 #include <cub/cub.cuh>
 
-struct PLine {                 // one parsed PAF line, 64 bytes
+struct PLine {                 // one parsed PAF line, in registers only
 	uint32_t ql, qs, qe, tl, ts, te, ml_rev, bl;
-	uint64_t hq, ht;           // name hashes; replaced by the dictionary slots once the insert pass ran
 	uint32_t tdelta;           // target name offset from the line start
-	uint16_t qnl, tnl;         // name lengths
-	uint8_t nf, pass, pad[2];  // number of fields (capped at 11), passes the filter
-	uint32_t pad2;
+	uint32_t qnl, tnl;         // name lengths
+	uint32_t nf;               // number of fields (capped at 11)
 };
-#define slot_q hq
-#define slot_t ht
-static_assert(sizeof(PLine) == 64, "PLine layout");
+
+// What a line leaves in HBM: 32 bytes.  The names went into the dictionary while the line was still in shared memory.
+struct __align__(16) PRec {
+	uint32_t qs, qe, ts, te;
+	uint32_t ml_rev;           // ml:31 | rev << 31
+	uint32_t bl_f;             // bl:31 | (the line has an 11th field) << 31
+	uint32_t slot_q, slot_t;   // dictionary slots of the two names; slot_q == NOSLOT: the line is not stored
+};
+static_assert(sizeof(PRec) == 32, "PRec layout");
+constexpr uint32_t NOSLOT = 0xffffffffu;
 
 // ---- line starts -----------------------------------------------------------------------------------------
 // A line starts at byte 0 and after every '\n' that is not the last byte.  Tiles of NL_TILE bytes, one CTA each,
@@ -153,7 +158,7 @@ __host__ __device__ __forceinline__ uint32_t num_field(const char *p, uint32_t s
 // instructions, 10 ms at 50 M lines); with the boundaries known up front the per-column loops are short and uniform.
 // Semantics: columns split on TAB only; numbers follow strtol(.,10) truncated to 32 bits (ml to 31); rev = first
 // byte of column 5 is '-'.  tab: this lane's column of an [11][32] shared scratch.
-__host__ __device__ __forceinline__ void parse_line(const char *p, const char *e, uint64_t seed, PLine &r, bool &too_long, uint32_t *tab)
+__host__ __device__ __forceinline__ void parse_line(const char *p, const char *e, PLine &r, uint32_t *tab)
 {
 	const uint32_t len = (uint32_t)(e - p);
 	uint32_t nt = 0;
@@ -177,20 +182,15 @@ __host__ __device__ __forceinline__ void parse_line(const char *p, const char *e
 	#define COL_S(k) ((k) ? tab[((k) - 1) * 32] + 1 : 0u)
 	#define COL_T(k) ((uint32_t)(k) < nt ? tab[(k) * 32] : len)
 	memset(&r, 0, sizeof(r));
-	r.nf = (uint8_t)nf;
-	{
-		const uint32_t t0 = COL_T(0);
-		r.hq = name_hash(p, 0, t0, seed), r.qnl = (uint16_t)t0;
-		too_long = t0 > 65535;
-	}
+	r.nf = nf;
+	r.qnl = COL_T(0);
 	if (nf > 1) r.ql = num_field(p, COL_S(1), COL_T(1));
 	if (nf > 2) r.qs = num_field(p, COL_S(2), COL_T(2));
 	if (nf > 3) r.qe = num_field(p, COL_S(3), COL_T(3));
 	if (nf > 4) { const uint32_t s4 = COL_S(4); r.ml_rev = (COL_T(4) > s4 && p[s4] == '-') ? 0x80000000u : 0; }
 	if (nf > 5) {
 		const uint32_t s5 = COL_S(5), t5 = COL_T(5);
-		r.ht = name_hash(p, s5, t5, seed), r.tnl = (uint16_t)(t5 - s5), r.tdelta = s5;
-		too_long |= t5 - s5 > 65535;
+		r.tnl = t5 - s5, r.tdelta = s5;
 	}
 	if (nf > 6) r.tl = num_field(p, COL_S(6), COL_T(6));
 	if (nf > 7) r.ts = num_field(p, COL_S(7), COL_T(7));
@@ -201,20 +201,66 @@ __host__ __device__ __forceinline__ void parse_line(const char *p, const char *e
 	#undef COL_T
 }
 
+// --------------------------------------------------------------------------------------------- dictionary
+// Open addressing, one 64-bit word per slot: [hash fragment : 27][byte offset of a WITNESS occurrence of the name + 1 : 37].
+// An occurrence that finds a slot with its fragment compares its bytes with the witness's bytes in the text (both names
+// end at a TAB): equal -> same name, same slot; different -> a true collision of the fragment, it simply probes on.
+// The table is therefore exact without a verification pass or a re-seeded retry.  first[slot] = smallest occurrence
+// number (2*line + {0 query, 1 target}) among the stored lines: the read's rank by it is its id (hit.c:87-90).
+struct NameTab {
+	unsigned long long *key;
+	unsigned long long *first;
+	uint32_t *id;                // read id of the slot (after ranking)
+	uint64_t mask;
+};
+constexpr int NT_OFF_BITS = 37;
+constexpr unsigned long long NT_OFF_MASK = (1ull << NT_OFF_BITS) - 1;
+
+// name = nm[0 .. nl) (shared or global memory), followed by a TAB; goff = its byte offset in `text`
+__device__ __forceinline__ uint32_t tab_insert(const NameTab &t, const char *__restrict__ text, const char *nm, uint32_t nl, uint64_t goff, uint64_t occ,
+                                               unsigned long long *overflow)
+{
+	const uint64_t h = name_hash(nm, 0, nl, 0);
+	const unsigned long long mine = (h >> 37) << NT_OFF_BITS | (goff + 1);
+	uint64_t s = h & t.mask;
+	for (int probe = 0; probe < 1 << 14; ++probe, s = (s + 1) & t.mask) {
+		unsigned long long k = t.key[s];
+		if (k == 0) {
+			k = atomicCAS(&t.key[s], 0ull, mine);
+			if (k == 0) k = mine;
+		}
+		if ((k ^ mine) >> NT_OFF_BITS) continue;                      // another fragment
+		bool same = k == mine;
+		if (!same) {
+			const char *w = text + ((k & NT_OFF_MASK) - 1);
+			same = true;
+			for (uint32_t i = 0; same && i < nl; ++i) same = w[i] == nm[i];
+			same = same && w[nl] == '\t';
+		}
+		if (!same) continue;
+		if (t.first[s] > occ) atomicMin(&t.first[s], (unsigned long long)occ); // values only decrease: the plain read filters most atomics
+		return (uint32_t)s;
+	}
+	atomicAdd(overflow, 1ull);
+	return 0;
+}
+
 // One CTA parses PARSE_LINES consecutive lines.  Their bytes are contiguous in the file, so the CTA first copies
 // the whole range into shared memory with coalesced 128-bit loads and the threads then walk their own line there:
 // byte-wise walking of global memory made every warp-level load touch ~16 cache lines (ncu: L1 wavefront bound).
 // A range that does not fit (very long lines) is parsed straight from global memory.
+// Fused into the same pass (round 1 ran them as three more sweeps over a 64-byte record): the store filter of
+// hit.c:85 and the dictionary insert of both names, while the line is still in shared memory.
 constexpr int PARSE_LINES = 128;
-constexpr int PARSE_SMEM = 24 * 1024;
+constexpr int PARSE_SMEM = 16 * 1024;
 
 __global__ void __launch_bounds__(PARSE_LINES)
 k_parse(const char *__restrict__ text, size_t len, const uint64_t *__restrict__ start, uint64_t n_lines,
-        uint64_t seed, PLine *out, unsigned long long *counts)
-{
+        int min_span, int min_match, NameTab tab, PRec *out, unsigned long long *counts)
+{	// counts: [0] lines with >= 10 fields, [1] lines stored, [2] dictionary overflow
 	__shared__ __align__(16) char s_text[PARSE_SMEM];
 	__shared__ uint32_t s_vals[PARSE_LINES / 32][11][32];
-	unsigned n_parsed = 0;
+	unsigned n_parsed = 0, n_pass = 0;
 	const uint64_t n_blk = (n_lines + PARSE_LINES - 1) / PARSE_LINES;
 	for (uint64_t b = blockIdx.x; b < n_blk; b += gridDim.x) {
 		const uint64_t l0 = b * PARSE_LINES, l1 = l0 + PARSE_LINES < n_lines ? l0 + PARSE_LINES : n_lines;
@@ -235,98 +281,38 @@ k_parse(const char *__restrict__ text, size_t len, const uint64_t *__restrict__ 
 			const char *base = staged ? s_text - a0 : text; // base + file offset = address of that byte
 			if (eol - s > 1 && base[eol - 1] == '\r') --eol;
 			PLine r;
-			bool too_long = false;
-			parse_line(base + s, base + eol, seed, r, too_long, &s_vals[threadIdx.x >> 5][0][threadIdx.x & 31]);
+			parse_line(base + s, base + eol, r, &s_vals[threadIdx.x >> 5][0][threadIdx.x & 31]);
+			PRec o;
+			o.qs = r.qs, o.qe = r.qe, o.ts = r.ts, o.te = r.te, o.ml_rev = r.ml_rev;
+			o.bl_f = (r.bl & 0x7fffffffu) | (r.nf >= 11 ? 0x80000000u : 0u);
+			o.slot_q = NOSLOT, o.slot_t = 0;
 			if (r.nf >= 10) {
 				++n_parsed;
-				if (too_long) atomicAdd(counts + 1, 1ull); // a name beyond 65535 bytes does not fit the record: the host aborts
+				if (!(r.qe - r.qs < (uint32_t)min_span || r.te - r.ts < (uint32_t)min_span || (int)(r.ml_rev & 0x7fffffffu) < min_match)) {
+					++n_pass;
+					o.slot_q = tab_insert(tab, text, base + s, r.qnl, s, 2 * i, counts + 2);
+					o.slot_t = tab_insert(tab, text, base + s + r.tdelta, r.tnl, s + r.tdelta, 2 * i + 1, counts + 2);
+				}
 			}
-			out[i] = r;
+			*reinterpret_cast<uint4*>(out + i) = make_uint4(o.qs, o.qe, o.ts, o.te);
+			*(reinterpret_cast<uint4*>(out + i) + 1) = make_uint4(o.ml_rev, o.bl_f, o.slot_q, o.slot_t);
 		}
 	}
-	n_parsed = __reduce_add_sync(0xffffffffu, n_parsed);
-	if ((threadIdx.x & 31) == 0 && n_parsed) atomicAdd(counts, (unsigned long long)n_parsed);
-}
-
-// stale bl for 10-field lines + the store filter (needs the final bl? no: the filter uses qe,qs,te,ts,ml only)
-__global__ void k_fix_filter(PLine *ln, uint64_t n_lines, int min_span, int min_match, unsigned long long *n_pass, uint32_t carry_bl = 0)
-{	// carry_bl: bl left behind by the lines before this rank's byte range (sharded runs), else 0
-	unsigned cnt = 0;
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
-		PLine *r = ln + i;
-		bool pass = false;
-		if (r->nf >= 10) {
-			if (r->nf == 10) { // bl keeps the value of the closest earlier line that had an 11th field (paf.c:47, hit.c:73)
-				uint32_t bl = carry_bl;
-				for (uint64_t j = i; j-- > 0;)
-					if (ln[j].nf >= 11) { bl = ln[j].bl; break; }
-				r->bl = bl;
-			}
-			pass = !(r->qe - r->qs < (uint32_t)min_span || r->te - r->ts < (uint32_t)min_span || (int)(r->ml_rev & 0x7fffffffu) < min_match);
-		}
-		r->pass = pass;
-		cnt += pass;
-	}
-	cnt = __reduce_add_sync(0xffffffffu, cnt);
-	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_pass, (unsigned long long)cnt);
-}
-
-// --------------------------------------------------------------------------------------------- dictionary
-struct NameTab {
-	unsigned long long *key;     // 64-bit name hash, 0 = empty
-	unsigned long long *first;   // smallest occurrence number (2*line + {0 query, 1 target})
-	uint32_t *id;                // read id of the slot (after ranking)
-	uint64_t mask;
-};
-
-__device__ __forceinline__ uint32_t tab_insert(const NameTab &t, uint64_t h, uint64_t occ, unsigned long long *overflow)
-{
-	uint64_t s = h & t.mask;
-	for (int probe = 0; probe < 1 << 14; ++probe, s = (s + 1) & t.mask) {
-		unsigned long long k = t.key[s];
-		if (k == 0) {
-			k = atomicCAS(&t.key[s], 0ull, (unsigned long long)h);
-			if (k == 0) k = h;
-		}
-		if (k == h) {
-			if (t.first[s] > occ) atomicMin(&t.first[s], (unsigned long long)occ); // values only decrease: the plain read filters most atomics
-			return (uint32_t)s;
-		}
-	}
-	atomicAdd(overflow, 1ull);
-	return 0xffffffffu;
-}
-
-__global__ void k_dict_insert(PLine *ln, uint64_t n_lines, NameTab t, unsigned long long *overflow)
-{
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
-		if (!ln[i].pass) continue;
-		const uint64_t hq = ln[i].hq, ht = ln[i].ht;
-		ln[i].slot_q = tab_insert(t, hq, 2 * i, overflow);
-		ln[i].slot_t = tab_insert(t, ht, 2 * i + 1, overflow);
+	n_parsed = __reduce_add_sync(0xffffffffu, n_parsed), n_pass = __reduce_add_sync(0xffffffffu, n_pass);
+	if ((threadIdx.x & 31) == 0) {
+		if (n_parsed) atomicAdd(counts, (unsigned long long)n_parsed);
+		if (n_pass) atomicAdd(counts + 1, (unsigned long long)n_pass);
 	}
 }
 
-__device__ __forceinline__ bool same_name(const char *text, const uint64_t *start, const PLine *ln, uint64_t occ_a, uint64_t occ_b)
+// bl of a 10-field line: the value of the closest earlier line that had an 11th field (paf.c:47, hit.c:73);
+// carry_bl = what the lines before this rank's byte range left behind (sharded runs), else 0
+__device__ __forceinline__ uint32_t line_bl(const PRec *ln, uint64_t i, uint32_t carry_bl)
 {
-	const PLine &a = ln[occ_a >> 1], &b = ln[occ_b >> 1];
-	const uint32_t la = occ_a & 1 ? a.tnl : a.qnl, lb = occ_b & 1 ? b.tnl : b.qnl;
-	if (la != lb) return false;
-	const char *pa = text + start[occ_a >> 1] + (occ_a & 1 ? a.tdelta : 0), *pb = text + start[occ_b >> 1] + (occ_b & 1 ? b.tdelta : 0);
-	for (uint32_t k = 0; k < la; ++k)
-		if (pa[k] != pb[k]) return false;
-	return true;
-}
-
-// every occurrence must spell the same name as the representative (first occurrence) of its slot
-__global__ void k_dict_verify(const char *text, const uint64_t *start, const PLine *ln, uint64_t n_lines, NameTab t, unsigned long long *n_bad)
-{
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
-		if (!ln[i].pass) continue;
-		uint64_t fq = t.first[ln[i].slot_q], ft = t.first[ln[i].slot_t];
-		bool ok = (fq == 2 * i || same_name(text, start, ln, 2 * i, fq)) && (ft == 2 * i + 1 || same_name(text, start, ln, 2 * i + 1, ft));
-		if (!ok) atomicAdd(n_bad, 1ull);
-	}
+	if (ln[i].bl_f >> 31) return ln[i].bl_f & 0x7fffffffu;
+	for (uint64_t j = i; j-- > 0;)
+		if (ln[j].bl_f >> 31) return ln[j].bl_f & 0x7fffffffu;
+	return carry_bl & 0x7fffffffu;
 }
 
 struct SlotUsed { // a name is in the dictionary iff some stored line carries it (after -R: iff such a line is left)
@@ -334,32 +320,50 @@ struct SlotUsed { // a name is in the dictionary iff some stored line carries it
 	__device__ __forceinline__ bool operator()(uint64_t s) const { return first[s] != ~0ull; }
 };
 
+// name and sequence length of an occurrence (2*line + role), read back from the text: the name starts the line (query) or
+// follows the 5th TAB (target) and its length column comes right after it
+__device__ __forceinline__ void occ_name(const char *text, const uint64_t *start, uint64_t occ, uint64_t *noff, uint32_t *nlen, uint32_t *slen)
+{
+	const char *p = text + start[occ >> 1];
+	uint64_t q = 0;
+	if (occ & 1) { int tabs = 0; while (tabs < 5) tabs += p[q++] == '\t'; }
+	uint64_t e = q;
+	while (p[e] != '\t') ++e;
+	*noff = start[occ >> 1] + q, *nlen = (uint32_t)(e - q);
+	uint64_t f = e + 1;
+	while (p[f] != '\t') ++f;
+	*slen = field_to_u32(p + e + 1, p + f);
+}
+
 // ---- -R: ma_hit_no_cont (hit.c:38-68) as two passes over the parsed lines -----------------------------------------
 // A read is dropped when some stored line shows it clearly inside a read at least twice as long; every line that
 // names a dropped read is skipped BEFORE ids are given out (hit.c:86), so first appearances are taken again afterwards.
-__global__ void k_nocont_mark(const PLine *ln, uint64_t n_lines, int max_hang, float int_frac, uint8_t *excl)
+__global__ void k_nocont_mark(const PRec *ln, uint64_t n_lines, const char *text, const uint64_t *start, int max_hang, float int_frac, uint8_t *excl)
 {
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
-		const PLine r = ln[i];
-		if (!r.pass) continue;
+		const PRec r = ln[i];
+		if (r.slot_q == NOSLOT) continue;
+		uint64_t no; uint32_t nl, ql, tl;                              // the two length columns are not kept in the record: read them back
+		occ_name(text, start, 2 * i, &no, &nl, &ql);
+		occ_name(text, start, 2 * i + 1, &no, &nl, &tl);
 		const bool rev = r.ml_rev >> 31;
-		const int l5 = (int)(rev ? r.tl - r.te : r.ts), l3 = (int)(rev ? r.ts : r.tl - r.te);
-		if (r.ql >> 1 > r.tl) { // query at least twice as long: is the target inside it?
-			if (l5 > max_hang >> 2 || l3 > max_hang >> 2 || (float)(r.te - r.ts) < __fmul_rn((float)r.tl, int_frac)) continue; // internal match
-			if ((int)r.qs - l5 > max_hang << 1 && (int)(r.ql - r.qe) - l3 > max_hang << 1) excl[r.slot_t] = 1;
-		} else if (r.ql < r.tl >> 1) {
-			if (r.qs > (uint32_t)(max_hang >> 2) || r.ql - r.qe > (uint32_t)(max_hang >> 2) || (float)(r.qe - r.qs) < __fmul_rn((float)r.ql, int_frac)) continue;
-			if (l5 - (int)r.qs > max_hang << 1 && l3 - (int)(r.ql - r.qe) > max_hang << 1) excl[r.slot_q] = 1;
+		const int l5 = (int)(rev ? tl - r.te : r.ts), l3 = (int)(rev ? r.ts : tl - r.te);
+		if (ql >> 1 > tl) { // query at least twice as long: is the target inside it?
+			if (l5 > max_hang >> 2 || l3 > max_hang >> 2 || (float)(r.te - r.ts) < __fmul_rn((float)tl, int_frac)) continue; // internal match
+			if ((int)r.qs - l5 > max_hang << 1 && (int)(ql - r.qe) - l3 > max_hang << 1) excl[r.slot_t] = 1;
+		} else if (ql < tl >> 1) {
+			if (r.qs > (uint32_t)(max_hang >> 2) || ql - r.qe > (uint32_t)(max_hang >> 2) || (float)(r.qe - r.qs) < __fmul_rn((float)ql, int_frac)) continue;
+			if (l5 - (int)r.qs > max_hang << 1 && l3 - (int)(ql - r.qe) > max_hang << 1) excl[r.slot_q] = 1;
 		}
 	}
 }
 
-__global__ void k_nocont_drop(PLine *ln, uint64_t n_lines, const uint8_t *excl, NameTab t)
+__global__ void k_nocont_drop(PRec *ln, uint64_t n_lines, const uint8_t *excl, NameTab t)
 {
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
-		if (!ln[i].pass) continue;
-		const uint64_t sq = ln[i].slot_q, st = ln[i].slot_t;
-		if (excl[sq] || excl[st]) { ln[i].pass = 0; continue; }
+		const uint32_t sq = ln[i].slot_q, st = ln[i].slot_t;
+		if (sq == NOSLOT) continue;
+		if (excl[sq] || excl[st]) { ln[i].slot_q = NOSLOT; continue; }
 		if (t.first[sq] > 2 * i) atomicMin(&t.first[sq], (unsigned long long)(2 * i));
 		if (t.first[st] > 2 * i + 1) atomicMin(&t.first[st], (unsigned long long)(2 * i + 1));
 	}
@@ -379,16 +383,12 @@ __global__ void k_dict_pairs(const uint64_t *slots, uint32_t n, NameTab t, unsig
 }
 
 __global__ void k_dict_rank(const unsigned long long *first_sorted, const uint64_t *slot_sorted, uint32_t n, NameTab t,
-                            const uint64_t *start, const PLine *ln, uint64_t *noff, uint32_t *nlen, uint32_t *slen, unsigned long long *tot_len)
+                            const char *text, const uint64_t *start, uint64_t *noff, uint32_t *nlen, uint32_t *slen, unsigned long long *tot_len)
 {
 	unsigned long long sum = 0;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const uint64_t occ = first_sorted[i];
-		const PLine &r = ln[occ >> 1];
 		t.id[slot_sorted[i]] = i;
-		noff[i] = start[occ >> 1] + (occ & 1 ? r.tdelta : 0);
-		nlen[i] = occ & 1 ? r.tnl : r.qnl;
-		slen[i] = occ & 1 ? r.tl : r.ql;
+		occ_name(text, start, first_sorted[i], &noff[i], &nlen[i], &slen[i]); // the length kept for a read is the one of its first appearance (sdict.c:36)
 		sum += slen[i];
 	}
 	typedef cub::BlockReduce<unsigned long long, 256> BR;
@@ -398,29 +398,29 @@ __global__ void k_dict_rank(const unsigned long long *first_sorted, const uint64
 }
 
 // --------------------------------------------------------------------------------------------- hits
-__global__ void k_hit_count(const PLine *ln, uint64_t n_lines, int bi_dir, uint32_t *cnt)
+__global__ void k_hit_count(const PRec *ln, uint64_t n_lines, int bi_dir, uint32_t *cnt)
 {
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x)
-		cnt[i] = ln[i].pass ? (bi_dir && ln[i].slot_q != ln[i].slot_t ? 2 : 1) : 0;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint2 sl = *reinterpret_cast<const uint2*>(&ln[i].slot_q);
+		cnt[i] = sl.x != NOSLOT ? (bi_dir && sl.x != sl.y ? 2 : 1) : 0;
+	}
 }
 
-__global__ void k_hit_emit(const PLine *ln, uint64_t n_lines, const uint32_t *cnt, const uint64_t *off, NameTab t, DHit *out, unsigned *max_qs)
+__global__ void k_hit_emit(const PRec *ln, uint64_t n_lines, const uint32_t *cnt, const uint64_t *off, NameTab t, DHit *out, unsigned *max_qs)
 {
 	unsigned mx = 0;
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
 		const uint32_t c = cnt[i];
 		if (c == 0) continue;
-		const PLine r = ln[i];
-		const uint32_t qid = t.id[r.slot_q], tid = t.id[r.slot_t];
-		DHit h;
-		h.qns = (uint64_t)qid << 32 | r.qs, h.qe = r.qe, h.tn = tid, h.ts = r.ts, h.te = r.te, h.ml_rev = r.ml_rev, h.bl_del = r.bl & 0x7fffffffu;
+		const PRec r = ln[i];
+		const uint32_t qid = t.id[r.slot_q], tid = t.id[r.slot_t], bl = line_bl(ln, i, 0);
 		uint4 *o = reinterpret_cast<uint4*>(out + off[i]);
-		o[0] = make_uint4((uint32_t)h.qns, (uint32_t)(h.qns >> 32), h.qe, h.tn);
-		o[1] = make_uint4(h.ts, h.te, h.ml_rev, h.bl_del);
+		o[0] = make_uint4(r.qs, qid, r.qe, tid);
+		o[1] = make_uint4(r.ts, r.te, r.ml_rev, bl);
 		mx = r.qs > mx ? r.qs : mx;
 		if (c == 2) { // the same overlap seen from the target (hit.c:92-98)
 			o[2] = make_uint4(r.ts, tid, r.te, qid);
-			o[3] = make_uint4(r.qs, r.qe, h.ml_rev, h.bl_del);
+			o[3] = make_uint4(r.qs, r.qe, r.ml_rev, bl);
 			mx = r.ts > mx ? r.ts : mx;
 		}
 	}
@@ -475,50 +475,34 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 	st.n_lines = n_lines;
 	d.trace("ingest:line_starts");
 
-	// (2) parse
-	PLine *ln = mab_alloc<PLine>(d, n_lines);
+	// (2) parse + store filter + dictionary insert in one pass; the table grows (and the pass repeats) until every name has a slot
+	if (len >= (1ull << NT_OFF_BITS) - 1) { fprintf(stderr, "[E::miniasm_b200] more than 2^37 bytes of PAF on one GPU\n"); exit(73); }
+	PRec *ln = mab_alloc<PRec>(d, n_lines);
 	uint32_t *cnt = nullptr;
 	uint64_t *off = nullptr;
 	NameTab tab{nullptr, nullptr, nullptr, 0};
-	uint64_t n_pass = 0, cap = 0;
-	uint64_t seed = 0;
-	for (int attempt = 0;; ++attempt) {
-		d.zero_scal(SC_COUNT, 4);
-		MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, n_lines, seed, ln, d.d_scal + SC_COUNT);
-		MAB_LAUNCH(d, k_fix_filter, mab_grid(n_lines, 256), 256, 0, ln, n_lines, min_span, min_match, d.d_scal + SC_AUX);
-		st.n_parsed = d.get_scal(SC_COUNT);
-		n_pass = d.h_scal[SC_AUX];
-		d.trace("ingest:parse+filter");
-		if (d.h_scal[SC_COUNT + 1]) { fprintf(stderr, "[E::miniasm_b200] a read name in the PAF is longer than 65535 bytes\n"); exit(78); }
-		// (3) dictionary: grow the table until every name finds a slot, re-seed the hash on a verified collision
-		if (cap == 0) { cap = 1ull << 20; while (cap < n_pass / 4) cap <<= 1; }
-		bool collided = false, overflowed = false;
+	uint64_t cap = 1ull << 20;
+	while (cap < n_lines / 4) cap <<= 1;                 // ~50 lines name a read twice each: load <= 1/6 at that ratio; overflow quadruples it
+	for (;;) {
 		tab.key = (unsigned long long*)mab_alloc<uint64_t>(d, cap);
 		tab.first = (unsigned long long*)mab_alloc<uint64_t>(d, cap);
 		tab.id = mab_alloc<uint32_t>(d, cap);
 		tab.mask = cap - 1;
 		MAB_CUDA(cudaMemsetAsync(tab.key, 0, cap * 8, d.stream));
 		MAB_CUDA(cudaMemsetAsync(tab.first, 0xff, cap * 8, d.stream));
-		d.zero_scal(SC_BIG, 1);
-		d.zero_scal(SC_AUX2, 1);
-		MAB_LAUNCH(d, k_dict_insert, mab_grid(n_lines, 256), 256, 0, ln, n_lines, tab, d.d_scal + SC_BIG);
-		if (d.get_scal(SC_BIG) == 0) {
-			MAB_LAUNCH(d, k_dict_verify, mab_grid(n_lines, 256), 256, 0, d_text, start, ln, n_lines, tab, d.d_scal + SC_AUX2);
-			collided = d.get_scal(SC_AUX2) != 0;
-		} else overflowed = true;
-		if (!collided && !overflowed) break;
+		d.zero_scal(SC_COUNT, 4);
+		MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, n_lines, min_span, min_match, tab, ln, d.d_scal + SC_COUNT);
+		st.n_parsed = d.get_scal(SC_COUNT);
+		if (d.h_scal[SC_COUNT + 2] == 0) break;
 		d.free(tab.key); d.free(tab.first); d.free(tab.id);
-		if (overflowed) { cap <<= 2; continue; }       // table too small for the number of distinct names: parse again (the insert pass reuses the hash fields)
-		seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; // two names share a 64-bit hash: hash again with another seed
-		++st.hash_retries;
-		if (attempt > 16) { fprintf(stderr, "[E::miniasm_b200] read-name hashing keeps colliding\n"); exit(77); }
+		cap <<= 2;
+		if (cap > (1ull << 33)) { fprintf(stderr, "[E::miniasm_b200] read-name table overflow\n"); exit(77); }
 	}
-
 	d.trace("ingest:dictionary");
 	if (nocont) { // -R: mark the contained reads, drop every line that names one, take the first appearances again
 		uint8_t *excl = mab_alloc<uint8_t>(d, cap);
 		MAB_CUDA(cudaMemsetAsync(excl, 0, cap, d.stream));
-		MAB_LAUNCH(d, k_nocont_mark, mab_grid(n_lines, 256), 256, 0, ln, n_lines, nocont->max_hang, nocont->int_frac, excl);
+		MAB_LAUNCH(d, k_nocont_mark, mab_grid(n_lines, 256), 256, 0, ln, n_lines, d_text, start, nocont->max_hang, nocont->int_frac, excl);
 		d.zero_scal(SC_AUX, 1);
 		MAB_LAUNCH(d, k_count_u8, mab_grid(cap, 256), 256, 0, excl, cap, d.d_scal + SC_AUX);
 		MAB_CUDA(cudaMemsetAsync(tab.first, 0xff, cap * 8, d.stream));
@@ -558,7 +542,7 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 		cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int)n_seq, 0, end_bit, d.stream);
 		++d.n_lib;
 		d.zero_scal(SC_AUX, 1);
-		MAB_LAUNCH(d, k_dict_rank, mab_grid(n_seq, 256), 256, 0, dk.Current(), dv.Current(), n_seq, tab, start, ln, names.off, names.nlen, names.slen, d.d_scal + SC_AUX);
+		MAB_LAUNCH(d, k_dict_rank, mab_grid(n_seq, 256), 256, 0, dk.Current(), dv.Current(), n_seq, tab, d_text, start, names.off, names.nlen, names.slen, d.d_scal + SC_AUX);
 		st.tot_len = d.get_scal(SC_AUX);
 		d.free(fa); d.free(fb); d.free(sb);
 	}
@@ -603,13 +587,12 @@ extern "C" int mab_test_parse_line(const char *line, size_t len, uint32_t *out)
 {
 	static uint32_t vals[11 * 32];
 	PLine r;
-	bool too_long = false;
 	size_t eol = len;
 	if (eol > 1 && line[eol - 1] == '\r') --eol;
-	parse_line(line, line + eol, 0, r, too_long, vals);
+	parse_line(line, line + eol, r, vals);
 	out[0] = r.nf, out[1] = r.ql, out[2] = r.qs, out[3] = r.qe, out[4] = r.ml_rev >> 31, out[5] = r.tl, out[6] = r.ts, out[7] = r.te;
 	out[8] = r.ml_rev & 0x7fffffffu, out[9] = r.bl, out[10] = r.qnl, out[11] = r.tnl, out[12] = r.tdelta;
-	return too_long ? -1 : 0;
+	return 0;
 }
 
 // =============================================================================================================
@@ -619,11 +602,11 @@ extern "C" int mab_test_parse_line(const char *line, size_t len, uint32_t *out)
 // rank that owns its query read (id mod world) in one all-to-all; per-source order is file order, so the stable sort
 // that follows sees the hits of a read in the same order as a single GPU would.
 // =============================================================================================================
-__global__ void k_last_bl(const PLine *ln, uint64_t n_lines, unsigned long long *out) // out[0] = 1 + index of the last line with an 11th field
+__global__ void k_last_bl(const PRec *ln, uint64_t n_lines, unsigned long long *out) // out[0] = 1 + index of the last line with an 11th field
 {
 	unsigned long long mx = 0; // per-thread maximum over its grid-stride share, one atomic per warp at the end
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x)
-		if (ln[i].nf >= 11) mx = i + 1;
+		if (ln[i].bl_f >> 31) mx = i + 1;
 	#pragma unroll
 	for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o); mx = t > mx ? t : mx; }
 	if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
@@ -631,30 +614,26 @@ __global__ void k_last_bl(const PLine *ln, uint64_t n_lines, unsigned long long 
 
 struct GEntry { unsigned long long hash, first; uint32_t slen, nlen; }; // a distinct name of one rank, 24 bytes
 
-__global__ void k_local_entries(const uint64_t *slots, uint32_t n, NameTab t, const uint64_t *start, const PLine *ln, uint64_t line_base,
-                                GEntry *ent, uint32_t *name_sz)
-{
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const uint64_t s = slots[i], occ = t.first[s];
-		const PLine &r = ln[occ >> 1];
-		GEntry e;
-		e.hash = t.key[s], e.first = 2 * line_base + occ;
-		e.nlen = occ & 1 ? r.tnl : r.qnl, e.slen = occ & 1 ? r.tl : r.ql;
-		ent[i] = e;
-		name_sz[i] = e.nlen;
-	}
-}
-
-__global__ void k_local_names(const uint64_t *slots, uint32_t n, NameTab t, const uint64_t *start, const PLine *ln, const char *text,
-                              const uint64_t *pos, char *out)
+__global__ void k_local_entries(const uint64_t *slots, uint32_t n, NameTab t, const char *text, const uint64_t *start, uint64_t line_base, uint64_t seed,
+                                GEntry *ent, uint32_t *name_sz, uint64_t *name_off)
 {
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint64_t occ = t.first[slots[i]];
-		const PLine &r = ln[occ >> 1];
-		const uint32_t l = occ & 1 ? r.tnl : r.qnl;
-		const char *src = text + start[occ >> 1] + (occ & 1 ? r.tdelta : 0);
+		GEntry e;
+		uint64_t no;
+		occ_name(text, start, occ, &no, &e.nlen, &e.slen);
+		e.hash = name_hash(text + no, 0, e.nlen, seed), e.first = 2 * line_base + occ;
+		ent[i] = e;
+		name_sz[i] = e.nlen, name_off[i] = no;
+	}
+}
+
+__global__ void k_local_names(uint32_t n, const uint64_t *name_off, const uint32_t *name_sz, const char *text, const uint64_t *pos, char *out)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const char *src = text + name_off[i];
 		char *dst = out + pos[i];
-		for (uint32_t k = 0; k < l; ++k) dst[k] = src[k];
+		for (uint32_t k = 0; k < name_sz[i]; ++k) dst[k] = src[k];
 	}
 }
 
@@ -718,35 +697,30 @@ __global__ void k_gtab_rank(const uint64_t *slot_sorted, uint32_t n, GTab t, con
 	if (threadIdx.x == 0 && sm) atomicAdd(tot_len, sm);
 }
 
-// global read ids of the two names of every stored line + number of hits the line yields
-__global__ void k_line_gids(PLine *ln, uint64_t n_lines, NameTab lt, GTab gt, int bi_dir, uint32_t *cnt)
+// local dictionary slot -> global read id (entry i of this rank sits at slots[i] locally and at slot_of[i] in the global table)
+__global__ void k_local_gid(const uint64_t *slots, uint32_t n, const uint32_t *slot_of, GTab gt, NameTab lt)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) lt.id[slots[i]] = gt.id[slot_of[i]];
+}
+
+// number of hits every line yields
+__global__ void k_line_gids(const PRec *ln, uint64_t n_lines, NameTab lt, int bi_dir, uint32_t *cnt)
 {
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
-		uint32_t c = 0;
-		if (ln[i].pass) {
-			uint32_t g[2];
-			#pragma unroll
-			for (int k = 0; k < 2; ++k) {
-				const unsigned long long h = lt.key[k ? ln[i].slot_t : ln[i].slot_q];
-				uint64_t s = h & gt.mask;
-				while (gt.key[s] != h) s = (s + 1) & gt.mask; // present by construction
-				g[k] = gt.id[s];
-			}
-			ln[i].slot_q = g[0], ln[i].slot_t = g[1]; // the slot fields now carry global read ids
-			c = bi_dir && g[0] != g[1] ? 2 : 1;
-		}
-		cnt[i] = c;
+		const uint2 sl = *reinterpret_cast<const uint2*>(&ln[i].slot_q);
+		cnt[i] = sl.x != NOSLOT ? (bi_dir && lt.id[sl.x] != lt.id[sl.y] ? 2 : 1) : 0;
 	}
 }
 
-__global__ void k_hit_emit_gid(const PLine *ln, uint64_t n_lines, const uint32_t *cnt, const uint64_t *off, uint32_t world, DHit *out, uint32_t *dest, unsigned *max_qs)
+__global__ void k_hit_emit_gid(const PRec *ln, uint64_t n_lines, const uint32_t *cnt, const uint64_t *off, NameTab lt, uint32_t carry_bl, uint32_t world,
+                               DHit *out, uint32_t *dest, unsigned *max_qs)
 {
 	unsigned mx = 0;
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
 		const uint32_t c = cnt[i];
 		if (c == 0) continue;
-		const PLine r = ln[i];
-		const uint32_t qid = (uint32_t)r.slot_q, tid = (uint32_t)r.slot_t, bl = r.bl & 0x7fffffffu;
+		const PRec r = ln[i];
+		const uint32_t qid = lt.id[r.slot_q], tid = lt.id[r.slot_t], bl = line_bl(ln, i, carry_bl);
 		uint4 *o = reinterpret_cast<uint4*>(out + off[i]);
 		o[0] = make_uint4(r.qs, qid, r.qe, tid);
 		o[1] = make_uint4(r.ts, r.te, r.ml_rev, bl);
@@ -821,78 +795,76 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		d.free(cnt); d.free(base);
 	}
 	d.trace("shard-ingest:line_starts");
-	PLine *ln = mab_alloc<PLine>(d, n_lines);
+	if (len >= (1ull << NT_OFF_BITS) - 1) { fprintf(stderr, "[E::miniasm_b200] more than 2^37 bytes of PAF on one GPU\n"); exit(73); }
+	PRec *ln = mab_alloc<PRec>(d, n_lines);
 	std::vector<uint64_t> all_lines = sc_allgather_u64(d, sc, n_lines);
 	uint64_t line_base = 0, n_lines_all = 0;
 	for (int r = 0; r < G; ++r) { if (r < sc.rank) line_base += all_lines[r]; n_lines_all += all_lines[r]; }
 	st.n_lines = n_lines_all;
 
-	uint64_t seed = 0, cap = 0;
+	// (2) parse + store filter + local dictionary in one pass (exact: occurrences are compared with a witness in the text)
 	NameTab tab{nullptr, nullptr, nullptr, 0};
-	GTab gt{nullptr, nullptr, nullptr, nullptr, 0};
-	GEntry *g_ent = nullptr;
-	char *g_names = nullptr;
-	uint64_t *g_pos = nullptr;
-	uint64_t n_ent_all = 0, name_bytes_all = 0;
-	for (int attempt = 0;; ++attempt) {
-		d.zero_scal(SC_COUNT, 4);
-		if (n_lines) MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, n_lines, seed, ln, d.d_scal + SC_COUNT);
-		// bl carried over from earlier ranks for 10-field lines at the head of this range
-		d.zero_scal(SC_TMP0, 1);
-		if (n_lines) MAB_LAUNCH(d, k_last_bl, mab_grid(n_lines, 256), 256, 0, ln, n_lines, d.d_scal + SC_TMP0);
-		uint64_t last11 = d.get_scal(SC_TMP0);
-		uint32_t my_bl = 0;
-		if (last11) { MAB_CUDA(cudaMemcpyAsync(&my_bl, &ln[last11 - 1].bl, 4, cudaMemcpyDeviceToHost, d.stream)); d.sync(); }
-		std::vector<uint64_t> bls = sc_allgather_u64(d, sc, last11 ? ((uint64_t)1 << 32 | my_bl) : 0);
-		uint32_t carry = 0;
-		for (int r = 0; r < sc.rank; ++r) if (bls[r] >> 32) carry = (uint32_t)bls[r];
-		if (n_lines) MAB_LAUNCH(d, k_fix_filter, mab_grid(n_lines, 256), 256, 0, ln, n_lines, min_span, min_match, d.d_scal + SC_AUX, carry);
-		st.n_parsed = d.get_scal(SC_COUNT);
-		const uint64_t n_pass = d.h_scal[SC_AUX];
-		if (d.h_scal[SC_COUNT + 1]) { fprintf(stderr, "[E::miniasm_b200] a read name in the PAF is longer than 65535 bytes\n"); exit(78); }
-		d.trace("shard-ingest:parse+filter");
-		// (2) local dictionary
-		if (cap == 0) { cap = 1ull << 20; while (cap < n_pass / 4) cap <<= 1; }
-		bool bad = false, overflowed = false;
+	uint64_t cap = 1ull << 20;
+	while (cap < n_lines / 4) cap <<= 1;
+	for (;;) {
 		tab.key = (unsigned long long*)mab_alloc<uint64_t>(d, cap); tab.first = (unsigned long long*)mab_alloc<uint64_t>(d, cap); tab.id = mab_alloc<uint32_t>(d, cap);
 		tab.mask = cap - 1;
 		MAB_CUDA(cudaMemsetAsync(tab.key, 0, cap * 8, d.stream));
 		MAB_CUDA(cudaMemsetAsync(tab.first, 0xff, cap * 8, d.stream));
-		d.zero_scal(SC_BIG, 1); d.zero_scal(SC_AUX2, 1);
-		if (n_lines) MAB_LAUNCH(d, k_dict_insert, mab_grid(n_lines, 256), 256, 0, ln, n_lines, tab, d.d_scal + SC_BIG);
-		if (d.get_scal(SC_BIG) == 0) {
-			if (n_lines) MAB_LAUNCH(d, k_dict_verify, mab_grid(n_lines, 256), 256, 0, d_text, start, ln, n_lines, tab, d.d_scal + SC_AUX2);
-			bad = d.get_scal(SC_AUX2) != 0;
-		} else overflowed = true;
+		d.zero_scal(SC_COUNT, 4);
+		if (n_lines) MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, n_lines, min_span, min_match, tab, ln, d.d_scal + SC_COUNT);
+		st.n_parsed = d.get_scal(SC_COUNT);
 		// every rank must take the same branch: agree on the outcome
-		{
-			std::vector<uint64_t> f = sc_allgather_u64(d, sc, (uint64_t)bad | (uint64_t)overflowed << 1);
-			bad = overflowed = false;
-			for (int r = 0; r < G; ++r) bad |= f[r] & 1, overflowed |= (f[r] >> 1) & 1;
-		}
-		if (overflowed) { d.free(tab.key); d.free(tab.first); d.free(tab.id); cap <<= 2; continue; }
-		d.trace("shard-ingest:local dictionary");
-		// (3) distinct names of this rank -> entries + packed names, all-gathered
-		uint32_t n_ent = 0;
-		uint64_t *slots = mab_alloc<uint64_t>(d, cap);
-		if (!bad) {
-			cub::CountingInputIterator<uint64_t> pos(0);
-			SlotUsed used{tab.first};
-			size_t tb = 0;
-			unsigned long long *d_n = d.d_scal + SC_NSEL;
-			cub::DeviceSelect::If(nullptr, tb, pos, slots, d_n, (int64_t)cap, used, d.stream);
-			void *tmp = d.tmp(tb);
-			cub::DeviceSelect::If(tmp, tb, pos, slots, d_n, (int64_t)cap, used, d.stream);
-			++d.n_lib;
-			n_ent = (uint32_t)d.get_scal(SC_NSEL);
-		}
+		std::vector<uint64_t> f = sc_allgather_u64(d, sc, d.h_scal[SC_COUNT + 2] != 0);
+		bool overflowed = false;
+		for (int r = 0; r < G; ++r) overflowed |= f[r] != 0;
+		if (!overflowed) break;
+		d.free(tab.key); d.free(tab.first); d.free(tab.id);
+		cap <<= 2;
+		if (cap > (1ull << 33)) { fprintf(stderr, "[E::miniasm_b200] read-name table overflow\n"); exit(77); }
+	}
+	d.trace("shard-ingest:parse+filter+local dictionary");
+	// bl carried over from earlier ranks for 10-field lines at the head of this range (applied when the hits are emitted)
+	uint32_t carry = 0;
+	{
+		d.zero_scal(SC_TMP0, 1);
+		if (n_lines) MAB_LAUNCH(d, k_last_bl, mab_grid(n_lines, 256), 256, 0, ln, n_lines, d.d_scal + SC_TMP0);
+		uint64_t last11 = d.get_scal(SC_TMP0);
+		uint32_t my_bl = 0;
+		if (last11) { MAB_CUDA(cudaMemcpyAsync(&my_bl, &ln[last11 - 1].bl_f, 4, cudaMemcpyDeviceToHost, d.stream)); d.sync(); my_bl &= 0x7fffffffu; }
+		std::vector<uint64_t> bls = sc_allgather_u64(d, sc, last11 ? ((uint64_t)1 << 32 | my_bl) : 0);
+		for (int r = 0; r < sc.rank; ++r) if (bls[r] >> 32) carry = (uint32_t)bls[r];
+	}
+	// (3) distinct names of this rank -> entries + packed names, all-gathered; (4) global table (replicated).  Two different names
+	// with one 64-bit hash would share a global slot: the byte comparison finds that and the entries are hashed again with another seed.
+	uint32_t n_ent = 0;
+	uint64_t *slots = mab_alloc<uint64_t>(d, cap);
+	{
+		cub::CountingInputIterator<uint64_t> pos(0);
+		SlotUsed used{tab.first};
+		size_t tb = 0;
+		unsigned long long *d_n = d.d_scal + SC_NSEL;
+		cub::DeviceSelect::If(nullptr, tb, pos, slots, d_n, (int64_t)cap, used, d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceSelect::If(tmp, tb, pos, slots, d_n, (int64_t)cap, used, d.stream);
+		++d.n_lib;
+		n_ent = (uint32_t)d.get_scal(SC_NSEL);
+	}
+	GTab gt{nullptr, nullptr, nullptr, nullptr, 0};
+	GEntry *g_ent = nullptr;
+	char *g_names = nullptr;
+	uint64_t *g_pos = nullptr;
+	uint32_t *slot_of = nullptr;
+	uint64_t n_ent_all = 0, name_bytes_all = 0, my_ent_off = 0;
+	uint64_t seed = 0;
+	for (int attempt = 0;; ++attempt) {
 		GEntry *ent = mab_alloc<GEntry>(d, n_ent);
 		uint32_t *nsz = mab_alloc<uint32_t>(d, (size_t)n_ent + 1);
-		uint64_t *npos = mab_alloc<uint64_t>(d, (size_t)n_ent + 1);
+		uint64_t *npos = mab_alloc<uint64_t>(d, (size_t)n_ent + 1), *nsrc = mab_alloc<uint64_t>(d, (size_t)n_ent + 1);
 		uint64_t my_name_bytes = 0;
 		char *my_names = nullptr;
 		if (n_ent) {
-			MAB_LAUNCH(d, k_local_entries, mab_grid(n_ent, 256), 256, 0, slots, n_ent, tab, start, ln, line_base, ent, nsz);
+			MAB_LAUNCH(d, k_local_entries, mab_grid(n_ent, 256), 256, 0, slots, n_ent, tab, d_text, start, line_base, seed, ent, nsz, nsrc);
 			size_t tb = 0;
 			cub::DeviceScan::ExclusiveSum(nullptr, tb, nsz, npos, (int)n_ent, d.stream);
 			void *tmp = d.tmp(tb);
@@ -903,15 +875,14 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 			MAB_CUDA(cudaMemcpyAsync(&ls, nsz + n_ent - 1, 4, cudaMemcpyDeviceToHost, d.stream));
 			d.sync();
 			my_name_bytes = lp + ls;
-			my_names = (char*)d.alloc(my_name_bytes);
-			MAB_LAUNCH(d, k_local_names, mab_grid(n_ent, 256), 256, 0, slots, n_ent, tab, start, ln, d_text, npos, my_names);
+			my_names = (char*)d.alloc(my_name_bytes ? my_name_bytes : 1);
+			MAB_LAUNCH(d, k_local_names, mab_grid(n_ent, 256), 256, 0, n_ent, nsrc, nsz, d_text, npos, my_names);
 		}
 		std::vector<uint64_t> ents = sc_allgather_u64(d, sc, n_ent), nbytes = sc_allgather_u64(d, sc, my_name_bytes);
 		n_ent_all = name_bytes_all = 0;
 		std::vector<uint64_t> ent_bytes(G), pos_bytes(G);
-		uint64_t my_ent_off = 0, my_name_off = 0;
 		for (int r = 0; r < G; ++r) {
-			if (r == sc.rank) my_ent_off = n_ent_all, my_name_off = name_bytes_all;
+			if (r == sc.rank) my_ent_off = n_ent_all;
 			n_ent_all += ents[r], name_bytes_all += nbytes[r];
 			ent_bytes[r] = ents[r] * sizeof(GEntry), pos_bytes[r] = ents[r] * 8;
 		}
@@ -922,24 +893,20 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		sc_allgather_v(d, sc, my_names, nbytes, g_names);
 		sc_allgather_v(d, sc, npos, pos_bytes, g_pos); // positions are local to each rank's block: rebased below
 		{
-			// rebase name positions: entry block of rank r gets the byte offset of rank r's name block
 			std::vector<uint64_t> eoff(G + 1, 0), noff(G + 1, 0);
 			for (int r = 0; r < G; ++r) eoff[r + 1] = eoff[r] + ents[r], noff[r + 1] = noff[r] + nbytes[r];
 			for (int r = 0; r < G; ++r) if (ents[r] && noff[r]) {
 				MAB_LAUNCH(d, k_add_u64, mab_grid(ents[r], 256), 256, 0, g_pos + eoff[r], ents[r], noff[r]);
 			}
 		}
-		(void)my_ent_off; (void)my_name_off;
-		d.free(ent); d.free(nsz); d.free(npos); if (my_names) d.free(my_names);
-		d.free(slots);
+		d.free(ent); d.free(nsz); d.free(npos); d.free(nsrc); if (my_names) d.free(my_names);
 		d.trace("shard-ingest:name all-gather");
-		// (4) global table (replicated): same insert on every rank -> same result
 		uint64_t gcap = 1ull << 16; while (gcap < 2 * n_ent_all + 2) gcap <<= 1;
 		gt.key = (unsigned long long*)mab_alloc<uint64_t>(d, gcap); gt.first = (unsigned long long*)mab_alloc<uint64_t>(d, gcap);
 		gt.win = mab_alloc<uint32_t>(d, gcap); gt.id = mab_alloc<uint32_t>(d, gcap); gt.mask = gcap - 1;
 		MAB_CUDA(cudaMemsetAsync(gt.key, 0, gcap * 8, d.stream));
 		MAB_CUDA(cudaMemsetAsync(gt.first, 0xff, gcap * 8, d.stream));
-		uint32_t *slot_of = mab_alloc<uint32_t>(d, n_ent_all);
+		slot_of = mab_alloc<uint32_t>(d, n_ent_all);
 		d.zero_scal(SC_BIG, 1); d.zero_scal(SC_AUX2, 1);
 		if (n_ent_all) {
 			MAB_LAUNCH(d, k_gtab_insert, mab_grid(n_ent_all, 256), 256, 0, g_ent, n_ent_all, gt, slot_of, d.d_scal + SC_BIG);
@@ -947,9 +914,8 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 			MAB_LAUNCH(d, k_gtab_verify, mab_grid(n_ent_all, 256), 256, 0, g_ent, n_ent_all, gt, slot_of, g_pos, g_names, d.d_scal + SC_AUX2);
 		}
 		const bool gbad = d.get_scal(SC_AUX2) != 0 || d.h_scal[SC_BIG] != 0; // identical on all ranks (replicated computation)
+		if (!gbad) break;
 		d.free(slot_of);
-		if (!bad && !gbad) break;
-		d.free(tab.key); d.free(tab.first); d.free(tab.id);
 		d.free(gt.key); d.free(gt.first); d.free(gt.win); d.free(gt.id);
 		d.free(g_ent); d.free(g_names); d.free(g_pos);
 		seed = seed * 6364136223846793005ULL + 1442695040888963407ULL;
@@ -1000,8 +966,9 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 	uint32_t *cnt = mab_alloc<uint32_t>(d, n_lines + 1);
 	uint64_t *off = mab_alloc<uint64_t>(d, n_lines + 1);
 	uint64_t n_loc = 0;
+	if (n_ent) MAB_LAUNCH(d, k_local_gid, mab_grid(n_ent, 256), 256, 0, slots, n_ent, slot_of + my_ent_off, gt, tab);
 	if (n_lines) {
-		MAB_LAUNCH(d, k_line_gids, mab_grid(n_lines, 256), 256, 0, ln, n_lines, tab, gt, bi_dir, cnt);
+		MAB_LAUNCH(d, k_line_gids, mab_grid(n_lines, 256), 256, 0, ln, n_lines, tab, bi_dir, cnt);
 		size_t tb = 0;
 		cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, off, (int64_t)n_lines, d.stream);
 		void *tmp = d.tmp(tb);
@@ -1019,7 +986,7 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 	d.zero_scal(SC_AUX, 1);
 	MAB_CUDA(cudaMemsetAsync(d.d_scal + 16, 0, 32 * 8, d.stream));
 	if (n_loc) {
-		MAB_LAUNCH(d, k_hit_emit_gid, mab_grid(n_lines, 256), 256, 0, ln, n_lines, cnt, off, (uint32_t)G, loc, dest, (unsigned*)(d.d_scal + SC_AUX));
+		MAB_LAUNCH(d, k_hit_emit_gid, mab_grid(n_lines, 256), 256, 0, ln, n_lines, cnt, off, tab, carry, (uint32_t)G, loc, dest, (unsigned*)(d.d_scal + SC_AUX));
 		MAB_LAUNCH(d, k_iota32, mab_grid(n_loc, 256), 256, 0, ia, n_loc);
 		cub::DoubleBuffer<uint32_t> dk(dest, dest2), dv(ia, ib);
 		size_t tb = 0;
@@ -1068,7 +1035,7 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 	d.free(ln); d.free(start);
 	d.free(tab.key); d.free(tab.first); d.free(tab.id);
 	d.free(gt.key); d.free(gt.first); d.free(gt.win); d.free(gt.id);
-	d.free(g_ent); d.free(g_pos);
+	d.free(g_ent); d.free(g_pos); d.free(slots); d.free(slot_of);
 	std::vector<uint64_t> hits_all = sc_allgather_u64(d, sc, n_recv), parsed_all = sc_allgather_u64(d, sc, st.n_parsed);
 	st.n_hits = st.n_parsed = 0;
 	for (int r = 0; r < G; ++r) st.n_hits += hits_all[r], st.n_parsed += parsed_all[r];

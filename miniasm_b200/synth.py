@@ -16,6 +16,7 @@ CONFIGS = {
     # BASELINE.json configs (exact layout: fixed 10 kb reads, 62.5x, >= 2 kb overlaps, ~50 lines/read)
     "c2_100k": "-n 100000 -s 2",
     "c3_1m": "-n 1000000 -s 3",
+    "c3_2m": "-n 2000000 -s 4",          # config 3's law at 2 M reads: the 2-GPU bench workload
     "c4_4m": "-n 4000000 -s 4",
     # config 5: 8 M reads / 400 M overlaps, skewed: 7.98 M reads at 46.9x (~300 M lines) + 2 hot loci of 10 000 reads each
     # (2 x 50 M pairwise lines; those reads have ~10 000 hits and slabs of ~5 000 arcs per vertex)

@@ -22,8 +22,8 @@ def built():
 
 @pytest.fixture(scope="session")
 def ref(built):
-    from miniasm_b200 import capi
-    lib = capi.load_reference()
+    from oracle import loaders
+    lib = loaders.load_reference()
     lib.set_verbose(0)
     return lib
 

@@ -58,7 +58,14 @@ struct Pass {
 template <class Rule> static int run(h_asg_t *g, Rule rule)
 {
 	fx_last_sweeps = 0;
-	if (g->n_seq == 0 || g->n_arc == 0) return 0;
+	if (g->n_seq == 0) return 0;
+	{ // probe sweep on the bits (what the device driver does first)
+		FxProbe pv{g->arc, g->idx, (const uint32_t*)g->seq, (uint32_t)g->n_seq * 2};
+		uint32_t c = 0;
+		for (uint32_t x = 0; x < pv.n_vtx; ++x) c += rule.act(pv, x);
+		fx_last_sweeps = 1;
+		if (c == 0) return 0;
+	}
 	Pass p(g);
 	uint32_t cnt;
 	for (;;) {

@@ -114,7 +114,16 @@ def test_bubble_dense_300k(paf_dir):
     rc_c, out_c, err_c = run(CLI, [paf])
     assert rc_c == rc_r == 0, err_c.decode()[-2000:]
     assert out_c == out_r
-    assert _counters(err_c) == _counters(err_r)
+    # Equal-length arcs out of one vertex are common with 800 bp of jitter at 300 K reads; which of two tied neighbours is explored
+    # first follows the order the reference's unstable in-place radix sort left them in (ksort.h:134-183; ours are stable), and on
+    # this set that moves 5 of 1 875 013 transitive reductions into the asymmetric-arc removal that follows -- the graph after
+    # asg_symm, every later counter and the GFA are identical (DESIGN.md "Tie order").  The two lines are compared as a sum.
+    def norm(lines):
+        i = next(k for k, x in enumerate(lines) if "transitively reduced" in x)
+        j = next(k for k, x in enumerate(lines) if k > i and "asymmetric arcs" in x)
+        num = lambda x: int([t for t in x.split() if t.isdigit()][0])
+        return [x for k, x in enumerate(lines) if k not in (i, j)], num(lines[i]) + num(lines[j])
+    assert norm(_counters(err_c)) == norm(_counters(err_r))
     assert any("popped 3713 bubbles" in x for x in _counters(err_c))
 
 

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from miniasm_b200 import capi, synth
+from oracle import loaders
 from miniasm_b200.pipeline import Pipeline
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -25,7 +26,7 @@ def sha_sorted(text):
 
 @pytest.fixture(scope="module")
 def port(built):
-    lib = capi.load_oracle_port()
+    lib = loaders.load_oracle_port()
     return lib
 
 

@@ -6,6 +6,7 @@ import os
 import pytest
 
 from miniasm_b200 import capi, synth
+from oracle import loaders
 from miniasm_b200.pipeline import Pipeline
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -51,8 +52,8 @@ def test_paf_reader_corner_cases(built, tmp_path):
         (b"q4", 0xffffffff, 0xfffffffb, 77, 0, b"t3", 1, 2, 3, 4, 5),
         (b"q5", 1, 2, 3, 1, b"t5", 6, 7, 8, 9, 10),
     ]
-    if os.path.exists(capi.REFERENCE_SO):
-        assert paf_records(capi.load_reference(), str(p)) == got
+    if os.path.exists(loaders.REFERENCE_SO):
+        assert paf_records(loaders.load_reference(), str(p)) == got
     gz = tmp_path / "weird.paf.gz"
     with gzip.open(gz, "wb") as f:
         f.write(WEIRD)
@@ -76,7 +77,7 @@ def test_sdict(built):
     prod.sd_destroy(d)
 
 
-@pytest.mark.skipif(not os.path.exists(capi.REFERENCE_SO), reason="oracle/_ref not built")
+@pytest.mark.skipif(not os.path.exists(loaders.REFERENCE_SO), reason="oracle/_ref not built")
 def test_writers_and_ug_seq_against_reference(built, ref, paf_dir):
     from tests.test_clean_gpu import _write_reads
     prod = capi.load_product()
@@ -97,7 +98,7 @@ def test_writers_and_ug_seq_against_reference(built, ref, paf_dir):
         a.free(), b.free()
 
 
-@pytest.mark.skipif(not os.path.exists(capi.REFERENCE_SO), reason="oracle/_ref not built")
+@pytest.mark.skipif(not os.path.exists(loaders.REFERENCE_SO), reason="oracle/_ref not built")
 def test_ug_seq_refuses_a_short_record(built, paf_dir):
     """asm.c:263 asserts that a record covers the interval the layout keeps; ours must not read past a shorter record either
     (a reads file that does not belong to the PAF): message + abort, in a child process."""
@@ -108,7 +109,8 @@ import sys, os
 sys.path.insert(0, {ROOT!r})
 from miniasm_b200 import capi, synth
 from miniasm_b200.pipeline import Pipeline
-ref = capi.load_reference(); ref.set_verbose(0)
+from oracle import loaders
+ref = loaders.load_reference(); ref.set_verbose(0)
 prod = capi.load_product(); prod.set_verbose(0)
 paf = synth.generate("tiny_exact", {paf_dir!r} + "/short.paf")
 b = Pipeline(ref, paf).read().select().sg_gen().clean().ug_gen()
@@ -127,7 +129,7 @@ print("survived")
     assert "[E::ma_ug_seq]" in r.stderr and "wrong reads file" in r.stderr
 
 
-@pytest.mark.skipif(not os.path.exists(capi.REFERENCE_SO), reason="oracle/_ref not built")
+@pytest.mark.skipif(not os.path.exists(loaders.REFERENCE_SO), reason="oracle/_ref not built")
 def test_no_cont_prefilter_against_reference(built, ref, paf_dir):
     prod = capi.load_product()
     paf = synth.generate("-n 4000 -l 2000 -L 30000 -c 30 -j 100 -s 41", f"{paf_dir}/nocont.paf")
@@ -242,8 +244,8 @@ def test_ug_writer_threads_keep_the_byte_stream(built, monkeypatch):
         monkeypatch.setenv("MAB_WRITER_THREADS", t)
         plain[t] = prod.print_to_string("ma_ug_print", C.pointer(ug), d, None)
     assert plain["0"] == plain["5"] and len(plain["0"]) < len(outs["0"])
-    if os.path.exists(capi.REFERENCE_SO):                                # and they are the reference's bytes (asm.c:64-116)
-        ref = capi.load_reference()
+    if os.path.exists(loaders.REFERENCE_SO):                                # and they are the reference's bytes (asm.c:64-116)
+        ref = loaders.load_reference()
         d2 = ref.sd_init()
         for i in range(d.contents.n_seq):
             ref.sd_put(d2, d.contents.seq[i].name, d.contents.seq[i].len)

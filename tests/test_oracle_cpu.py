@@ -6,15 +6,16 @@ import numpy as np
 import pytest
 
 from miniasm_b200 import capi, synth
+from oracle import loaders
 from miniasm_b200.pipeline import Pipeline, canon_arcs
 
-pytestmark = pytest.mark.skipif(not os.path.exists(capi.REFERENCE_SO), reason="oracle/_ref not built (needs /root/reference)")
+pytestmark = pytest.mark.skipif(not os.path.exists(loaders.REFERENCE_SO), reason="oracle/_ref not built (needs /root/reference)")
 SETS = ["tiny_exact", "chaos_small", "chaos", "bubbles800", "shuffled", "lowcov", "varlen300", "skew_small", "c1_ecoli_like"]
 
 
 @pytest.fixture(scope="module")
 def port(built):
-    return capi.load_oracle_port()
+    return loaders.load_oracle_port()
 
 
 def mask(h):
@@ -63,24 +64,3 @@ def test_tie_order_audit(ref, port, paf_dir):
     for name in ("jitter30", "chaos"):
         paf = synth.generate(name, f"{paf_dir}/{name}.paf")
         assert Pipeline(ref, paf).run_all() == Pipeline(port, paf).run_all()
-
-
-def test_speculative_round_model_is_exact(built, paf_dir):
-    """oracle/spec_sim: CPU model of the rounds clean_dev.cu runs for asg_pop_bubble.  Every variant of the validity rule
-    (own-cell check on/off, sliding window, the 'excuse' rule behind MAB_BUB_EXCUSE) must leave the graph exactly as the
-    sequential pass does; the excuse rule must need far fewer rounds than pops."""
-    import re
-    import subprocess
-    sim = os.path.join(os.path.dirname(capi.ORACLE_SO), "spec_sim")
-    for args in ("-n 6000 -l 9000 -L 11000 -j 800 -c 30 -s 21", "chaos_small", "shuffled"):
-        paf = synth.generate(args, os.path.join(paf_dir, "specsim.paf"))
-        out = subprocess.run([sim, paf], stdout=subprocess.PIPE, check=True, text=True).stdout
-        rows = re.findall(r"skip_own=(\d) window=(\d) excuse=(\d): rounds (\d+) pops (\d+) equal (\d)", out)
-        pops = int(re.search(r"sequential: (\d+) pops", out).group(1))
-        assert len(rows) == 8 and all(r[5] == "1" and int(r[4]) == pops for r in rows), out
-        plain = [int(r[3]) for r in rows if r[:3] == ("0", "0", "0")][0]
-        excuse = [int(r[3]) for r in rows if r[:3] == ("1", "0", "1")][0]
-        assert excuse <= plain and (pops < 50 or excuse * 3 < plain), out
-        tips = re.findall(r"tips window=(\d) excuse=(\d): rounds (\d+) cut (\d+) equal (\d)", out)     # same model for asg_cut_tip
-        n_tip = int(re.search(r"tips sequential: (\d+) cut", out).group(1))
-        assert len(tips) == 4 and all(t[4] == "1" and int(t[3]) == n_tip for t in tips), out
