@@ -12,8 +12,9 @@ file order (rank r generates and holds part r), read ids are hash-sharded (owner
 
 * value  : whole-job PAF records/s with the PAF bytes already resident in HBM (timed on the device, CUDA
            events on the library's stream, max over ranks).
-* e2e    : the same through the C ABI with HOST buffers: pinned PAF text -> H2D -> all steps -> GFA text (formatted on
-           the GPU, one D2H, written to /dev/null by rank 0); wall clock bracketed by device synchronisation.
+* e2e    : the same through the C ABI with HOST buffers: pinned PAF text -> H2D (in chunks; at N=1 the chunks that have arrived
+           are parsed while the next ones cross PCIe, mab_load_ingest_text) -> all steps -> GFA text (formatted on the GPU, one
+           D2H, written to /dev/null by rank 0); wall clock bracketed by device synchronisation.
 * roofline : asg_arc_del_trans kernel, algorithmic bytes / CUDA-event time vs the measured HBM copy peak;
   roofline_phases: the other phases against SURVEY.md 8(d)'s byte counts.
 * check  : sha256 of the GFA text of the last step (compared with tests/golden/configs.json when the workload has a
@@ -312,8 +313,14 @@ def main():
         free()
 
         def e2e_step():
-            lib.mab_load_paf_text(ctx, pinned.data_ptr(), n_bytes)            # H2D
-            device_steps()
+            if world > 1:
+                lib.mab_load_paf_text(ctx, pinned.data_ptr(), n_bytes)        # H2D
+                device_steps()
+            else:                                                              # H2D in chunks, parsed while the next ones arrive
+                lib.mab_load_ingest_text(ctx, pinned.data_ptr(), n_bytes, opt.min_span, opt.min_match, 1)
+                lib.mab_select(ctx, C.byref(opt), 0, 0, 100)
+                lib.mab_layout(ctx, C.byref(opt), 100)
+                lib.mab_unitigs(ctx)
             if rank != 0:                                                      # the result is replicated; rank 0 writes it
                 return 0
             if not a.host_gfa:                                                 # GFA text formatted on the GPU, one D2H of the text

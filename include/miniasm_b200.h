@@ -163,6 +163,8 @@ const mab_stats_t *mab_stats(const mab_ctx_t *ctx);
 int mab_load_paf_text(mab_ctx_t *ctx, const char *text, size_t len);
 int mab_load_paf_file(mab_ctx_t *ctx, const char *fn);  /* -1 if the file cannot be opened */
 int mab_ingest(mab_ctx_t *ctx, int min_span, int min_match, int bi_dir);
+/* load + ingest overlapped: chunks of the host text are parsed while the next ones cross PCIe (same result as the two calls) */
+int mab_load_ingest_text(mab_ctx_t *ctx, const char *text, size_t len, int min_span, int min_match, int bi_dir);
 /* -R: ma_hit_no_cont (hit.c:38-68) + ma_hit_read with its exclusion list (hit.c:86) as one pass over the resident text */
 int mab_ingest_nocont(mab_ctx_t *ctx, int min_span, int min_match, int bi_dir, int max_hang, float int_frac);
 /* alternative to load+ingest: hits and dictionary produced by the drop-in ma_hit_read (host arrays) */

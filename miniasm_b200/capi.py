@@ -139,6 +139,7 @@ _PRODUCT_ONLY = {
     "mab_load_paf_text": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mab_load_paf_file": (C.c_int, [C.c_void_p, C.c_char_p]),
     "mab_ingest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mab_load_ingest_text": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]),
     "mab_ingest_nocont": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "mab_load_hits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Sdict)]),
     "mab_select": (C.c_int, [C.c_void_p, C.POINTER(MaOpt), C.c_int, C.c_int, C.c_int]),

@@ -42,7 +42,6 @@ struct mab_ctx {
 	// sharded runs (mab_shard_init): communicator + the packed names of all ranks (names.off indexes it instead of d_text)
 	ShardComm sc;
 	char *name_text = nullptr;
-	std::map<std::string, void*> ipc_open;   // peer segments mapped through CUDA IPC (handle bytes -> local address)
 	char *h_gfa = nullptr;    // pinned landing buffer of mab_write_gfa (grow-only)
 	size_t h_gfa_cap = 0;
 	// -f reads: the file streams into HBM on its own thread and stream while the graph stages run (mab_reads_prefetch)
@@ -139,7 +138,7 @@ void mab_destroy(mab_ctx_t *c)
 	d.free(c->d_text);
 	d.sync();
 	for (int i = 0; i < 2; ++i) if (c->pin[i]) MAB_CUDA(cudaFreeHost(c->pin[i]));
-	for (auto &kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
+	for (auto &kv : c->sc.ipc_open) cudaIpcCloseMemHandle(kv.second);
 	if (c->h_gfa) MAB_CUDA(cudaFreeHost(c->h_gfa));
 	reads_drop(c);
 	d.destroy();
@@ -230,6 +229,26 @@ int mab_ingest(mab_ctx_t *c, int min_span, int min_match, int bi_dir)
 	PhaseTimer pt(d, &c->stats.ms_ingest, "mab_ingest");
 	ctx_reset_reads(c);
 	ingest_paf(d, c->d_text, c->text_len, min_span, min_match, bi_dir, c->hits, c->names, c->ist);
+	c->n_seq = c->names.n_seq;
+	c->stats.n_lines = c->ist.n_parsed, c->stats.n_hits_stored = c->ist.n_hits, c->stats.n_seq_in = c->ist.n_seq;
+	if (!mab_mute && ma_verbose >= 3)
+		fprintf(stderr, "[M::%s::%s] read %ld hits; stored %ld hits and %d sequences (%ld bp)\n", "ma_hit_read", sys_timestamp(),
+				(long)c->ist.n_parsed, (long)c->ist.n_hits, (int)c->ist.n_seq, (long)c->ist.tot_len);
+	return 0;
+}
+
+/* mab_load_paf_text + mab_ingest in one call, overlapped: chunk k of the text is scanned for line starts and parsed (store filter,
+ * dictionary) while chunk k+1 crosses PCIe on a second stream; when the last byte lands only the id ranking, the hit emission and the
+ * sort are left.  `text` may be pageable or pinned (pinned overlaps fully). */
+int mab_load_ingest_text(mab_ctx_t *c, const char *text, size_t len, int min_span, int min_match, int bi_dir)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	ctx_reset_reads(c);
+	text_reserve(c, len);
+	c->text_len = len;
+	PhaseTimer pt(d, &c->stats.ms_ingest, "mab_load_ingest_text");
+	ingest_paf_stream(d, c->d_text, text, len, min_span, min_match, bi_dir, c->hits, c->names, c->ist);
 	c->n_seq = c->names.n_seq;
 	c->stats.n_lines = c->ist.n_parsed, c->stats.n_hits_stored = c->ist.n_hits, c->stats.n_seq_in = c->ist.n_seq;
 	if (!mab_mute && ma_verbose >= 3)
@@ -795,55 +814,11 @@ int mab_layout_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	if (tot >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 arcs in the graph\n"); exit(73); }
 	c->stats.n_arc_sg = tot;
 	if (MAB_V(1)) fprintf(stderr, "[M::%s] read %d arcs\n", "ma_sg_gen", (int)tot);
-	// ---- neighbour slabs: peer access over NVLink (CUDA IPC) when every rank can offer it, else an all-gather of all arcs
-	// (ranks that are threads of ONE process -- the CLI's MINIASM_B200_GPUS mode -- share an address space: there the raw
-	// pointer is used after cudaDeviceEnablePeerAccess; an IPC handle cannot be opened by the process that exported it)
-	struct PeerInfo { cudaIpcMemHandle_t h; uint64_t off, ok, pid, ptr, dev; };
-	PeerInfo mine;
-	memset(&mine, 0, sizeof(mine));
-	{
-		char *base; size_t off;
-		const char *env = getenv("MAB_SHARD_P2P");
-		mine.pid = (uint64_t)getpid(), mine.ptr = (uint64_t)(uintptr_t)loc.arc, mine.dev = (uint64_t)d.device;
-		if (!(env && atoi(env) == 0) && d.arena.segment_of(loc.arc, &base, &off) && cudaIpcGetMemHandle(&mine.h, base) == cudaSuccess) mine.off = off, mine.ok = 1;
-		else cudaGetLastError();
-	}
-	std::vector<PeerInfo> peers((size_t)G);
-	{
-		PeerInfo *buf = (PeerInfo*)d.alloc(sizeof(PeerInfo) * ((size_t)G + 1));
-		MAB_CUDA(cudaMemcpyAsync(buf + G, &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice, d.stream));
-		if (sc.active()) MAB_NCCL(ncclAllGather(buf + G, buf, sizeof(PeerInfo), ncclUint8, sc.comm, d.stream));
-		else MAB_CUDA(cudaMemcpyAsync(buf, buf + G, sizeof(PeerInfo), cudaMemcpyDeviceToDevice, d.stream));
-		MAB_CUDA(cudaMemcpyAsync(peers.data(), buf, sizeof(PeerInfo) * (size_t)G, cudaMemcpyDeviceToHost, d.stream));
-		d.sync();
-		d.free(buf);
-	}
-	bool p2p = true;
+	// ---- neighbour slabs: peer access over NVLink when every rank can offer it (shard_comm.cuh), else an all-gather of all arcs
+	std::vector<void*> peer_any;
+	const bool p2p = sc_peer_ptrs(d, sc, loc.arc, peer_any);
 	std::vector<const DArc*> peer_ptr((size_t)G, nullptr);
-	for (int r = 0; r < G && p2p; ++r) {
-		if (!peers[r].ok) { p2p = false; break; }
-		if (r == sc.rank) { peer_ptr[r] = loc.arc; continue; }
-		if (peers[r].pid == mine.pid) { // same process: direct peer access
-			int can = 0;
-			if (cudaDeviceCanAccessPeer(&can, d.device, (int)peers[r].dev) != cudaSuccess || !can) { cudaGetLastError(); p2p = false; break; }
-			cudaError_t e = cudaDeviceEnablePeerAccess((int)peers[r].dev, 0);
-			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); p2p = false; break; }
-			cudaGetLastError();
-			peer_ptr[r] = (const DArc*)(uintptr_t)peers[r].ptr;
-			continue;
-		}
-		std::string key((const char*)&peers[r].h, sizeof(cudaIpcMemHandle_t));
-		auto it = c->ipc_open.find(key);
-		void *base = nullptr;
-		if (it != c->ipc_open.end()) base = it->second;
-		else if (cudaIpcOpenMemHandle(&base, peers[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) c->ipc_open[key] = base;
-		else { cudaGetLastError(); p2p = false; break; }
-		peer_ptr[r] = (const DArc*)((const char*)base + peers[r].off);
-	}
-	{ // all ranks take the same route
-		std::vector<uint64_t> okv = sc_allgather_u64(d, sc, p2p ? 1 : 0);
-		for (int r = 0; r < G; ++r) p2p = p2p && okv[r] != 0;
-	}
+	for (int r = 0; r < G; ++r) peer_ptr[r] = (const DArc*)peer_any[r];
 	if (p2p) {
 		dg_arc_index(d, loc);                                   // slabs of the vertices this rank owns
 		uint64_t *nidx = mab_alloc<uint64_t>(d, (size_t)n * 2);

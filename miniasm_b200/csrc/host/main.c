@@ -144,6 +144,7 @@ static mab_ctx_t *run_sharded(const char *fn, const ma_opt_t *opt, int bi_dir, i
 		cut[r] = q ? (size_t)(q - text) + 1 : len;
 	}
 	cut[world] = len;
+	setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);      /* stdout carries the GFA: NCCL's version banner / debug lines go to stderr */
 	mab_nccl_unique_id(id);
 	for (r = 0; r < world; ++r) {
 		job[r].rank = r, job[r].world = world, job[r].device = device0 + r, job[r].bi_dir = bi_dir, job[r].opt = opt;

@@ -96,6 +96,58 @@ __global__ void __launch_bounds__(NL_THREADS) k_nl_write(const char *__restrict_
 	}
 }
 
+// Streaming variants (ingest_paf_stream): tiles [t0, t1) of the text have just arrived.  nl_state[0] = newline-started lines
+// seen so far (line 0 starts at byte 0 and is not counted), nl_state[1] = capacity of `out`.
+__global__ void __launch_bounds__(NL_THREADS) k_nl_count_range(const char *__restrict__ text, size_t len, uint64_t t0, uint64_t t1, uint64_t *cnt)
+{
+	typedef cub::BlockReduce<uint32_t, NL_THREADS> BR;
+	__shared__ typename BR::TempStorage ts;
+	for (uint64_t t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
+		uint32_t c = 0;
+		#pragma unroll
+		for (int k = 0; k < NL_PER_THREAD; ++k) c += __popc(nl_bits16(text, len, t * NL_TILE + ((uint64_t)k * NL_THREADS + threadIdx.x) * 16));
+		c = BR(ts).Sum(c);
+		if (threadIdx.x == 0) cnt[t - t0] = c;
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(NL_THREADS) k_nl_write_range(const char *__restrict__ text, size_t len, uint64_t t0, uint64_t t1, const uint64_t *__restrict__ base,
+                                                              const unsigned long long *nl_state, uint64_t *out)
+{
+	typedef cub::BlockScan<uint32_t, NL_THREADS> BS;
+	__shared__ typename BS::TempStorage ts;
+	const uint64_t seen = nl_state[0], cap = nl_state[1];
+	for (uint64_t t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
+		uint64_t at = seen + base[t - t0];
+		#pragma unroll
+		for (int k = 0; k < NL_PER_THREAD; ++k) {
+			const uint64_t off = t * NL_TILE + ((uint64_t)k * NL_THREADS + threadIdx.x) * 16;
+			uint32_t bits = nl_bits16(text, len, off), rank, total;
+			BS(ts).ExclusiveSum((uint32_t)__popc(bits), rank, total);
+			uint64_t q = at + rank;
+			while (bits) { const int b = __ffs(bits) - 1; if (q + 1 < cap) out[q + 1] = off + b + 1; ++q; bits &= bits - 1; }
+			at += total;
+			__syncthreads();
+		}
+	}
+}
+
+// after the tiles [t0, t1): lines whose END is known now are [rng[0], rng[1]); rng[2] = total number of lines once the text is complete
+__global__ void k_nl_advance(unsigned long long *nl_state, const uint64_t *base, const uint64_t *cnt, uint64_t n_tiles, unsigned long long *rng, int last)
+{
+	if (blockIdx.x || threadIdx.x) return;
+	const unsigned long long seen = nl_state[0] + (n_tiles ? base[n_tiles - 1] + cnt[n_tiles - 1] : 0);
+	nl_state[0] = seen;
+	const unsigned long long known_starts = seen + 1;                 // lines 0 .. seen have a start
+	unsigned long long cap = nl_state[1];
+	unsigned long long hi = last ? known_starts : known_starts - 1;   // the last known line's end is the next line's start, or the end of the text
+	if (hi > cap - 1) hi = cap - 1;                                   // (overflow of the estimate: start[] is only filled below cap; the host notices and falls back)
+	rng[0] = rng[1] > hi ? hi : rng[1];                               // previous upper bound becomes the lower one
+	rng[1] = hi;
+	rng[2] = last ? known_starts : ~0ull;
+}
+
 struct IsLineStart {
 	const char *text;
 	__device__ __forceinline__ bool operator()(uint64_t p) const { return p == 0 || text[p - 1] == '\n'; }
@@ -255,15 +307,17 @@ constexpr int PARSE_LINES = 128;
 constexpr int PARSE_SMEM = 16 * 1024;
 
 __global__ void __launch_bounds__(PARSE_LINES)
-k_parse(const char *__restrict__ text, size_t len, const uint64_t *__restrict__ start, uint64_t n_lines,
+k_parse(const char *__restrict__ text, size_t len, const uint64_t *__restrict__ start, const unsigned long long *__restrict__ rng,
         int min_span, int min_match, NameTab tab, PRec *out, unsigned long long *counts)
-{	// counts: [0] lines with >= 10 fields, [1] lines stored, [2] dictionary overflow
+{	// rng: lines [rng[0], rng[1]) are parsed; rng[2] = number of lines of the whole text, or ~0 while it is still arriving (then
+	// line rng[1] exists and its start ends line rng[1]-1).  counts: [0] lines with >= 10 fields, [1] lines stored, [2] dictionary overflow
 	__shared__ __align__(16) char s_text[PARSE_SMEM];
 	__shared__ uint32_t s_vals[PARSE_LINES / 32][11][32];
 	unsigned n_parsed = 0, n_pass = 0;
-	const uint64_t n_blk = (n_lines + PARSE_LINES - 1) / PARSE_LINES;
+	const uint64_t line_lo = rng[0], line_hi = rng[1], n_lines = rng[2];
+	const uint64_t n_blk = (line_hi - line_lo + PARSE_LINES - 1) / PARSE_LINES;
 	for (uint64_t b = blockIdx.x; b < n_blk; b += gridDim.x) {
-		const uint64_t l0 = b * PARSE_LINES, l1 = l0 + PARSE_LINES < n_lines ? l0 + PARSE_LINES : n_lines;
+		const uint64_t l0 = line_lo + b * PARSE_LINES, l1 = l0 + PARSE_LINES < line_hi ? l0 + PARSE_LINES : line_hi;
 		const uint64_t s0 = start[l0], s1 = l1 < n_lines ? start[l1] : len;
 		const uint64_t a0 = s0 & ~(uint64_t)15;
 		const bool staged = s1 - a0 <= PARSE_SMEM;
@@ -460,6 +514,29 @@ void names_free(MabDev &d, DNames &n)
 
 static inline uint32_t bits_for(uint64_t x) { uint32_t b = 0; while (x) ++b, x >>= 1; return b ? b : 1; }
 
+constexpr int SC_RNG = 40;   // d_scal[40..42]: the line range k_parse works on (lo, hi, total or ~0)
+
+static void set_rng(MabDev &d, uint64_t lo, uint64_t hi, uint64_t total)
+{
+	const unsigned long long v[3] = { lo, hi, total };
+	MAB_CUDA(cudaMemcpyAsync(d.d_scal + SC_RNG, v, sizeof(v), cudaMemcpyHostToDevice, d.stream));
+}
+
+static NameTab tab_alloc(MabDev &d, uint64_t cap)
+{
+	NameTab tab;
+	tab.key = (unsigned long long*)mab_alloc<uint64_t>(d, cap);
+	tab.first = (unsigned long long*)mab_alloc<uint64_t>(d, cap);
+	tab.id = mab_alloc<uint32_t>(d, cap);
+	tab.mask = cap - 1;
+	MAB_CUDA(cudaMemsetAsync(tab.key, 0, cap * 8, d.stream));
+	MAB_CUDA(cudaMemsetAsync(tab.first, 0xff, cap * 8, d.stream));
+	return tab;
+}
+
+static void ingest_finish(MabDev &d, const char *d_text, size_t len, uint64_t *start, PRec *ln, uint64_t n_lines, NameTab tab, uint64_t cap, int bi_dir,
+                          const NoContParams *nocont, DHits &h, DNames &names, IngestStats &st);
+
 void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min_match, int bi_dir, DHits &h, DNames &names, IngestStats &st,
                 const NoContParams *nocont)
 {
@@ -478,26 +555,96 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 	// (2) parse + store filter + dictionary insert in one pass; the table grows (and the pass repeats) until every name has a slot
 	if (len >= (1ull << NT_OFF_BITS) - 1) { fprintf(stderr, "[E::miniasm_b200] more than 2^37 bytes of PAF on one GPU\n"); exit(73); }
 	PRec *ln = mab_alloc<PRec>(d, n_lines);
-	uint32_t *cnt = nullptr;
-	uint64_t *off = nullptr;
 	NameTab tab{nullptr, nullptr, nullptr, 0};
 	uint64_t cap = 1ull << 20;
 	while (cap < n_lines / 4) cap <<= 1;                 // ~50 lines name a read twice each: load <= 1/6 at that ratio; overflow quadruples it
 	for (;;) {
-		tab.key = (unsigned long long*)mab_alloc<uint64_t>(d, cap);
-		tab.first = (unsigned long long*)mab_alloc<uint64_t>(d, cap);
-		tab.id = mab_alloc<uint32_t>(d, cap);
-		tab.mask = cap - 1;
-		MAB_CUDA(cudaMemsetAsync(tab.key, 0, cap * 8, d.stream));
-		MAB_CUDA(cudaMemsetAsync(tab.first, 0xff, cap * 8, d.stream));
+		tab = tab_alloc(d, cap);
 		d.zero_scal(SC_COUNT, 4);
-		MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, n_lines, min_span, min_match, tab, ln, d.d_scal + SC_COUNT);
+		set_rng(d, 0, n_lines, n_lines);
+		MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, d.d_scal + SC_RNG, min_span, min_match, tab, ln, d.d_scal + SC_COUNT);
 		st.n_parsed = d.get_scal(SC_COUNT);
 		if (d.h_scal[SC_COUNT + 2] == 0) break;
 		d.free(tab.key); d.free(tab.first); d.free(tab.id);
 		cap <<= 2;
 		if (cap > (1ull << 33)) { fprintf(stderr, "[E::miniasm_b200] read-name table overflow\n"); exit(77); }
 	}
+	ingest_finish(d, d_text, len, start, ln, n_lines, tab, cap, bi_dir, nocont, h, names, st);
+}
+
+// Load + ingest in one call: the text crosses PCIe in chunks on a copy stream while the chunks that have arrived are scanned for
+// line starts and parsed on the context's stream (k_parse needs nothing global any more), so of the ingest only the id ranking, the
+// hit emission and the sort are left when the last byte lands.  host_text may be pageable or pinned; d_text has room for len + 64.
+// Capacities are estimates (a 12-column line has >= 24 bytes); a text that breaks them is ingested again the plain way.
+void ingest_paf_stream(MabDev &d, char *d_text, const char *host_text, size_t len, int min_span, int min_match, int bi_dir,
+                       DHits &h, DNames &names, IngestStats &st)
+{
+	memset(&st, 0, sizeof(st));
+	names = DNames();
+	h.n = 0, h.n_seq = 0;
+	if (len == 0) { dh_reserve(d, h, 1); return; }
+	if (len >= (1ull << NT_OFF_BITS) - 1) { fprintf(stderr, "[E::miniasm_b200] more than 2^37 bytes of PAF on one GPU\n"); exit(73); }
+	const uint64_t CH_TILES = (64ull << 20) / NL_TILE, n_tile = (len + NL_TILE - 1) / NL_TILE;       // 64 MB chunks, whole tiles
+	const uint64_t n_chunk = (n_tile + CH_TILES - 1) / CH_TILES;
+	const uint64_t line_cap = len / 24 + 1024;
+	uint64_t cap = 1ull << 20;
+	while (cap < line_cap / 8) cap <<= 1;
+	uint64_t *start = mab_alloc<uint64_t>(d, line_cap + 1);
+	PRec *ln = mab_alloc<PRec>(d, line_cap);
+	uint64_t *cnt = mab_alloc<uint64_t>(d, CH_TILES + 1), *base = mab_alloc<uint64_t>(d, CH_TILES + 1);
+	unsigned long long *state = (unsigned long long*)mab_alloc<uint64_t>(d, 8);   // [0] newline-started lines seen, [1] capacity; [4..6] = rng
+	NameTab tab = tab_alloc(d, cap);
+	{
+		const unsigned long long init[8] = { 0, line_cap, 0, 0, 0, 0, ~0ull, 0 };
+		MAB_CUDA(cudaMemcpyAsync(state, init, sizeof(init), cudaMemcpyHostToDevice, d.stream));
+		MAB_CUDA(cudaMemsetAsync(start, 0, 8, d.stream));
+	}
+	d.zero_scal(SC_COUNT, 4);
+	size_t tb = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, base, (int64_t)CH_TILES, d.stream);
+	void *tmp = d.tmp(tb);
+	if (!d.copy_stream) MAB_CUDA(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+	std::vector<cudaEvent_t> ev(n_chunk);
+	cudaEvent_t ready;
+	MAB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+	MAB_CUDA(cudaEventRecord(ready, d.stream));                 // the copies may not overtake whatever still uses d_text on the main stream
+	MAB_CUDA(cudaStreamWaitEvent(d.copy_stream, ready, 0));
+	for (uint64_t k = 0; k < n_chunk; ++k) { // copy k is issued before the kernels of chunk k: a pageable source blocks the host per chunk, not for the whole text
+		const uint64_t t0 = k * CH_TILES, t1 = (k + 1) * CH_TILES < n_tile ? (k + 1) * CH_TILES : n_tile;
+		const uint64_t b0 = t0 * NL_TILE, b1 = t1 * NL_TILE < len ? t1 * NL_TILE : len;
+		MAB_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+		MAB_CUDA(cudaMemcpyAsync(d_text + b0, host_text + b0, b1 - b0, cudaMemcpyHostToDevice, d.copy_stream));
+		MAB_CUDA(cudaEventRecord(ev[k], d.copy_stream));
+		MAB_CUDA(cudaStreamWaitEvent(d.stream, ev[k], 0));
+		MAB_LAUNCH(d, k_nl_count_range, mab_grid(t1 - t0, 1, 148u * 8u), NL_THREADS, 0, d_text, len, t0, t1, cnt);
+		cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, base, (int64_t)(t1 - t0), d.stream);
+		++d.n_lib;
+		MAB_LAUNCH(d, k_nl_write_range, mab_grid(t1 - t0, 1, 148u * 8u), NL_THREADS, 0, d_text, len, t0, t1, base, state, start);
+		MAB_LAUNCH(d, k_nl_advance, 1, 32, 0, state, base, cnt, t1 - t0, state + 4, (int)(k + 1 == n_chunk));
+		MAB_LAUNCH(d, k_parse, 148u * 8u, PARSE_LINES, 0, d_text, len, start, state + 4, min_span, min_match, tab, ln, d.d_scal + SC_COUNT);
+	}
+	unsigned long long fin[8];
+	MAB_CUDA(cudaMemcpyAsync(fin, state, sizeof(fin), cudaMemcpyDeviceToHost, d.stream));
+	st.n_parsed = d.get_scal(SC_COUNT);                         // (synchronises)
+	for (uint64_t k = 0; k < n_chunk; ++k) MAB_CUDA(cudaEventDestroy(ev[k]));
+	MAB_CUDA(cudaEventDestroy(ready));
+	d.free(cnt); d.free(base); d.free(state);
+	const uint64_t n_lines = fin[0] + 1;
+	if (n_lines >= line_cap || d.h_scal[SC_COUNT + 2] != 0) {    // estimates broken (very short lines / more names than slots): the plain path sizes exactly
+		d.free(start); d.free(ln); d.free(tab.key); d.free(tab.first); d.free(tab.id);
+		ingest_paf(d, d_text, len, min_span, min_match, bi_dir, h, names, st, nullptr);
+		return;
+	}
+	st.n_lines = n_lines;
+	d.trace("ingest:stream (copy + line starts + parse + dictionary)");
+	ingest_finish(d, d_text, len, start, ln, n_lines, tab, cap, bi_dir, nullptr, h, names, st);
+}
+
+static void ingest_finish(MabDev &d, const char *d_text, size_t len, uint64_t *start, PRec *ln, uint64_t n_lines, NameTab tab, uint64_t cap, int bi_dir,
+                          const NoContParams *nocont, DHits &h, DNames &names, IngestStats &st)
+{
+	uint32_t *cnt = nullptr;
+	uint64_t *off = nullptr;
 	d.trace("ingest:dictionary");
 	if (nocont) { // -R: mark the contained reads, drop every line that names one, take the first appearances again
 		uint8_t *excl = mab_alloc<uint8_t>(d, cap);
@@ -637,6 +784,8 @@ __global__ void k_local_names(uint32_t n, const uint64_t *name_off, const uint32
 	}
 }
 
+struct U32ToU64i { __host__ __device__ __forceinline__ uint64_t operator()(uint32_t x) const { return x; } };
+
 struct GTab { unsigned long long *key, *first; uint32_t *win, *id; uint64_t mask; }; // global table: winner entry and read id per slot
 
 __global__ void k_gtab_insert(const GEntry *ent, uint64_t n, GTab t, uint32_t *slot_of, unsigned long long *overflow)
@@ -737,6 +886,89 @@ __global__ void k_hit_emit_gid(const PRec *ln, uint64_t n_lines, const uint32_t 
 	if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_qs, mx);
 }
 
+// ---- emit + exchange fused: every hit is written straight into the receive buffer of the rank that owns its query read ------
+// (over NVLink for remote owners).  Order inside a (source rank, destination) bucket must be file order, so positions come from a
+// two-level count: per 256-line block and destination (k_push_count -> exclusive scan, destination-major), and inside a block the
+// rank of a hit among the block's hits to the same destination (ballots per destination; a line's own hit precedes its mirror).
+constexpr int PUSH_LINES = 256;
+
+struct PushLine { bool has0, has1; uint32_t d0, d1, qid, tid; };
+
+__device__ __forceinline__ PushLine push_line(const PRec *ln, uint64_t i, uint64_t n_lines, const NameTab &lt, int bi_dir, uint32_t world)
+{
+	PushLine p{false, false, 0, 0, 0, 0};
+	if (i < n_lines) {
+		const uint2 sl = *reinterpret_cast<const uint2*>(&ln[i].slot_q);
+		if (sl.x != NOSLOT) {
+			p.qid = lt.id[sl.x], p.tid = lt.id[sl.y];
+			p.has0 = true, p.has1 = bi_dir && p.qid != p.tid;
+			p.d0 = p.qid % world, p.d1 = p.tid % world;
+		}
+	}
+	return p;
+}
+
+__global__ void __launch_bounds__(PUSH_LINES) k_push_count(const PRec *ln, uint64_t n_lines, NameTab lt, int bi_dir, uint32_t world, uint64_t n_blk, uint32_t *blk_cnt)
+{
+	__shared__ uint32_t s_cnt[32];
+	for (uint64_t b = blockIdx.x; b < n_blk; b += gridDim.x) {
+		if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
+		__syncthreads();
+		const PushLine p = push_line(ln, b * PUSH_LINES + threadIdx.x, n_lines, lt, bi_dir, world);
+		for (uint32_t g = 0; g < world; ++g) {
+			const unsigned b0 = __ballot_sync(0xffffffffu, p.has0 && p.d0 == g), b1 = __ballot_sync(0xffffffffu, p.has1 && p.d1 == g);
+			if ((threadIdx.x & 31) == 0 && (b0 | b1)) atomicAdd(&s_cnt[g], (uint32_t)(__popc(b0) + __popc(b1)));
+		}
+		__syncthreads();
+		if (threadIdx.x < world) blk_cnt[(uint64_t)threadIdx.x * n_blk + b] = s_cnt[threadIdx.x];
+		__syncthreads();
+	}
+}
+
+// dst[g] = receive buffer of rank g (peer address); pos_base[g] = (offset of this rank's bucket in it) - blk_off[g * n_blk]
+__global__ void __launch_bounds__(PUSH_LINES) k_push_emit(const PRec *ln, uint64_t n_lines, NameTab lt, int bi_dir, uint32_t carry_bl, uint32_t world, uint64_t n_blk,
+                                                          const uint64_t *__restrict__ blk_off, const long long *__restrict__ pos_base, DHit *const *__restrict__ dst, unsigned *max_qs)
+{
+	__shared__ uint32_t s_wc[PUSH_LINES / 32][32];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
+	unsigned mx = 0;
+	for (uint64_t b = blockIdx.x; b < n_blk; b += gridDim.x) {
+		const uint64_t i = b * PUSH_LINES + threadIdx.x;
+		const PushLine p = push_line(ln, i, n_lines, lt, bi_dir, world);
+		uint32_t r0 = 0, r1 = 0;                       // rank of my two hits inside the warp, among the hits to the same destination
+		for (uint32_t g = 0; g < world; ++g) {
+			const unsigned b0 = __ballot_sync(0xffffffffu, p.has0 && p.d0 == g), b1 = __ballot_sync(0xffffffffu, p.has1 && p.d1 == g);
+			const uint32_t before = (uint32_t)(__popc(b0 & lt_mask) + __popc(b1 & lt_mask));
+			if (p.has0 && p.d0 == g) r0 = before;
+			if (p.has1 && p.d1 == g) r1 = before + (p.d0 == g ? 1u : 0u);
+			if (lane == 0) s_wc[warp][g] = (uint32_t)(__popc(b0) + __popc(b1));
+		}
+		__syncthreads();
+		if (p.has0) {
+			const PRec r = ln[i];
+			const uint32_t bl = line_bl(ln, i, carry_bl);
+			uint32_t w0 = 0, w1 = 0;
+			for (uint32_t w = 0; w < warp; ++w) w0 += s_wc[w][p.d0], w1 += s_wc[w][p.d1];
+			{
+				uint4 *o = reinterpret_cast<uint4*>(dst[p.d0] + (pos_base[p.d0] + (long long)blk_off[(uint64_t)p.d0 * n_blk + b] + w0 + r0));
+				o[0] = make_uint4(r.qs, p.qid, r.qe, p.tid);
+				o[1] = make_uint4(r.ts, r.te, r.ml_rev, bl);
+			}
+			mx = r.qs > mx ? r.qs : mx;
+			if (p.has1) { // the same overlap seen from the target (hit.c:92-98)
+				uint4 *o = reinterpret_cast<uint4*>(dst[p.d1] + (pos_base[p.d1] + (long long)blk_off[(uint64_t)p.d1 * n_blk + b] + w1 + r1));
+				o[0] = make_uint4(r.ts, p.tid, r.te, p.qid);
+				o[1] = make_uint4(r.qs, r.qe, r.ml_rev, bl);
+				mx = r.ts > mx ? r.ts : mx;
+			}
+		}
+		__syncthreads();
+	}
+	__threadfence_system();                            // the stores to peer memory are out before the grid reports completion
+	mx = __reduce_max_sync(0xffffffffu, mx);
+	if (lane == 0 && mx) atomicMax(max_qs, mx);
+}
+
 // bucket sizes from the SORTED destination keys: bucket g = [lower_bound(g), lower_bound(g+1)); one thread per rank
 // (a per-element atomicAdd on `world` counters serialised 100 M atomics on two addresses: 85 ms at N=2)
 __global__ void k_dest_bounds(const uint32_t *sorted_dest, uint64_t n, uint32_t world, unsigned long long *cnt)
@@ -812,7 +1044,8 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		MAB_CUDA(cudaMemsetAsync(tab.key, 0, cap * 8, d.stream));
 		MAB_CUDA(cudaMemsetAsync(tab.first, 0xff, cap * 8, d.stream));
 		d.zero_scal(SC_COUNT, 4);
-		if (n_lines) MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, n_lines, min_span, min_match, tab, ln, d.d_scal + SC_COUNT);
+		set_rng(d, 0, n_lines, n_lines);
+		if (n_lines) MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, d.d_scal + SC_RNG, min_span, min_match, tab, ln, d.d_scal + SC_COUNT);
 		st.n_parsed = d.get_scal(SC_COUNT);
 		// every rank must take the same branch: agree on the outcome
 		std::vector<uint64_t> f = sc_allgather_u64(d, sc, d.h_scal[SC_COUNT + 2] != 0);
@@ -962,11 +1195,76 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 	}
 	*name_text_out = g_names; // names.off points into this buffer (owned by the caller from now on)
 	d.trace("shard-ingest:global ids");
-	// (6) local hits with global ids, bucketed by owner rank, exchanged
+	// (6) local hits with global ids go to the rank that owns their query read
+	if (G > 32) { fprintf(stderr, "[E::miniasm_b200] more than 32 ranks\n"); exit(79); }
+	if (n_ent) MAB_LAUNCH(d, k_local_gid, mab_grid(n_ent, 256), 256, 0, slots, n_ent, slot_of + my_ent_off, gt, tab);
+	uint32_t max_qs = 0;
+	uint64_t n_recv = 0;
+	std::vector<uint64_t> send_cnt(G, 0), recv_cnt(G, 0), mat((size_t)G * G, 0);
+	auto counts_matrix = [&]() { // every rank learns how much it receives from whom
+		uint64_t *m = mab_alloc<uint64_t>(d, (size_t)G * G + G);
+		MAB_CUDA(cudaMemcpyAsync(m + (size_t)G * G, send_cnt.data(), 8 * (size_t)G, cudaMemcpyHostToDevice, d.stream));
+		if (sc.active()) MAB_NCCL(ncclAllGather(m + (size_t)G * G, m, G, ncclUint64, sc.comm, d.stream));
+		else MAB_CUDA(cudaMemcpyAsync(m, m + (size_t)G * G, 8 * (size_t)G, cudaMemcpyDeviceToDevice, d.stream));
+		MAB_CUDA(cudaMemcpyAsync(mat.data(), m, 8 * (size_t)G * G, cudaMemcpyDeviceToHost, d.stream));
+		d.sync();
+		n_recv = 0;
+		for (int r = 0; r < G; ++r) recv_cnt[r] = mat[(size_t)r * G + sc.rank], n_recv += recv_cnt[r];
+		d.free(m);
+		if (n_recv >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 hits on one GPU\n"); exit(73); }
+	};
+	// (6a) fused route: count per (256-line block, destination), scan, then ONE kernel emits every hit straight into its owner's
+	// receive buffer over NVLink -- no send buffer, no bucket sort, no NCCL all-to-all.  Needs peer access to all receive buffers.
+	const uint64_t n_blk = (n_lines + PUSH_LINES - 1) / PUSH_LINES;
+	uint32_t *blk_cnt = mab_alloc<uint32_t>(d, (size_t)G * n_blk + 1);
+	uint64_t *blk_off = mab_alloc<uint64_t>(d, (size_t)G * n_blk + 1);
+	MAB_CUDA(cudaMemsetAsync(blk_cnt, 0, ((size_t)G * n_blk + 1) * 4, d.stream));
+	if (n_blk) MAB_LAUNCH(d, k_push_count, mab_grid(n_blk, 1, 148u * 8u), PUSH_LINES, 0, ln, n_lines, tab, bi_dir, (uint32_t)G, n_blk, blk_cnt);
+	{
+		cub::TransformInputIterator<uint64_t, U32ToU64i, const uint32_t*> in(blk_cnt, U32ToU64i());
+		size_t tb = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tb, in, blk_off, (int64_t)((size_t)G * n_blk + 1), d.stream);
+		void *tmp = d.tmp(tb);
+		cub::DeviceScan::ExclusiveSum(tmp, tb, in, blk_off, (int64_t)((size_t)G * n_blk + 1), d.stream);
+		++d.n_lib;
+	}
+	std::vector<uint64_t> bstart((size_t)G + 1, 0);
+	for (int g = 0; g <= G; ++g) MAB_CUDA(cudaMemcpyAsync(&bstart[g], blk_off + (size_t)g * n_blk, 8, cudaMemcpyDeviceToHost, d.stream));
+	d.sync();
+	for (int g = 0; g < G; ++g) send_cnt[g] = bstart[g + 1] - bstart[g];
+	const uint64_t n_loc = bstart[G];
+	if (n_loc >= (1ull << 32)) { fprintf(stderr, "[E::miniasm_b200] more than 2^32 hits parsed by one rank\n"); exit(73); }
+	counts_matrix();
+	dh_reserve(d, h, n_recv ? n_recv : 1);
+	std::vector<void*> peer;
+	const bool push = sc_peer_ptrs(d, sc, h.a, peer);       // (collective: also the barrier after which every receive buffer exists)
+	d.trace("shard-ingest:count hits per owner");
+	if (push) {
+		std::vector<long long> pos_base((size_t)G);
+		for (int g = 0; g < G; ++g) {
+			uint64_t before = 0;                            // hits rank g receives from the ranks before this one
+			for (int r = 0; r < sc.rank; ++r) before += mat[(size_t)r * G + g];
+			pos_base[g] = (long long)before - (long long)bstart[g];
+		}
+		long long *d_pos = (long long*)d.alloc(sizeof(long long) * (size_t)G);
+		DHit **d_dst = (DHit**)d.alloc(sizeof(void*) * (size_t)G);
+		MAB_CUDA(cudaMemcpyAsync(d_pos, pos_base.data(), sizeof(long long) * (size_t)G, cudaMemcpyHostToDevice, d.stream));
+		MAB_CUDA(cudaMemcpyAsync(d_dst, peer.data(), sizeof(void*) * (size_t)G, cudaMemcpyHostToDevice, d.stream));
+		d.zero_scal(SC_AUX, 1);
+		if (n_blk) MAB_LAUNCH(d, k_push_emit, mab_grid(n_blk, 1, 148u * 8u), PUSH_LINES, 0, ln, n_lines, tab, bi_dir, carry, (uint32_t)G, n_blk, blk_off, d_pos, d_dst, (unsigned*)(d.d_scal + SC_AUX));
+		max_qs = (uint32_t)(d.get_scal(SC_AUX) & 0xffffffffu);
+		{ // nobody sorts before everybody has finished writing: a one-word all-reduce, stream-ordered after the emit kernel on every rank
+			std::vector<uint64_t> mq = sc_allgather_u64(d, sc, max_qs);
+			for (int r = 0; r < G; ++r) if (mq[r] > max_qs) max_qs = (uint32_t)mq[r];
+		}
+		d.free(d_pos); d.free((void*)d_dst);
+		d.trace("shard-ingest:emit + push over NVLink");
+	}
+	d.free(blk_cnt); d.free(blk_off);
+	if (!push) {
+	// (6b) NCCL route: hits emitted locally, bucketed by owner with a stable one-pass radix sort, exchanged in an all-to-all
 	uint32_t *cnt = mab_alloc<uint32_t>(d, n_lines + 1);
 	uint64_t *off = mab_alloc<uint64_t>(d, n_lines + 1);
-	uint64_t n_loc = 0;
-	if (n_ent) MAB_LAUNCH(d, k_local_gid, mab_grid(n_ent, 256), 256, 0, slots, n_ent, slot_of + my_ent_off, gt, tab);
 	if (n_lines) {
 		MAB_LAUNCH(d, k_line_gids, mab_grid(n_lines, 256), 256, 0, ln, n_lines, tab, bi_dir, cnt);
 		size_t tb = 0;
@@ -974,17 +1272,10 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		void *tmp = d.tmp(tb);
 		cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, off, (int64_t)n_lines, d.stream);
 		++d.n_lib;
-		uint64_t lo; uint32_t lc;
-		MAB_CUDA(cudaMemcpyAsync(&lo, off + n_lines - 1, 8, cudaMemcpyDeviceToHost, d.stream));
-		MAB_CUDA(cudaMemcpyAsync(&lc, cnt + n_lines - 1, 4, cudaMemcpyDeviceToHost, d.stream));
-		d.sync();
-		n_loc = lo + lc;
 	}
-	if (n_loc >= (1ull << 32)) { fprintf(stderr, "[E::miniasm_b200] more than 2^32 hits parsed by one rank\n"); exit(73); }
 	DHit *loc = mab_alloc<DHit>(d, n_loc), *snd = mab_alloc<DHit>(d, n_loc);
 	uint32_t *dest = mab_alloc<uint32_t>(d, n_loc), *dest2 = mab_alloc<uint32_t>(d, n_loc), *ia = mab_alloc<uint32_t>(d, n_loc), *ib = mab_alloc<uint32_t>(d, n_loc);
 	d.zero_scal(SC_AUX, 1);
-	MAB_CUDA(cudaMemsetAsync(d.d_scal + 16, 0, 32 * 8, d.stream));
 	if (n_loc) {
 		MAB_LAUNCH(d, k_hit_emit_gid, mab_grid(n_lines, 256), 256, 0, ln, n_lines, cnt, off, tab, carry, (uint32_t)G, loc, dest, (unsigned*)(d.d_scal + SC_AUX));
 		MAB_LAUNCH(d, k_iota32, mab_grid(n_loc, 256), 256, 0, ia, n_loc);
@@ -996,42 +1287,25 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 		cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int64_t)n_loc, 0, eb, d.stream); // stable: file order kept inside every bucket
 		++d.n_lib;
 		MAB_LAUNCH(d, k_gather_hits, mab_grid(n_loc, 256), 256, 0, loc, dv.Current(), n_loc, snd);
-		MAB_LAUNCH(d, k_dest_bounds, 1, 32, 0, dk.Current(), n_loc, (uint32_t)G, d.d_scal + 16);
 	}
 	d.trace("shard-ingest:emit+bucket hits");
-	if (G > 32) { fprintf(stderr, "[E::miniasm_b200] more than 32 ranks\n"); exit(79); }
-	uint32_t max_qs = (uint32_t)(d.get_scal(SC_AUX) & 0xffffffffu);
-	std::vector<uint64_t> send_cnt(G), recv_cnt(G);
-	for (int r = 0; r < G; ++r) send_cnt[r] = d.h_scal[16 + r];
-	{ // counts matrix: every rank learns how much it receives from whom
-		uint64_t *m = mab_alloc<uint64_t>(d, (size_t)G * G + G);
-		MAB_CUDA(cudaMemcpyAsync(m + (size_t)G * G, send_cnt.data(), 8 * (size_t)G, cudaMemcpyHostToDevice, d.stream));
-		if (sc.active()) MAB_NCCL(ncclAllGather(m + (size_t)G * G, m, G, ncclUint64, sc.comm, d.stream));
-		else MAB_CUDA(cudaMemcpyAsync(m, m + (size_t)G * G, 8 * (size_t)G, cudaMemcpyDeviceToDevice, d.stream));
-		std::vector<uint64_t> mat((size_t)G * G);
-		MAB_CUDA(cudaMemcpyAsync(mat.data(), m, 8 * (size_t)G * G, cudaMemcpyDeviceToHost, d.stream));
-		d.sync();
-		for (int r = 0; r < G; ++r) recv_cnt[r] = mat[(size_t)r * G + sc.rank];
-		d.free(m);
-	}
-	uint64_t n_recv = 0;
-	for (int r = 0; r < G; ++r) n_recv += recv_cnt[r];
-	if (n_recv >= (1ull << 31)) { fprintf(stderr, "[E::miniasm_b200] more than 2^31 hits on one GPU\n"); exit(73); }
-	dh_reserve(d, h, n_recv ? n_recv : 1);
+	max_qs = (uint32_t)(d.get_scal(SC_AUX) & 0xffffffffu);
 	{
 		std::vector<uint64_t> sb(G), rb(G);
 		for (int r = 0; r < G; ++r) sb[r] = send_cnt[r] * sizeof(DHit), rb[r] = recv_cnt[r] * sizeof(DHit);
 		if (sc.active()) sc_alltoall_v(d, sc, snd, sb, h.a, rb);
 		else if (n_loc) MAB_CUDA(cudaMemcpyAsync(h.a, snd, n_loc * sizeof(DHit), cudaMemcpyDeviceToDevice, d.stream));
 	}
-	h.n = n_recv, h.n_seq = n_seq;
-	d.trace("shard-ingest:all-to-all");
 	{ // sort key width must cover the largest query start of any rank
 		std::vector<uint64_t> mq = sc_allgather_u64(d, sc, max_qs);
 		for (int r = 0; r < G; ++r) if (mq[r] > max_qs) max_qs = (uint32_t)mq[r];
 	}
 	d.sync();
 	d.free(loc); d.free(snd); d.free(dest); d.free(dest2); d.free(ia); d.free(ib); d.free(cnt); d.free(off);
+	}
+	h.n = n_recv, h.n_seq = n_seq;
+	d.trace("shard-ingest:exchange");
+	d.sync();
 	d.free(ln); d.free(start);
 	d.free(tab.key); d.free(tab.first); d.free(tab.id);
 	d.free(gt.key); d.free(gt.first); d.free(gt.win); d.free(gt.id);

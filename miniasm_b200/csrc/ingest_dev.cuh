@@ -22,6 +22,9 @@ struct NoContParams { int max_hang; float int_frac; }; // -R (ma_hit_no_cont, hi
 // line that names them before ids are assigned (st.n_dropped = their number).
 void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min_match, int bi_dir,
                 DHits &h, DNames &names, IngestStats &st, const NoContParams *nocont = nullptr);
+// load + ingest overlapped: host_text -> d_text in chunks on MabDev::copy_stream while arrived chunks are scanned and parsed
+void ingest_paf_stream(MabDev &d, char *d_text, const char *host_text, size_t len, int min_span, int min_match, int bi_dir,
+                       DHits &h, DNames &names, IngestStats &st);
 void names_free(MabDev &d, DNames &n);
 // byte offsets of the line starts of a text in device memory (len > 0); free with d.free.  start[n_lines] is not set.
 uint64_t *dev_line_starts(MabDev &d, const char *d_text, size_t len, uint64_t *n_lines_out);

@@ -73,6 +73,7 @@ struct MabDev {
 	int device = 0;
 	MabArena arena;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr;     // created on first use: H2D chunks of mab_load_ingest_text overlap the kernels on `stream`
 	void *cub_tmp = nullptr;
 	size_t cub_tmp_bytes = 0;
 	unsigned long long *d_scal = nullptr;   // 64 device scalars

@@ -31,6 +31,8 @@ void MabDev::destroy()
 	arena.release_all();
 	MAB_CUDA(cudaFree(d_scal));
 	MAB_CUDA(cudaFreeHost(h_scal));
+	if (copy_stream) MAB_CUDA(cudaStreamDestroy(copy_stream));
+	copy_stream = nullptr;
 	MAB_CUDA(cudaStreamDestroy(stream));
 	stream = nullptr; cub_tmp = nullptr; cub_tmp_bytes = 0; d_scal = h_scal = nullptr;
 }

@@ -6,6 +6,9 @@
 #include "mab_common.cuh"
 #include <nccl.h>
 #include <vector>
+#include <map>
+#include <string>
+#include <unistd.h>
 
 #define MAB_NCCL(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) { \
 	fprintf(stderr, "[E::miniasm_b200] %s failed at %s:%d: %s\n", #x, __FILE__, __LINE__, ncclGetErrorString(r_)); exit(79); } } while (0)
@@ -13,6 +16,7 @@
 struct ShardComm {
 	int rank = 0, world = 1;
 	ncclComm_t comm = nullptr;
+	std::map<std::string, void*> ipc_open;   // peer segments mapped through CUDA IPC (handle bytes -> local address), kept for the life of the context
 	bool active() const { return world > 1; }
 	uint32_t owner(uint32_t read_id) const { return read_id % (uint32_t)world; } // hash-sharding of read ids
 };
@@ -61,4 +65,59 @@ static inline void sc_alltoall_v(MabDev &d, ShardComm &sc, const void *send, con
 		so += send_cnt[r], ro += recv_cnt[r];
 	}
 	MAB_NCCL(ncclGroupEnd());
+}
+
+// Addresses under which this rank can load from / store to a buffer of every rank (NVLink peer access): `mine` is this rank's
+// buffer (inside an arena segment), out[r] the address of rank r's.  Ranks in other PROCESSES are reached through CUDA IPC handles
+// of their arena segment, ranks that are threads of THIS process through plain peer access (an IPC handle cannot be opened by the
+// process that exported it).  Collective: every rank calls it; false (on all ranks alike) if any rank cannot offer or reach a
+// buffer, or MAB_SHARD_P2P=0 -- the callers then take their NCCL route.
+static inline bool sc_peer_ptrs(MabDev &d, ShardComm &sc, const void *mine_ptr, std::vector<void*> &out)
+{
+	const int G = sc.world;
+	out.assign((size_t)G, nullptr);
+	struct PeerInfo { cudaIpcMemHandle_t h; uint64_t off, ok, pid, ptr, dev; };
+	PeerInfo mine;
+	memset(&mine, 0, sizeof(mine));
+	{
+		char *base; size_t off;
+		const char *env = getenv("MAB_SHARD_P2P");
+		mine.pid = (uint64_t)getpid(), mine.ptr = (uint64_t)(uintptr_t)mine_ptr, mine.dev = (uint64_t)d.device;
+		if (!(env && atoi(env) == 0) && d.arena.segment_of(mine_ptr, &base, &off) && cudaIpcGetMemHandle(&mine.h, base) == cudaSuccess) mine.off = off, mine.ok = 1;
+		else cudaGetLastError();
+	}
+	std::vector<PeerInfo> peers((size_t)G);
+	{
+		PeerInfo *buf = (PeerInfo*)d.alloc(sizeof(PeerInfo) * ((size_t)G + 1));
+		MAB_CUDA(cudaMemcpyAsync(buf + G, &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice, d.stream));
+		if (sc.active()) MAB_NCCL(ncclAllGather(buf + G, buf, sizeof(PeerInfo), ncclUint8, sc.comm, d.stream));
+		else MAB_CUDA(cudaMemcpyAsync(buf, buf + G, sizeof(PeerInfo), cudaMemcpyDeviceToDevice, d.stream));
+		MAB_CUDA(cudaMemcpyAsync(peers.data(), buf, sizeof(PeerInfo) * (size_t)G, cudaMemcpyDeviceToHost, d.stream));
+		d.sync();
+		d.free(buf);
+	}
+	bool p2p = true;
+	for (int r = 0; r < G && p2p; ++r) {
+		if (!peers[r].ok) { p2p = false; break; }
+		if (r == sc.rank) { out[r] = (void*)mine_ptr; continue; }
+		if (peers[r].pid == mine.pid) { // same process: direct peer access
+			int can = 0;
+			if (cudaDeviceCanAccessPeer(&can, d.device, (int)peers[r].dev) != cudaSuccess || !can) { cudaGetLastError(); p2p = false; break; }
+			cudaError_t e = cudaDeviceEnablePeerAccess((int)peers[r].dev, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); p2p = false; break; }
+			cudaGetLastError();
+			out[r] = (void*)(uintptr_t)peers[r].ptr;
+			continue;
+		}
+		std::string key((const char*)&peers[r].h, sizeof(cudaIpcMemHandle_t));
+		auto it = sc.ipc_open.find(key);
+		void *base = nullptr;
+		if (it != sc.ipc_open.end()) base = it->second;
+		else if (cudaIpcOpenMemHandle(&base, peers[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) sc.ipc_open[key] = base;
+		else { cudaGetLastError(); p2p = false; break; }
+		out[r] = (char*)base + peers[r].off;
+	}
+	std::vector<uint64_t> okv = sc_allgather_u64(d, sc, p2p ? 1 : 0); // all ranks take the same route
+	for (int r = 0; r < G; ++r) p2p = p2p && okv[r] != 0;
+	return p2p;
 }

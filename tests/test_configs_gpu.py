@@ -21,8 +21,9 @@ GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "
 CASES = [("c2_100k", 100_000, 2), ("c3_1m", 1_000_000, 3), ("c4_4m", 4_000_000, 4)]
 
 
+@pytest.mark.parametrize("mode", ["plain", "stream"])
 @pytest.mark.parametrize("name,n_reads,seed", CASES)
-def test_full_size_config_matches_reference_digest(name, n_reads, seed, built):
+def test_full_size_config_matches_reference_digest(name, n_reads, seed, mode, built):
     if name not in GOLD:
         pytest.skip(f"no golden digest for {name}")
     if name == "c4_4m" and os.environ.get("MAB_TEST_FULL") != "1":
@@ -38,8 +39,11 @@ def test_full_size_config_matches_reference_digest(name, n_reads, seed, built):
         del view
         ctx = lib.mab_create(0)
         opt = lib.default_opt()
-        assert lib.mab_load_paf_text(ctx, buf, n_bytes) == 0
-        lib.mab_ingest(ctx, opt.min_span, opt.min_match, 1)     # (synchronises: the host text is no longer needed)
+        if mode == "stream":                                    # load + ingest overlapped, chunk by chunk (pageable source here)
+            assert lib.mab_load_ingest_text(ctx, buf, n_bytes, opt.min_span, opt.min_match, 1) == 0
+        else:
+            assert lib.mab_load_paf_text(ctx, buf, n_bytes) == 0
+            lib.mab_ingest(ctx, opt.min_span, opt.min_match, 1) # (synchronises: the host text is no longer needed)
     finally:
         free()
     lib.mab_select(ctx, C.byref(opt), 0, 0, 100)

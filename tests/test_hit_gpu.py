@@ -147,3 +147,34 @@ def test_sub_group_sizes(ref, prod):
         sp = prod.ma_hit_sub(dp, 0.05, clip, len(a), pa, 200)
         assert np.array_equal(capi.np_from_ptr(sr, 200, SUB_DT), capi.np_from_ptr(sp, 200, SUB_DT)), (dp, clip)
         capi.c_free(sr), capi.c_free(sp), capi.c_free(pa)
+
+
+@pytest.mark.parametrize("name", ["tiny_exact", "chaos", "shuffled", "skew_small"])
+def test_streamed_ingest_equals_two_calls(name, pafs, prod):
+    """mab_load_ingest_text (chunks parsed while the next ones cross PCIe) must leave exactly the hits and the dictionary that
+    mab_load_paf_text + mab_ingest leave; the weird-line file of test_cli_gpu exercises the short-line capacity fallback."""
+    data = open(pafs[name], "rb").read()
+    opt = prod.default_opt()
+    res = []
+    for stream in (False, True):
+        ctx = prod.mab_create(0)
+        if stream:
+            assert prod.mab_load_ingest_text(ctx, data, len(data), opt.min_span, opt.min_match, 1) == 0
+        else:
+            assert prod.mab_load_paf_text(ctx, data, len(data)) == 0
+            prod.mab_ingest(ctx, opt.min_span, opt.min_match, 1)
+        n = C.c_size_t(0)
+        hp = prod.mab_export_hits(ctx, C.byref(n))
+        hits = capi.np_from_ptr(hp, n.value, HIT_DT)
+        capi.c_free(hp)
+        d = prod.mab_export_dict(ctx)
+        names = [(d.contents.seq[i].name, d.contents.seq[i].len) for i in range(d.contents.n_seq)]
+        prod.sd_destroy(d)
+        prod.mab_destroy(ctx)
+        res.append((canon_mask(hits), names))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+    tiny = b"a\t1\t2\n\n\n\nq\t5000\t0\t4000\t+\tt\t5000\t1000\t5000\t800\t4000\t255\n" + b"\n" * 5000   # far more lines than len/24
+    ctx = prod.mab_create(0)
+    assert prod.mab_load_ingest_text(ctx, tiny, len(tiny), opt.min_span, opt.min_match, 1) == 0
+    assert prod.mab_stats(ctx).contents.n_hits_stored == 2
+    prod.mab_destroy(ctx)
