@@ -313,10 +313,12 @@ def main():
         free()
 
         def e2e_step():
-            if world > 1:
-                lib.mab_load_paf_text(ctx, pinned.data_ptr(), n_bytes)        # H2D
-                device_steps()
-            else:                                                              # H2D in chunks, parsed while the next ones arrive
+            if world > 1:                                                      # H2D in chunks, parsed while the next ones arrive
+                lib.mab_load_ingest_text_sharded(ctx, pinned.data_ptr(), n_bytes, opt.min_span, opt.min_match, 1)
+                lib.mab_select_sharded(ctx, C.byref(opt))
+                lib.mab_layout_sharded(ctx, C.byref(opt))
+                lib.mab_unitigs(ctx)
+            else:
                 lib.mab_load_ingest_text(ctx, pinned.data_ptr(), n_bytes, opt.min_span, opt.min_match, 1)
                 lib.mab_select(ctx, C.byref(opt), 0, 0, 100)
                 lib.mab_layout(ctx, C.byref(opt), 100)

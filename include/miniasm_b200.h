@@ -204,6 +204,7 @@ long mab_write_gfa_reads(mab_ctx_t *ctx, FILE *fp, const char *fn_reads);
 int mab_nccl_unique_id(void *out128);
 int mab_shard_init(mab_ctx_t *ctx, int rank, int world, const void *id128);
 int mab_ingest_sharded(mab_ctx_t *ctx, int min_span, int min_match, int bi_dir);
+int mab_load_ingest_text_sharded(mab_ctx_t *ctx, const char *text, size_t len, int min_span, int min_match, int bi_dir); /* load (this rank's byte range) + ingest, overlapped */
 int mab_select_sharded(mab_ctx_t *ctx, const ma_opt_t *opt);
 int mab_layout_sharded(mab_ctx_t *ctx, const ma_opt_t *opt);
 

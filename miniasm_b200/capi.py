@@ -164,6 +164,7 @@ _PRODUCT_ONLY = {
     "mab_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mab_shard_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "mab_ingest_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "mab_load_ingest_text_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]),
     "mab_select_sharded": (C.c_int, [C.c_void_p, C.POINTER(MaOpt)]),
     "mab_layout_sharded": (C.c_int, [C.c_void_p, C.POINTER(MaOpt)]),
     "mab_set_verbose": (None, [C.c_int]),

@@ -735,6 +735,24 @@ int mab_ingest_sharded(mab_ctx_t *c, int min_span, int min_match, int bi_dir)
 	return 0;
 }
 
+/* mab_load_paf_text + mab_ingest_sharded in one call: this rank's bytes cross PCIe in chunks while the arrived ones are parsed */
+int mab_load_ingest_text_sharded(mab_ctx_t *c, const char *text, size_t len, int min_span, int min_match, int bi_dir)
+{
+	MAB_CUDA(cudaSetDevice(c->dev.device));
+	MabDev &d = c->dev;
+	ctx_reset_reads(c);
+	text_reserve(c, len);
+	c->text_len = len;
+	PhaseTimer pt(d, &c->stats.ms_ingest, "mab_load_ingest_text_sharded");
+	ingest_paf_sharded(d, c->sc, c->d_text, c->text_len, min_span, min_match, bi_dir, c->hits, c->names, &c->name_text, c->ist, text);
+	c->n_seq = c->names.n_seq;
+	c->stats.n_lines = c->ist.n_parsed, c->stats.n_hits_stored = c->ist.n_hits, c->stats.n_seq_in = c->ist.n_seq;
+	if (!mab_mute && ma_verbose >= 3 && c->sc.rank == 0)
+		fprintf(stderr, "[M::%s::%s] read %ld hits; stored %ld hits and %d sequences (%ld bp)\n", "ma_hit_read", sys_timestamp(),
+				(long)c->ist.n_parsed, (long)c->ist.n_hits, (int)c->ist.n_seq, (long)c->ist.tot_len);
+	return 0;
+}
+
 /* default read selection (main.c:119-142 with no -1/-2/-S): the interval tables are completed by all-reduce */
 int mab_select_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 {

@@ -82,8 +82,7 @@ static void *rank_main(void *p)
 	rank_job_t *j = (rank_job_t*)p;
 	j->ctx = mab_create(j->device);
 	mab_shard_init(j->ctx, j->rank, j->world, j->nccl_id);
-	mab_load_paf_text(j->ctx, j->text, j->len);
-	mab_ingest_sharded(j->ctx, j->opt->min_span, j->opt->min_match, j->bi_dir);
+	mab_load_ingest_text_sharded(j->ctx, j->text, j->len, j->opt->min_span, j->opt->min_match, j->bi_dir); /* chunks parsed while the next ones are copied */
 	mab_select_sharded(j->ctx, j->opt);
 	mab_layout_sharded(j->ctx, j->opt);
 	return 0;
@@ -144,7 +143,6 @@ static mab_ctx_t *run_sharded(const char *fn, const ma_opt_t *opt, int bi_dir, i
 		cut[r] = q ? (size_t)(q - text) + 1 : len;
 	}
 	cut[world] = len;
-	setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);      /* stdout carries the GFA: NCCL's version banner / debug lines go to stderr */
 	mab_nccl_unique_id(id);
 	for (r = 0; r < world; ++r) {
 		job[r].rank = r, job[r].world = world, job[r].device = device0 + r, job[r].bi_dir = bi_dir, job[r].opt = opt;
@@ -164,6 +162,7 @@ int main(int argc, char *argv[])
 	int i, c, stage = 100, no_first = 0, no_second = 0, bi_dir = 1, o_set = 0, no_cont = 0, device = 0, n_gpus = 1, sharded_done = 0, gpu_seq = 0;
 	const char *fn_reads = 0, *outfmt = "ug", *env;
 	mab_ctx_t *ctx;
+	FILE *out = stdout;          /* where the GFA goes */
 	sdict_t *d = 0;
 	ma_sub_t *sub = 0;
 
@@ -210,6 +209,13 @@ int main(int argc, char *argv[])
 		n_gpus = 1;
 	}
 	if (n_gpus > 1) { /* steps 1-4 sharded; what follows (unitigs, output) runs on rank 0's context as in a single-GPU run */
+		/* stdout carries the GFA and NCCL prints its version banner (NCCL_DEBUG=VERSION) there: the GFA keeps the original
+		 * descriptor, everything else that writes to fd 1 from here on lands on stderr */
+		int fd;
+		fflush(stdout);
+		fd = dup(1);
+		if (fd >= 0 && dup2(2, 1) >= 0) out = fdopen(fd, "w");
+		if (out == 0) out = stdout;
 		fprintf(stderr, "[M::%s] ===> Step 1: reading read mappings <===\n", __func__);
 		fprintf(stderr, "[M::%s] ===> Step 2: 1-pass (crude) read selection <===\n", __func__);
 		fprintf(stderr, "[M::%s] ===> Step 3: 2-pass (fine) read selection <===\n", __func__);
@@ -260,23 +266,24 @@ int main(int argc, char *argv[])
 			fprintf(stderr, "[M::%s] ===> Step 5: generating unitigs <===\n", __func__);
 			mab_unitigs(ctx);
 			if (gpu_gfa) {
-				mab_write_gfa(ctx, stdout);
-			} else if (gpu_seq && mab_write_gfa_reads(ctx, stdout, fn_reads) != -2) {
+				mab_write_gfa(ctx, out);
+			} else if (gpu_seq && mab_write_gfa_reads(ctx, out, fn_reads) != -2) {
 				/* ma_ug_seq + ma_ug_print on the GPU (MAB_GPU_SEQ=0, or a reads file that is neither FASTA-like nor 4-line FASTQ: host path below) */
 			} else {
 				d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
 				ug = mab_export_ug(ctx);
 				if (fn_reads) ma_ug_seq(ug, d, sub, fn_reads);
-				ma_ug_print(ug, d, sub, stdout);
+				ma_ug_print(ug, d, sub, out);
 				ma_ug_destroy(ug);
 			}
 		} else {
 			asg_t *sg = mab_export_sg(ctx);
 			d = mab_export_dict(ctx), sub = mab_export_sub(ctx);
-			ma_sg_print(sg, d, sub, stdout);
+			ma_sg_print(sg, d, sub, out);
 			asg_destroy(sg);
 		}
 	}
+	if (out != stdout) fclose(out);
 	free(sub);
 	if (d) sd_destroy(d);
 	mab_destroy(ctx);

@@ -572,18 +572,14 @@ void ingest_paf(MabDev &d, const char *d_text, size_t len, int min_span, int min
 	ingest_finish(d, d_text, len, start, ln, n_lines, tab, cap, bi_dir, nocont, h, names, st);
 }
 
-// Load + ingest in one call: the text crosses PCIe in chunks on a copy stream while the chunks that have arrived are scanned for
-// line starts and parsed on the context's stream (k_parse needs nothing global any more), so of the ingest only the id ranking, the
-// hit emission and the sort are left when the last byte lands.  host_text may be pageable or pinned; d_text has room for len + 64.
-// Capacities are estimates (a 12-column line has >= 24 bytes); a text that breaks them is ingested again the plain way.
-void ingest_paf_stream(MabDev &d, char *d_text, const char *host_text, size_t len, int min_span, int min_match, int bi_dir,
-                       DHits &h, DNames &names, IngestStats &st)
+// Front end of an ingest with the text still on the host: it crosses PCIe in 64 MB chunks on a copy stream while the chunks that
+// have arrived are scanned for line starts and parsed (store filter, dictionary) on the context's stream -- k_parse needs nothing
+// global any more.  host_text may be pageable or pinned (pinned overlaps fully); d_text has room for len + 64.  Capacities are
+// estimates (a 12-column line has >= 24 bytes): false = the text broke them (or the dictionary overflowed), nothing is kept and the
+// caller parses the now-resident text the plain way.  No collectives inside (the sharded ingest calls it rank by rank).
+static bool stream_parse(MabDev &d, char *d_text, const char *host_text, size_t len, int min_span, int min_match,
+                         uint64_t **start_out, PRec **ln_out, NameTab *tab_out, uint64_t *cap_out, uint64_t *n_lines_out, uint64_t *n_parsed_out)
 {
-	memset(&st, 0, sizeof(st));
-	names = DNames();
-	h.n = 0, h.n_seq = 0;
-	if (len == 0) { dh_reserve(d, h, 1); return; }
-	if (len >= (1ull << NT_OFF_BITS) - 1) { fprintf(stderr, "[E::miniasm_b200] more than 2^37 bytes of PAF on one GPU\n"); exit(73); }
 	const uint64_t CH_TILES = (64ull << 20) / NL_TILE, n_tile = (len + NL_TILE - 1) / NL_TILE;       // 64 MB chunks, whole tiles
 	const uint64_t n_chunk = (n_tile + CH_TILES - 1) / CH_TILES;
 	const uint64_t line_cap = len / 24 + 1024;
@@ -625,17 +621,35 @@ void ingest_paf_stream(MabDev &d, char *d_text, const char *host_text, size_t le
 	}
 	unsigned long long fin[8];
 	MAB_CUDA(cudaMemcpyAsync(fin, state, sizeof(fin), cudaMemcpyDeviceToHost, d.stream));
-	st.n_parsed = d.get_scal(SC_COUNT);                         // (synchronises)
+	*n_parsed_out = d.get_scal(SC_COUNT);                       // (synchronises)
 	for (uint64_t k = 0; k < n_chunk; ++k) MAB_CUDA(cudaEventDestroy(ev[k]));
 	MAB_CUDA(cudaEventDestroy(ready));
 	d.free(cnt); d.free(base); d.free(state);
 	const uint64_t n_lines = fin[0] + 1;
-	if (n_lines >= line_cap || d.h_scal[SC_COUNT + 2] != 0) {    // estimates broken (very short lines / more names than slots): the plain path sizes exactly
+	if (n_lines >= line_cap || d.h_scal[SC_COUNT + 2] != 0) {   // estimates broken (very short lines / more names than slots)
 		d.free(start); d.free(ln); d.free(tab.key); d.free(tab.first); d.free(tab.id);
-		ingest_paf(d, d_text, len, min_span, min_match, bi_dir, h, names, st, nullptr);
+		return false;
+	}
+	*start_out = start, *ln_out = ln, *tab_out = tab, *cap_out = cap, *n_lines_out = n_lines;
+	return true;
+}
+
+// mab_load_paf_text + mab_ingest in one call (same result): when the last byte of the text lands only the id ranking, the hit
+// emission and the sort are left.
+void ingest_paf_stream(MabDev &d, char *d_text, const char *host_text, size_t len, int min_span, int min_match, int bi_dir,
+                       DHits &h, DNames &names, IngestStats &st)
+{
+	memset(&st, 0, sizeof(st));
+	names = DNames();
+	h.n = 0, h.n_seq = 0;
+	if (len == 0) { dh_reserve(d, h, 1); return; }
+	if (len >= (1ull << NT_OFF_BITS) - 1) { fprintf(stderr, "[E::miniasm_b200] more than 2^37 bytes of PAF on one GPU\n"); exit(73); }
+	uint64_t *start; PRec *ln; NameTab tab; uint64_t cap, n_lines, n_parsed;
+	if (!stream_parse(d, d_text, host_text, len, min_span, min_match, &start, &ln, &tab, &cap, &n_lines, &n_parsed)) {
+		ingest_paf(d, d_text, len, min_span, min_match, bi_dir, h, names, st, nullptr); // the text is resident now: the plain path sizes exactly
 		return;
 	}
-	st.n_lines = n_lines;
+	st.n_parsed = n_parsed, st.n_lines = n_lines;
 	d.trace("ingest:stream (copy + line starts + parse + dictionary)");
 	ingest_finish(d, d_text, len, start, ln, n_lines, tab, cap, bi_dir, nullptr, h, names, st);
 }
@@ -925,11 +939,16 @@ __global__ void __launch_bounds__(PUSH_LINES) k_push_count(const PRec *ln, uint6
 	}
 }
 
-// dst[g] = receive buffer of rank g (peer address); pos_base[g] = (offset of this rank's bucket in it) - blk_off[g * n_blk]
+// dst[g] = receive buffer of rank g (peer address); pos_base[g] = (offset of this rank's bucket in it) - blk_off[g * n_blk].
+// The block's hits are first laid out in shared memory grouped by destination (in file order inside a group), then the whole
+// staging area goes out with consecutive threads writing consecutive 16-byte halves: every destination receives one contiguous
+// run per block (2 KB at 8 ranks) instead of isolated 32-byte stores -- isolated stores ran the NVLink at ~290 GB/s (11 ms at N=4).
 __global__ void __launch_bounds__(PUSH_LINES) k_push_emit(const PRec *ln, uint64_t n_lines, NameTab lt, int bi_dir, uint32_t carry_bl, uint32_t world, uint64_t n_blk,
                                                           const uint64_t *__restrict__ blk_off, const long long *__restrict__ pos_base, DHit *const *__restrict__ dst, unsigned *max_qs)
 {
 	__shared__ uint32_t s_wc[PUSH_LINES / 32][32];
+	__shared__ uint32_t s_seg[33];                                  // exclusive prefix of the block's per-destination totals
+	__shared__ __align__(16) uint4 s_hit[2 * 2 * PUSH_LINES];        // up to two hits per line, two 16-byte halves per hit
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
 	unsigned mx = 0;
 	for (uint64_t b = blockIdx.x; b < n_blk; b += gridDim.x) {
@@ -944,23 +963,40 @@ __global__ void __launch_bounds__(PUSH_LINES) k_push_emit(const PRec *ln, uint64
 			if (lane == 0) s_wc[warp][g] = (uint32_t)(__popc(b0) + __popc(b1));
 		}
 		__syncthreads();
+		if (warp == 0) { // per-destination totals of the block and their exclusive prefix
+			uint32_t t = 0;
+			if (lane < world) for (uint32_t w = 0; w < PUSH_LINES / 32; ++w) t += s_wc[w][lane];
+			uint32_t inc = t;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += y; }
+			s_seg[lane + 1] = inc;
+			if (lane == 0) s_seg[0] = 0;
+		}
+		__syncthreads();
 		if (p.has0) {
 			const PRec r = ln[i];
 			const uint32_t bl = line_bl(ln, i, carry_bl);
 			uint32_t w0 = 0, w1 = 0;
 			for (uint32_t w = 0; w < warp; ++w) w0 += s_wc[w][p.d0], w1 += s_wc[w][p.d1];
-			{
-				uint4 *o = reinterpret_cast<uint4*>(dst[p.d0] + (pos_base[p.d0] + (long long)blk_off[(uint64_t)p.d0 * n_blk + b] + w0 + r0));
-				o[0] = make_uint4(r.qs, p.qid, r.qe, p.tid);
-				o[1] = make_uint4(r.ts, r.te, r.ml_rev, bl);
-			}
+			const uint32_t k0 = s_seg[p.d0] + w0 + r0;
+			s_hit[2 * k0] = make_uint4(r.qs, p.qid, r.qe, p.tid);
+			s_hit[2 * k0 + 1] = make_uint4(r.ts, r.te, r.ml_rev, bl);
 			mx = r.qs > mx ? r.qs : mx;
 			if (p.has1) { // the same overlap seen from the target (hit.c:92-98)
-				uint4 *o = reinterpret_cast<uint4*>(dst[p.d1] + (pos_base[p.d1] + (long long)blk_off[(uint64_t)p.d1 * n_blk + b] + w1 + r1));
-				o[0] = make_uint4(r.ts, p.tid, r.te, p.qid);
-				o[1] = make_uint4(r.qs, r.qe, r.ml_rev, bl);
+				const uint32_t k1 = s_seg[p.d1] + w1 + r1;
+				s_hit[2 * k1] = make_uint4(r.ts, p.tid, r.te, p.qid);
+				s_hit[2 * k1 + 1] = make_uint4(r.qs, r.qe, r.ml_rev, bl);
 				mx = r.ts > mx ? r.ts : mx;
 			}
+		}
+		__syncthreads();
+		const uint32_t total = s_seg[world];
+		for (uint32_t j = threadIdx.x; j < 2 * total; j += PUSH_LINES) {
+			const uint32_t k = j >> 1;
+			uint32_t g = 0;
+			while (s_seg[g + 1] <= k) ++g;                // destination whose group holds staging slot k
+			uint4 *o = reinterpret_cast<uint4*>(dst[g] + (pos_base[g] + (long long)blk_off[(uint64_t)g * n_blk + b] + (k - s_seg[g])));
+			o[j & 1] = s_hit[j];
 		}
 		__syncthreads();
 	}
@@ -999,63 +1035,54 @@ __global__ void k_add_u64(uint64_t *a, uint64_t n, uint64_t add) { for (uint64_t
 
 __global__ void k_iota32(uint32_t *a, uint64_t n) { for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) a[i] = (uint32_t)i; }
 
-void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len, int min_span, int min_match, int bi_dir,
-                        DHits &h, DNames &names, char **name_text_out, IngestStats &st)
-{
+void ingest_paf_sharded(MabDev &d, ShardComm &sc, char *d_text, size_t len, int min_span, int min_match, int bi_dir,
+                        DHits &h, DNames &names, char **name_text_out, IngestStats &st, const char *host_text)
+{	// host_text != nullptr: this rank's bytes are still on the host; they are copied in chunks while the arrived chunks are parsed
 	memset(&st, 0, sizeof(st));
 	names = DNames();
 	h.n = 0, h.n_seq = 0;
 	const int G = sc.world;
-	// (1) local line starts and parse
-	uint64_t *start = nullptr, n_lines = 0;
-	if (len) {
-		const uint64_t n_tile = (len + NL_TILE - 1) / NL_TILE;
-		uint64_t *cnt = mab_alloc<uint64_t>(d, n_tile + 1), *base = mab_alloc<uint64_t>(d, n_tile + 1);
-		MAB_LAUNCH(d, k_nl_count, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, cnt);
-		size_t tb = 0;
-		cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, base, (int64_t)(n_tile + 1), d.stream);
-		void *tmp = d.tmp(tb);
-		cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, base, (int64_t)(n_tile + 1), d.stream);
-		++d.n_lib;
-		uint64_t n_nl;
-		MAB_CUDA(cudaMemcpyAsync(&n_nl, base + n_tile, 8, cudaMemcpyDeviceToHost, d.stream));
-		d.sync();
-		n_lines = n_nl + 1;
-		start = mab_alloc<uint64_t>(d, n_lines + 1);
-		MAB_CUDA(cudaMemsetAsync(start, 0, 8, d.stream));
-		MAB_LAUNCH(d, k_nl_write, mab_grid(n_tile, 1, 148u * 32u), NL_THREADS, 0, d_text, len, n_tile, base, start + 1);
-		d.free(cnt); d.free(base);
-	}
-	d.trace("shard-ingest:line_starts");
+	// (1)+(2) local line starts, parse + store filter + local dictionary (exact: occurrences are compared with a witness in the text)
 	if (len >= (1ull << NT_OFF_BITS) - 1) { fprintf(stderr, "[E::miniasm_b200] more than 2^37 bytes of PAF on one GPU\n"); exit(73); }
-	PRec *ln = mab_alloc<PRec>(d, n_lines);
+	uint64_t *start = nullptr, n_lines = 0, cap = 1ull << 20, n_parsed = 0;
+	PRec *ln = nullptr;
+	NameTab tab{nullptr, nullptr, nullptr, 0};
+	bool have = false;                                      // this rank holds a finished local parse
+	if (host_text && len) {
+		have = stream_parse(d, d_text, host_text, len, min_span, min_match, &start, &ln, &tab, &cap, &n_lines, &n_parsed);
+		if (!have) cap = 1ull << 20;
+		d.trace("shard-ingest:stream (copy + line starts + parse + dictionary)");
+	}
+	if (!have) {
+		if (len) start = dev_line_starts(d, d_text, len, &n_lines);
+		ln = mab_alloc<PRec>(d, n_lines);
+		while (cap < n_lines / 4) cap <<= 1;
+	}
+	for (;;) {
+		bool overflow = false;
+		if (!have) {
+			tab = tab_alloc(d, cap);
+			d.zero_scal(SC_COUNT, 4);
+			set_rng(d, 0, n_lines, n_lines);
+			if (n_lines) MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, d.d_scal + SC_RNG, min_span, min_match, tab, ln, d.d_scal + SC_COUNT);
+			n_parsed = d.get_scal(SC_COUNT);
+			overflow = d.h_scal[SC_COUNT + 2] != 0;
+		}
+		// every rank must take the same branch: agree on the outcome
+		std::vector<uint64_t> f = sc_allgather_u64(d, sc, overflow);
+		bool any = false;
+		for (int r = 0; r < G; ++r) any |= f[r] != 0;
+		if (!any) break;
+		d.free(tab.key); d.free(tab.first); d.free(tab.id);   // (a rank whose own table was fine parses again too: same branch everywhere)
+		have = false;
+		cap <<= 2;
+		if (cap > (1ull << 33)) { fprintf(stderr, "[E::miniasm_b200] read-name table overflow\n"); exit(77); }
+	}
+	st.n_parsed = n_parsed;
 	std::vector<uint64_t> all_lines = sc_allgather_u64(d, sc, n_lines);
 	uint64_t line_base = 0, n_lines_all = 0;
 	for (int r = 0; r < G; ++r) { if (r < sc.rank) line_base += all_lines[r]; n_lines_all += all_lines[r]; }
 	st.n_lines = n_lines_all;
-
-	// (2) parse + store filter + local dictionary in one pass (exact: occurrences are compared with a witness in the text)
-	NameTab tab{nullptr, nullptr, nullptr, 0};
-	uint64_t cap = 1ull << 20;
-	while (cap < n_lines / 4) cap <<= 1;
-	for (;;) {
-		tab.key = (unsigned long long*)mab_alloc<uint64_t>(d, cap); tab.first = (unsigned long long*)mab_alloc<uint64_t>(d, cap); tab.id = mab_alloc<uint32_t>(d, cap);
-		tab.mask = cap - 1;
-		MAB_CUDA(cudaMemsetAsync(tab.key, 0, cap * 8, d.stream));
-		MAB_CUDA(cudaMemsetAsync(tab.first, 0xff, cap * 8, d.stream));
-		d.zero_scal(SC_COUNT, 4);
-		set_rng(d, 0, n_lines, n_lines);
-		if (n_lines) MAB_LAUNCH(d, k_parse, mab_grid((n_lines + PARSE_LINES - 1) / PARSE_LINES, 1, 148u * 16u), PARSE_LINES, 0, d_text, len, start, d.d_scal + SC_RNG, min_span, min_match, tab, ln, d.d_scal + SC_COUNT);
-		st.n_parsed = d.get_scal(SC_COUNT);
-		// every rank must take the same branch: agree on the outcome
-		std::vector<uint64_t> f = sc_allgather_u64(d, sc, d.h_scal[SC_COUNT + 2] != 0);
-		bool overflowed = false;
-		for (int r = 0; r < G; ++r) overflowed |= f[r] != 0;
-		if (!overflowed) break;
-		d.free(tab.key); d.free(tab.first); d.free(tab.id);
-		cap <<= 2;
-		if (cap > (1ull << 33)) { fprintf(stderr, "[E::miniasm_b200] read-name table overflow\n"); exit(77); }
-	}
 	d.trace("shard-ingest:parse+filter+local dictionary");
 	// bl carried over from earlier ranks for 10-field lines at the head of this range (applied when the hits are emitted)
 	uint32_t carry = 0;
@@ -1237,7 +1264,8 @@ void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len
 	counts_matrix();
 	dh_reserve(d, h, n_recv ? n_recv : 1);
 	std::vector<void*> peer;
-	const bool push = sc_peer_ptrs(d, sc, h.a, peer);       // (collective: also the barrier after which every receive buffer exists)
+	const char *penv = getenv("MAB_SHARD_PUSH");
+	const bool push = sc_peer_ptrs(d, sc, h.a, peer) && !(penv && atoi(penv) == 0); // (collective: also the barrier after which every receive buffer exists)
 	d.trace("shard-ingest:count hits per owner");
 	if (push) {
 		std::vector<long long> pos_base((size_t)G);

@@ -48,5 +48,6 @@ __host__ __device__ __forceinline__ uint64_t name_hash(const char *p, uint32_t s
 struct ShardComm;
 // Sharded variant: this rank's byte range of the PAF in, the hits of the reads this rank owns out.
 // *name_text_out receives a device buffer with all read names packed (names.off indexes it); the caller frees it.
-void ingest_paf_sharded(MabDev &d, ShardComm &sc, const char *d_text, size_t len, int min_span, int min_match, int bi_dir,
-                        DHits &h, DNames &names, char **name_text_out, IngestStats &st);
+// host_text != nullptr: the bytes are still on the host and cross PCIe in chunks while the arrived chunks are parsed.
+void ingest_paf_sharded(MabDev &d, ShardComm &sc, char *d_text, size_t len, int min_span, int min_match, int bi_dir,
+                        DHits &h, DNames &names, char **name_text_out, IngestStats &st, const char *host_text = nullptr);

@@ -21,18 +21,28 @@ def main():
     lib.set_verbose(0)
     ctx = lib.mab_create(local)
     sharded.init(lib, ctx, rank, world)
+    opt = lib.default_opt()
+    stream = os.environ.get("MAB_SHARD_STREAM", "1") != "0"     # load + ingest overlapped (what the CLI and bench.py's e2e leg do) or as two calls
+    free = None
     if paf.startswith("gen:"):
         import bench
         buf, n_bytes, _, free = bench.generate_args(bench.WORKLOADS[paf[4:]]["args"], rank, world)
-        lib.mab_load_paf_text(ctx, buf, n_bytes)           # (synchronises: the host copy can go)
-        free()
+        part, n_part = buf, n_bytes
     else:
         data = open(paf, "rb").read()
         b, e = sharded.split_ranges(data, world)[rank]
         part = data[b:e]
-        lib.mab_load_paf_text(ctx, part, len(part))
-    opt = lib.default_opt()
-    sharded.run(lib, ctx, opt)
+        n_part = len(part)
+    if stream:
+        lib.mab_load_ingest_text_sharded(ctx, part, n_part, opt.min_span, opt.min_match, 1)
+    else:
+        lib.mab_load_paf_text(ctx, part, n_part)
+        lib.mab_ingest_sharded(ctx, opt.min_span, opt.min_match, 1)
+    if free:
+        free()                                                  # (both calls synchronise: the host copy can go)
+    lib.mab_select_sharded(ctx, C.byref(opt))
+    lib.mab_layout_sharded(ctx, C.byref(opt))
+    lib.mab_unitigs(ctx)
     if rank == 0:
         st = lib.mab_stats(ctx).contents
         print(f"[shard_worker] world {world}: {st.n_lines} lines on rank 0, {st.n_seq_final} reads kept, {st.n_reduced} arcs reduced, {st.n_utg} unitigs", flush=True)

@@ -32,7 +32,9 @@ def test_sharded_gfa_equals_reference(name, world, built, paf_dir):
     out = f"{paf_dir}/sh_{name}_{world}.gfa"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "shard_worker.py"), paf, out]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    # half of the sets load and ingest in two calls, the other half overlapped (MAB_SHARD_STREAM, tests/shard_worker.py)
+    env = {**os.environ, "MAB_SHARD_STREAM": "0" if name in ("chaos_small", "bubbles800", "shuffled") else "1"}
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:]
     want = subprocess.run([REF, paf], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
     assert open(out, "rb").read() == want
@@ -89,3 +91,18 @@ def test_cli_multi_gpu(name, world, extra, built, paf_dir):
         cnt = lambda err: [re.sub(r"::\d+\.\d+\*\d+\.\d+\]", "]", x) for x in err.decode().splitlines()
                            if x.startswith("[M::") and "::main]" not in x and any(k in x for k in ("ma_hit_read", "ma_hit_contained", "ma_sg_gen", "asg_")) and "===>" not in x]
         assert cnt(got.stderr) == cnt(want.stderr)
+
+
+@pytest.mark.parametrize("name", ["chaos", "shuffled", "bubbles800", "lowcov", "c2_100k"])
+@pytest.mark.parametrize("stream", ["1", "0"])
+def test_sharded_pipeline_world1(name, stream, built, paf_dir):
+    """The sharded code path with ONE rank on one GPU: every kernel of it runs (count / scan / staged emit into the receive buffer, the
+    global name table, the replicated tail), only the collectives degenerate -- keeps the multi-GPU path under test on 1-GPU boxes."""
+    paf = synth.generate(name, f"{paf_dir}/sh1_{name}.paf")
+    out = f"{paf_dir}/sh1_{name}_{stream}.gfa"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", os.path.join(ROOT, "tests", "shard_worker.py"), paf, out]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env={**os.environ, "MAB_SHARD_STREAM": stream})
+    assert r.returncode == 0, r.stdout[-3000:]
+    want = subprocess.run([REF, paf], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+    assert open(out, "rb").read() == want
