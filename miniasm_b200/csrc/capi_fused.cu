@@ -753,6 +753,19 @@ int mab_load_ingest_text_sharded(mab_ctx_t *c, const char *text, size_t len, int
 	return 0;
 }
 
+static void sum_over_ranks(void *ctx, unsigned long long *v, int n) // MabCountHook: the counts of a log line, summed over the ranks
+{
+	mab_ctx *c = (mab_ctx*)ctx;
+	if (!c->sc.active() || n <= 0 || n > 8) return;
+	MabDev &d = c->dev;
+	unsigned long long *buf = (unsigned long long*)mab_alloc<uint64_t>(d, 8);
+	MAB_CUDA(cudaMemcpyAsync(buf, v, 8 * (size_t)n, cudaMemcpyHostToDevice, d.stream));
+	MAB_NCCL(ncclAllReduce(buf, buf, (size_t)n, ncclUint64, ncclSum, c->sc.comm, d.stream));
+	MAB_CUDA(cudaMemcpyAsync(v, buf, 8 * (size_t)n, cudaMemcpyDeviceToHost, d.stream));
+	d.sync();
+	d.free(buf);
+}
+
 /* default read selection (main.c:119-142 with no -1/-2/-S): the interval tables are completed by all-reduce */
 int mab_select_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 {
@@ -763,15 +776,21 @@ int mab_select_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	PhaseTimer pt(d, &c->stats.ms_select, "mab_select_sharded");
 	ctx_drop_graphs(c);
 	const int msave = mab_mute;
-	if (sc.rank != 0) mab_mute = 1; // counts in the log lines are per rank: only rank 0 talks (thread-local: ranks may be threads of one process)
+	if (sc.rank != 0) mab_mute = 1; // only rank 0 talks (thread-local: ranks may be threads of one process); the counts it prints are summed over the ranks
+	mab_count_hook = sum_over_ranks, mab_count_hook_ctx = c;
 	const uint32_t n = c->n_seq;
 	d.free(c->sub);
 	c->sub = mab_alloc<DSub>(d, n);
+	d.trace("shard-select:begin");
 	dh_sub(d, h, opt->min_dp, opt->min_iden, 0, c->sub);                  // rows of the reads this rank owns; zeros elsewhere
+	d.trace("shard-select:sub1");
 	sc_allreduce(d, sc, c->sub, n, ncclUint64, ncclSum);                   // every row is written by exactly one rank
+	d.trace("shard-select:all-reduce sub1");
 	dh_cut_flt(d, h, c->sub, opt->min_span, (int)(opt->max_hang * 1.5), (int)(opt->min_ovlp * .5), &c->cov);
+	d.trace("shard-select:cut1+flt");
 	DSub *sub2 = mab_alloc<DSub>(d, n), *cut2 = mab_alloc<DSub>(d, n);
 	dh_sub(d, h, opt->min_dp, opt->min_iden, opt->min_span / 2, sub2);
+	d.trace("shard-select:sub2");
 	sc_allreduce(d, sc, sub2, n, ncclUint64, ncclSum);
 	if (n) MAB_CUDA(cudaMemcpyAsync(cut2, sub2, (size_t)n * sizeof(DSub), cudaMemcpyDeviceToDevice, d.stream));
 	dh_sub_merge(d, n, c->sub, sub2);
@@ -784,6 +803,7 @@ int mab_select_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 		sc_allreduce(d, sc, used, n_seq, ncclUint8, ncclMax);
 	};
 	dh_contained(d, h, c->sub, nullptr, p, map, cut2, opt->min_span, &ex);
+	d.trace("shard-select:cut2+contained (+2 all-reduces)");
 	uint32_t *orig_new = mab_alloc<uint32_t>(d, h.n_seq);
 	if (n) MAB_LAUNCH(d, k_orig_from_map, mab_grid(n, 256), 256, 0, n, map, c->orig_id, orig_new);
 	d.free(c->orig_id);
@@ -791,6 +811,7 @@ int mab_select_sharded(mab_ctx_t *c, const ma_opt_t *opt)
 	c->n_seq = h.n_seq;
 	d.free(map); d.free(cut2);
 	mab_mute = msave;
+	mab_count_hook = nullptr, mab_count_hook_ctx = nullptr;
 	c->stats.n_hits_final = h.n, c->stats.n_seq_final = c->n_seq;
 	d.sync();
 	return 0;

@@ -10,6 +10,12 @@ extern "C" int ma_verbose;              // hit.c prints its [M::fn::timestamp] l
 extern "C" const char *sys_timestamp(void);
 #define ma_verbose_dev (mab_mute ? 0 : ma_verbose)
 
+// Sharded runs: the counts in the [M::...] lines are per rank; the caller installs a hook that sums them over the ranks (a collective:
+// every rank reaches every print site, muted or not).  Unset = single GPU, nothing to do.
+thread_local MabCountHook mab_count_hook = nullptr;
+thread_local void *mab_count_hook_ctx = nullptr;
+static inline void sum_ranks(unsigned long long *v, int n) { if (mab_count_hook) mab_count_hook(mab_count_hook_ctx, v, n); }
+
 __device__ __forceinline__ DHit ld_hit(const DHit *p)
 {
 	const uint4 *q = reinterpret_cast<const uint4*>(p);
@@ -63,7 +69,7 @@ constexpr int SEL_ROWS = 8, SEL_THREADS = 256, SEL_TILE = SEL_ROWS * SEL_THREADS
 static_assert(SEL_ROWS * (SEL_THREADS / 32) == 64, "k_sel_scatter scans exactly two counts per lane of one warp");
 
 __global__ void __launch_bounds__(SEL_THREADS)
-k_sel_count(const uint8_t *__restrict__ flag, size_t n, uint32_t *__restrict__ tile_cnt)
+k_sel_count(const uint8_t *__restrict__ flag, size_t n, uint32_t *__restrict__ tile_cnt, unsigned long long *__restrict__ total)
 {
 	__shared__ unsigned s_w[SEL_THREADS / 32];
 	const size_t base = (size_t)blockIdx.x * SEL_TILE;
@@ -81,6 +87,7 @@ k_sel_count(const uint8_t *__restrict__ flag, size_t n, uint32_t *__restrict__ t
 		#pragma unroll
 		for (int w = 0; w < SEL_THREADS / 32; ++w) t += s_w[w];
 		tile_cnt[blockIdx.x] = t;
+		if (t) atomicAdd(total, (unsigned long long)t);
 	}
 }
 
@@ -138,7 +145,12 @@ static size_t select_hits(MabDev &d, DHits &h, const uint8_t *flag)
 	} else {
 		const uint32_t n_tile = (uint32_t)((h.n + SEL_TILE - 1) / SEL_TILE);
 		uint32_t *cnt = mab_alloc<uint32_t>(d, n_tile), *off = mab_alloc<uint32_t>(d, n_tile);
-		MAB_LAUNCH(d, k_sel_count, n_tile, SEL_THREADS, 0, flag, h.n, cnt);
+		d.zero_scal(SC_NSEL);
+		MAB_LAUNCH(d, k_sel_count, n_tile, SEL_THREADS, 0, flag, h.n, cnt, d_n);
+		if ((size_t)d.get_scal(SC_NSEL) == h.n) { // every record stays (clean data: the common case of ma_hit_cut/flt): nothing to move
+			d.free(cnt); d.free(off);
+			return h.n;
+		}
 		size_t tb = 0;
 		cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, off, (int)n_tile, d.stream);
 		void *tmp = d.tmp(tb);
@@ -456,20 +468,122 @@ k_sub_warp(const DHit *__restrict__ a, const uint64_t *__restrict__ grp, uint32_
 	if (lane == 0 && remained) atomicAdd(scal + SC_COUNT, (unsigned long long)remained);
 }
 
+// Large groups (hot spots: thousands of hits on one read).  The depth sweep only depends on HOW MANY intervals start and end at
+// every coordinate, so a read whose coordinates fit the counter array is not sorted at all: one pass counts starts / ends per
+// coordinate (16 + 16 bits in one shared-memory word; a group has <= 16 384 hits), a block scan turns the counts into depths, and the
+// up / down crossings of min_dp are read off per coordinate -- starts before ends at a coordinate, exactly the order of the sorted keys
+// (hit.c:137-149).  O(hits + coordinates) instead of the 120-stage bitonic network over 32 768 keys, which is kept for reads whose
+// coordinates reach 32 768 or beyond.
+constexpr uint32_t SUBC_COORDS = 2 * SUBC_HITS;      // counters that fit the CTA's 128 KB
+
+__device__ __forceinline__ bool sub_count_sweep(uint32_t *cnt, uint32_t n_coord, int min_dp, uint32_t clip, DSub *out)
+{	// cnt[p] = starts(p) | ends(p) << 16; all 512 threads of the CTA; returns (to every thread) whether an interval was kept
+	__shared__ int s_part[512];
+	__shared__ uint32_t s_up[512];
+	__shared__ unsigned long long s_best[512];
+	const int tid = threadIdx.x;
+	const uint32_t per = (n_coord + 511) / 512, p0 = tid * per, p1 = p0 + per < n_coord ? p0 + per : n_coord;
+	int delta = 0;
+	for (uint32_t p = p0; p < p1; ++p) { const uint32_t c = cnt[p]; delta += (int)(c & 0xffffu) - (int)(c >> 16); }
+	s_part[tid] = delta;
+	__syncthreads();
+	for (int o = 1; o < 512; o <<= 1) { // inclusive scan of the per-thread depth changes
+		const int t = tid >= o ? s_part[tid - o] : 0;
+		__syncthreads();
+		s_part[tid] += t;
+		__syncthreads();
+	}
+	const int depth0 = s_part[tid] - delta;            // depth before coordinate p0
+	uint32_t last_up = 0xffffffffu;                    // pass 1: the last coordinate of my range where the depth rises through min_dp
+	{
+		int dp = depth0;
+		for (uint32_t p = p0; p < p1; ++p) {
+			const uint32_t c = cnt[p];
+			const int mid = dp + (int)(c & 0xffffu);
+			if (dp < min_dp && mid >= min_dp) last_up = p;
+			dp = mid - (int)(c >> 16);
+		}
+	}
+	s_up[tid] = last_up;
+	__syncthreads();
+	for (int o = 1; o < 512; o <<= 1) { // "latest crossing at or before my range": positions ascend with the thread index, NONE = 0xffffffff
+		const uint32_t t = tid >= o ? s_up[tid - o] : 0xffffffffu;
+		__syncthreads();
+		if (s_up[tid] == 0xffffffffu) s_up[tid] = t;
+		__syncthreads();
+	}
+	uint32_t start = tid ? s_up[tid - 1] : 0xffffffffu; // the interval that is open when my range begins started here
+	if (start == 0xffffffffu) start = 0;               // (the reference's `start` is 0 until the first crossing)
+	unsigned long long best = 0;                       // pass 2: intervals closing in my range: longest, earliest on ties
+	{
+		int dp = depth0;
+		for (uint32_t p = p0; p < p1; ++p) {
+			const uint32_t c = cnt[p];
+			const int mid = dp + (int)(c & 0xffffu);
+			if (dp < min_dp && mid >= min_dp) start = p;
+			dp = mid - (int)(c >> 16);
+			if (mid >= min_dp && dp < min_dp) {
+				const unsigned long long cand = (unsigned long long)(p - start) << 32 | (0xffffffffu - p);
+				if ((cand >> 32) != 0 && cand > best) best = cand;
+			}
+		}
+	}
+	s_best[tid] = best;
+	__syncthreads();
+	for (int o = 256; o; o >>= 1) {
+		if (tid < o && s_best[tid + o] > s_best[tid]) s_best[tid] = s_best[tid + o];
+		__syncthreads();
+	}
+	best = s_best[0];
+	const uint32_t len = (uint32_t)(best >> 32), end = 0xffffffffu - (uint32_t)best;
+	if (tid == 0) {
+		DSub sres;
+		if (len > 0) sres.s_del = ((end - len) - clip) & 0x7fffffffu, sres.e = end + clip;
+		else sres.s_del = MAB_DEL_BIT, sres.e = 0;
+		*out = sres;
+	}
+	__syncthreads();
+	return len > 0;
+}
+
 __global__ void __launch_bounds__(512)
 k_sub_cta(const DHit *__restrict__ a, const uint64_t *__restrict__ grp, const uint32_t *__restrict__ big_list, uint32_t n_big,
           int min_dp, float min_iden, uint32_t clip, DSub *sub, uint32_t *huge_list, unsigned long long *scal)
 {
 	extern __shared__ uint32_t c_key[];
-	__shared__ uint32_t s_n;
+	__shared__ uint32_t s_n, s_max;
 	const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
 	for (uint32_t b = blockIdx.x; b < n_big; b += gridDim.x) {
 		const uint32_t r = big_list[b];
 		const uint64_t g = grp[r];
 		const uint32_t first = (uint32_t)(g >> 32), cnt = (uint32_t)g - first;
 		if (cnt > SUBC_HITS) { if (tid == 0) huge_list[atomicAdd(scal + SC_AUX2, 1ull)] = r; continue; }
-		if (tid == 0) s_n = 0;
+		if (tid == 0) s_n = 0, s_max = 0;
 		__syncthreads();
+		{ // largest coordinate any kept hit of the group touches
+			uint32_t mx = 0;
+			for (uint32_t c = tid; c < cnt; c += nt) {
+				uint32_t ks, ke;
+				if (sub_hit_keys(ld_hit(a + first + c), r, min_iden, clip, &ks, &ke)) mx = (ke >> 1) > mx ? (ke >> 1) : mx;
+			}
+			mx = __reduce_max_sync(0xffffffffu, mx);
+			if (lane == 0 && mx) atomicMax(&s_max, mx);
+		}
+		__syncthreads();
+		if (s_max < SUBC_COORDS) { // counting sweep
+			const uint32_t n_coord = s_max + 1;
+			for (uint32_t i = tid; i < n_coord; i += nt) c_key[i] = 0;
+			__syncthreads();
+			for (uint32_t c = tid; c < cnt; c += nt) {
+				uint32_t ks, ke;
+				if (sub_hit_keys(ld_hit(a + first + c), r, min_iden, clip, &ks, &ke)) { atomicAdd(&c_key[ks >> 1], 1u); atomicAdd(&c_key[ke >> 1], 1u << 16); }
+			}
+			__syncthreads();
+			const bool kept = sub_count_sweep(c_key, n_coord, min_dp, clip, sub + r);
+			if (tid == 0 && kept) atomicAdd(scal + SC_COUNT, 1ull);
+			__syncthreads();
+			continue;
+		}
 		for (uint32_t c = tid; c < cnt; c += nt) {
 			uint32_t ks, ke;
 			if (sub_hit_keys(ld_hit(a + first + c), r, min_iden, clip, &ks, &ke)) { const uint32_t p = atomicAdd(&s_n, 2u); c_key[p] = ks, c_key[p + 1] = ke; }
@@ -543,6 +657,7 @@ uint64_t dh_sub(MabDev &d, const DHits &h, int min_dp, float min_iden, int end_c
 	}
 	uint64_t n_remained = d.get_scal(SC_COUNT);
 	d.free(grp); d.free(big);
+	{ unsigned long long v[1] = { n_remained }; sum_ranks(v, 1); n_remained = v[0]; }
 	if (ma_verbose_dev >= 3)
 		fprintf(stderr, "[M::%s::%s] %ld query sequences remain after sub\n", "ma_hit_sub", sys_timestamp(), (long)n_remained);
 	return n_remained;
@@ -701,10 +816,12 @@ size_t dh_cut_flt(MabDev &d, DHits &h, const DSub *sub, int min_span, int max_ha
 		if (h.n) MAB_LAUNCH(d, k_flt_len, mab_grid(h.n, 256), 256, 0, h.a, h.n, sub, d.d_scal + SC_AUX2);
 		tot_dp = d.get_scal(SC_AUX), tot_len = d.h_scal[SC_AUX2], n_cut = d.h_scal[SC_COUNT];
 	}
-	*cov = (float)((double)tot_dp / tot_len);
+	unsigned long long gv[4] = { tot_dp, tot_len, n_cut, (unsigned long long)h.n };
+	sum_ranks(gv, 4);
+	*cov = (float)((double)gv[0] / gv[1]);
 	if (ma_verbose_dev >= 3) {
-		fprintf(stderr, "[M::%s::%s] %ld hits remain after cut\n", "ma_hit_cut", sys_timestamp(), (long)n_cut);
-		fprintf(stderr, "[M::%s::%s] %ld hits remain after filtering; crude coverage after filtering: %.2f\n", "ma_hit_flt", sys_timestamp(), (long)h.n, *cov);
+		fprintf(stderr, "[M::%s::%s] %ld hits remain after cut\n", "ma_hit_cut", sys_timestamp(), (long)gv[2]);
+		fprintf(stderr, "[M::%s::%s] %ld hits remain after filtering; crude coverage after filtering: %.2f\n", "ma_hit_flt", sys_timestamp(), (long)gv[3], *cov);
 	}
 	return h.n;
 }
@@ -717,7 +834,8 @@ size_t dh_cut(MabDev &d, DHits &h, const DSub *reg, int min_span)
 		select_hits(d, h, flag);
 		d.free(flag);
 	}
-	if (ma_verbose_dev >= 3) fprintf(stderr, "[M::%s::%s] %ld hits remain after cut\n", "ma_hit_cut", sys_timestamp(), (long)h.n);
+	{ unsigned long long v[1] = { (unsigned long long)h.n }; sum_ranks(v, 1);
+	  if (ma_verbose_dev >= 3) fprintf(stderr, "[M::%s::%s] %ld hits remain after cut\n", "ma_hit_cut", sys_timestamp(), (long)v[0]); }
 	return h.n;
 }
 
@@ -773,9 +891,11 @@ size_t dh_flt(MabDev &d, DHits &h, const DSub *sub, int max_hang, int min_ovlp, 
 		if (h.n) MAB_LAUNCH(d, k_flt_len, mab_grid(h.n, 256), 256, 0, h.a, h.n, sub, d.d_scal + SC_AUX2);
 		tot_dp = d.get_scal(SC_AUX), tot_len = d.h_scal[SC_AUX2];
 	}
-	*cov = (float)((double)tot_dp / tot_len);
+	unsigned long long gv[3] = { tot_dp, tot_len, (unsigned long long)h.n };
+	sum_ranks(gv, 3);
+	*cov = (float)((double)gv[0] / gv[1]);
 	if (ma_verbose_dev >= 3)
-		fprintf(stderr, "[M::%s::%s] %ld hits remain after filtering; crude coverage after filtering: %.2f\n", "ma_hit_flt", sys_timestamp(), (long)h.n, *cov);
+		fprintf(stderr, "[M::%s::%s] %ld hits remain after filtering; crude coverage after filtering: %.2f\n", "ma_hit_flt", sys_timestamp(), (long)gv[2], *cov);
 	return h.n;
 }
 
@@ -887,9 +1007,11 @@ size_t dh_contained(MabDev &d, DHits &h, DSub *sub, const uint8_t *seq_del, cons
 		d.free(used); d.free(keep); d.free(excl); d.free(sub2);
 	}
 	h.n_seq = n_new;
-	if (cut_reg && ma_verbose_dev >= 3) fprintf(stderr, "[M::%s::%s] %ld hits remain after cut\n", "ma_hit_cut", sys_timestamp(), (long)n_cut);
+	unsigned long long gv[2] = { (unsigned long long)n_cut, (unsigned long long)h.n };
+	sum_ranks(gv, 2);
+	if (cut_reg && ma_verbose_dev >= 3) fprintf(stderr, "[M::%s::%s] %ld hits remain after cut\n", "ma_hit_cut", sys_timestamp(), (long)gv[0]);
 	if (ma_verbose_dev >= 3)
-		fprintf(stderr, "[M::%s::%s] %d sequences and %ld hits remain after containment removal\n", "ma_hit_contained", sys_timestamp(), n_new, (long)h.n);
+		fprintf(stderr, "[M::%s::%s] %d sequences and %ld hits remain after containment removal\n", "ma_hit_contained", sys_timestamp(), n_new, (long)gv[1]);
 	return h.n;
 }
 

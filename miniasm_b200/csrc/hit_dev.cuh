@@ -5,6 +5,11 @@
 #include "asg_dev.cuh"
 #include <functional>
 
+// sharded runs: sums the per-rank counters of a log line over all ranks (installed by mab_select_sharded; null = single GPU)
+typedef void (*MabCountHook)(void *ctx, unsigned long long *v, int n);
+extern thread_local MabCountHook mab_count_hook;
+extern thread_local void *mab_count_hook_ctx;
+
 struct DHits {
 	DHit *a = nullptr, *a2 = nullptr;   // hit array + ping-pong buffer for compaction
 	size_t n = 0, m = 0;

@@ -126,15 +126,18 @@ def test_empty_inputs(prod):
     capi.c_free(s), capi.c_free(z)
 
 
-def test_sub_group_sizes(ref, prod):
+@pytest.mark.parametrize("span", [(30000, 20000), (9000, 11000), (200, 32000), (3, 40)], ids=["beyond32k", "reads10k", "edge32k", "tiny_coords"])
+def test_sub_group_sizes(span, ref, prod):
     """Groups beyond the warp kernel (256 hits), beyond the CTA kernel (16384 hits) and tiny ones, in one array:
-    the shared-memory paths and the device-wide-sort fallback of ma_hit_sub must agree with the reference."""
+    the shared-memory paths and the device-wide-sort fallback of ma_hit_sub must agree with the reference.  `span` = (range of
+    the interval starts, longest interval): below 32 768 the CTA kernel counts starts/ends per coordinate instead of sorting
+    (many intervals share a coordinate in the small spans: the order of starts and ends at one coordinate matters)."""
     rng = np.random.default_rng(9)
     rows = []
     sizes = {0: 3, 1: 40, 2: 256, 3: 257, 4: 700, 5: 5000, 6: 16384, 7: 16385, 8: 20000, 9: 1, 10: 9000, 11: 12288}
     for q, n in sizes.items():
-        qs = rng.integers(0, 30000, size=n)
-        ln = rng.integers(500, 20000, size=n)
+        qs = rng.integers(0, span[0], size=n)
+        ln = rng.integers(min(500, span[1] // 2), span[1], size=n)
         for k in range(n):
             lowid = rng.random() < 0.05
             rows.append(((q << 32) | int(qs[k]), int(qs[k] + ln[k]), int(100 + rng.integers(0, 50)) if rng.random() > 0.02 else q,
