@@ -50,6 +50,7 @@ WORKLOADS = {
     "c4_4m": dict(args=synth.CONFIGS["c4_4m"], label="Synthetic PAF: 4M reads / 200M overlaps"),
     "c5_8m_skew": dict(args=synth.CONFIGS["c5_8m_skew"], label="Synthetic PAF: 8M reads / 400M overlaps, skewed degree (hot loci of 10 000 reads)"),
     "noisy_600k": dict(args="-n 600000 -l 9000 -L 11000 -j 800 -c 30 -s 15", label="Synthetic PAF: 600K reads U[9k,11k] / 30x / ends jittered by U[0,800] (tips and bubbles)"),
+    "skew_1m": dict(args="-n 1000000 -s 5 -H 1 -R 10000 -W 8000", label="Synthetic PAF: 1M reads / 50M overlaps + one hot locus of 10 000 reads (50M more overlaps, ~10 000 hits per hot read)"),
     "tiny": dict(args="-n 20000 -s 12", label="Synthetic PAF: 20K reads / 1M overlaps (smoke)"),
 }
 BY_GPUS = {1: "c3_1m", 2: "c3_2m", 4: "c4_4m", 8: "c5_8m_skew"}
