@@ -456,6 +456,7 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 				if (m0) { nxt = base + __ffs(m0) - 1; break; }
 				if (m1) { nxt = base + 32 + __ffs(m1) - 1; break; }
 			}
+			__syncwarp();                                      // the marks just read are rewritten below (the ballots already order it; this makes it explicit for racecheck)
 			if (nxt >= nv) break;
 			i = nxt;
 			const uint32_t w = hkey[slot[i]], li = tl[i];

@@ -158,6 +158,7 @@ static void text_reserve(mab_ctx *c, size_t len)
 	c->dev.free(c->d_text);
 	c->text_cap = len + (len >> 3) + 4096;
 	c->d_text = (char*)c->dev.alloc(c->text_cap);
+	MAB_CUDA(cudaMemsetAsync(c->d_text, 0, c->text_cap, c->dev.stream)); // kernels fetch whole 16-byte words: the bytes after the text are defined
 }
 
 /* PAF bytes from host memory to the GPU (one H2D copy; `text` may be pageable or pinned) */
@@ -206,6 +207,7 @@ int mab_load_paf_file(mab_ctx_t *c, const char *fn)
 			size_t ncap = (total + got) * 2;
 			char *nt = (char*)c->dev.alloc(ncap);
 			if (total) MAB_CUDA(cudaMemcpyAsync(nt, c->d_text, total, cudaMemcpyDeviceToDevice, c->dev.stream));
+			MAB_CUDA(cudaMemsetAsync(nt + total, 0, ncap - total, c->dev.stream));
 			c->dev.free(c->d_text);
 			c->d_text = nt, c->text_cap = ncap;
 		}
