@@ -456,7 +456,9 @@ k_del_trans_warp(const DArc *__restrict__ arc, const uint64_t *__restrict__ idx,
 				if (m0) { nxt = base + __ffs(m0) - 1; break; }
 				if (m1) { nxt = base + 32 + __ffs(m1) - 1; break; }
 			}
-			__syncwarp();                                      // the marks just read are rewritten below (the ballots already order it; this makes it explicit for racecheck)
+			// (no __syncwarp here: every lane's reads of hmark feed its ballot predicate and no lane passes the ballot before all have
+			// arrived, so the marks are read before any lane rewrites them below.  racecheck reports the pattern as a warp-level WAR
+			// *warning*; with an explicit barrier it reports nothing and the kernel is 3 % slower -- profiles/r02_racecheck_*.log)
 			if (nxt >= nv) break;
 			i = nxt;
 			const uint32_t w = hkey[slot[i]], li = tl[i];
