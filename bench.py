@@ -362,14 +362,14 @@ def main():
         barrier()
         wall_dev = time.perf_counter() - t_wall0
         st = lib.mab_stats(ctx).contents
-        rounds, committed = C.c_uint32(), C.c_uint32()
-        lib.mab_last_clean(C.byref(rounds), C.byref(committed))
+        cl = [C.c_uint32() for _ in range(4)]
+        lib.mab_clean_totals(*[C.byref(x) for x in cl])
         res = {"n_lines": n_lines, "n_bytes": n_bytes, "inner": inner, "dev_ms": sum(x[0] for x in dt_ms), "kernel_ms": sum(x[1] for x in dt_ms) / len(dt_ms),
                "launches": st.n_kernel_launches - launches0, "libcalls": st.n_lib_calls - libcalls0, "wall_dev": wall_dev,
                "n_arc_in": st.n_arc_trans_in, "n_vtx": 2 * st.n_seq_final // world, "n_reduced": st.n_reduced, "n_utg": st.n_utg, "n_arc_sg": st.n_arc_sg,
                "n_hits": st.n_hits_stored, "n_hits_final": st.n_hits_final, "n_seq": st.n_seq_in,
                "phases": {"ingest": st.ms_ingest, "select": st.ms_select, "layout": st.ms_layout, "unitigs": st.ms_unitigs},
-               "last_pass_sweeps": rounds.value}
+               "cleaning": {"passes": cl[0].value, "max_sweeps_of_a_pass": cl[1].value, "sweeps": cl[2].value, "actions": cl[3].value}}
         lib.mab_event_destroy(e0), lib.mab_event_destroy(e1)
         # ---- e2e: host buffers in, GFA text out
         for _ in range(min(warmup, 2)):
@@ -419,7 +419,7 @@ def main():
                  "value": nres["n_lines"] * 3 / (nres["dev_ms"] * 1e-3), "ms_per_step": nres["dev_ms"] / 3,
                  "e2e": {"value": nres["n_lines"] * 3 / nres["e2e_s"], "ms_per_step": nres["e2e_s"] / 3 * 1e3},
                  "phase_ms_last_step": nres["phases"], "n_reduced": nres["n_reduced"], "n_utg": nres["n_utg"], "gfa_sha256": nres["gfa_sha256"],
-                 "sweeps_of_last_cleaning_pass": nres["last_pass_sweeps"]}
+                 "cleaning_passes": nres["cleaning"]}
 
     if rank == 0:
         peaks = {}
@@ -518,7 +518,7 @@ def main():
             "gpu_launches": res["launches"], "lib_calls": res["libcalls"],
             "arcs_per_sec_del_trans": n_arc_in / (kms * 1e-3) if kms else None,
             "del_trans": {"n_arc_in": n_arc_in, "inner_iters": inner, "n_vtx": n_vtx, "kernel_ms": kms},
-            "phase_ms_last_step": res["phases"],
+            "phase_ms_last_step": res["phases"], "cleaning_passes": res["cleaning"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "frac_kind": "algorithmic bytes / kernel time / measured copy peak", "traffic": traffic,
                          "dram_gbs": traffic / (kms * 1e-3) / 1e9 if traffic and kms else None,

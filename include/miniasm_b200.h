@@ -216,6 +216,7 @@ void mab_event_destroy(void *ev);
 void mab_sync(mab_ctx_t *ctx);
 void mab_last_del_trans(uint64_t *n_arc_in, uint64_t *inner, uint64_t *n_reduced, uint64_t *n_big, double *kernel_ms);
 void mab_last_clean(uint32_t *rounds, uint32_t *committed);
+void mab_clean_totals(uint32_t *passes, uint32_t *max_sweeps, uint32_t *sweeps, uint32_t *actions); /* tip/bubble/internal/bi-loop passes of the last mab_layout */
 void mab_count_del_trans_inner(int on);                /* 1: asg_arc_del_trans also counts inner-loop iterations (mab_stats_t::trans_inner); costs time */
 
 #ifdef __cplusplus

@@ -160,6 +160,7 @@ _PRODUCT_ONLY = {
     "mab_event_destroy": (None, [C.c_void_p]),
     "mab_sync": (None, [C.c_void_p]),
     "mab_last_clean": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "mab_clean_totals": (None, [C.POINTER(C.c_uint32)] * 4),
     "mab_count_del_trans_inner": (None, [C.c_int]),
     "mab_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mab_shard_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),

@@ -66,4 +66,13 @@ void mab_last_clean(uint32_t *rounds, uint32_t *committed)
 	if (committed) *committed = g_clean_stats.committed;
 }
 
+/* all order-dependent passes since the last reset (mab_layout resets): passes run, most sweeps any pass needed, sweeps and actions in total */
+void mab_clean_totals(uint32_t *passes, uint32_t *max_sweeps, uint32_t *sweeps, uint32_t *actions)
+{
+	if (passes) *passes = g_clean_stats.passes;
+	if (max_sweeps) *max_sweeps = g_clean_stats.max_rounds;
+	if (sweeps) *sweeps = g_clean_stats.sum_rounds;
+	if (actions) *actions = g_clean_stats.sum_committed;
+}
+
 }

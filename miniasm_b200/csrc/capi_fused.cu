@@ -422,6 +422,7 @@ static void layout_tail(mab_ctx *c, const ma_opt_t *opt, int stage)
 {
 	MabDev &d = c->dev;
 	DGraph &g = c->sg;
+	g_clean_stats = CleanStats();                          // mab_clean_totals counts the passes of this layout
 	if (stage >= 7) {
 		if (!mab_mute && ma_verbose >= 1) fprintf(stderr, "[M::main] ===> Step 4.2: initial tip cutting and bubble popping <===\n");
 		dg_cut_tip(d, g, opt->max_ext);

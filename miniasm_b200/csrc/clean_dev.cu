@@ -10,6 +10,13 @@
 #include <cub/cub.cuh>
 
 thread_local CleanStats g_clean_stats;
+static inline void clean_note(uint32_t rounds, uint32_t committed)
+{
+	CleanStats &c = g_clean_stats;
+	c.rounds = rounds, c.committed = committed;
+	++c.passes, c.sum_rounds += rounds, c.sum_committed += committed;
+	if (rounds > c.max_rounds) c.max_rounds = rounds;
+}
 
 struct GV { // device view of the graph (unitig construction)
 	DArc *arc;
@@ -96,13 +103,11 @@ static void fx_finish(MabDev &d, DGraph &g, FxBuf &b)
 template <class Rule>
 static uint32_t run_fixpoint(MabDev &d, DGraph &g, Rule rule)
 {
-	g_clean_stats.rounds = 0, g_clean_stats.committed = 0;
-	if (g.n_seq == 0) return 0;                        // (a graph WITHOUT arcs still has work: every live read is a tip, asg.c:243-249)
+	if (g.n_seq == 0) { clean_note(0, 0); return 0; }                        // (a graph WITHOUT arcs still has work: every live read is a tip, asg.c:243-249)
 	// probe: the first sweep straight on the deletion bits, stamping nothing.  Nobody acts -> the pass is over.
 	d.zero_scal(SC_COUNT);
 	MAB_LAUNCH(d, (k_fx_sweep<FxProbe, Rule>), mab_grid((size_t)g.n_seq * 2, 128), 128, 0, FxProbe{g.arc, g.idx, g.seq, g.n_seq * 2}, rule, d.d_scal + SC_COUNT);
-	g_clean_stats.rounds = 1;
-	if (d.get_scal(SC_COUNT) == 0) return 0;
+	if (d.get_scal(SC_COUNT) == 0) { clean_note(1, 0); return 0; }
 	FxBuf b;
 	fx_alloc(d, g, b);
 	uint32_t sweeps = 0, cnt;
@@ -115,7 +120,7 @@ static uint32_t run_fixpoint(MabDev &d, DGraph &g, Rule rule)
 		if (fixed) break;       // the sweep ran on the fixed point itself: its count is the reference's
 	}
 	fx_finish(d, g, b);
-	g_clean_stats.rounds = sweeps + 1, g_clean_stats.committed = cnt;
+	clean_note(sweeps + 1, cnt);
 	return cnt;
 }
 
@@ -248,7 +253,7 @@ uint64_t dg_pop_bubble(MabDev &d, DGraph &g, int max_dist)
 		}
 		d.free(src);
 	}
-	g_clean_stats.rounds = sweeps, g_clean_stats.committed = (uint32_t)n_pop;
+	clean_note(sweeps, (uint32_t)n_pop);
 	if (n_pop) dg_cleanup(d, g);
 	if (MAB_V(1)) fprintf(stderr, "[M::%s] popped %d bubbles and trimmed %d tips\n", "asg_pop_bubble", (uint32_t)n_pop, (uint32_t)n_tip);
 	return (n_pop & 0xffffffffull) | n_tip << 32;

@@ -9,7 +9,8 @@ uint32_t dg_cut_biloop(MabDev &d, DGraph &g, int max_ext);     // asg.c:274-306
 uint64_t dg_pop_bubble(MabDev &d, DGraph &g, int max_dist);    // asg.c:312-433 (pops | trimmed tips << 32)
 
 // statistics of the speculative rounds (DESIGN.md "sequential passes"): rounds and candidates of the last call
-struct CleanStats { uint32_t rounds, committed; };
+struct CleanStats { uint32_t rounds, committed;   // sweeps / actions of the last pass
+                    uint32_t passes, max_rounds, sum_rounds, sum_committed; }; // accumulated since mab_clean_totals_reset (one layout)
 extern thread_local CleanStats g_clean_stats;
 
 // Unitigs (asm.c:121-210).  Device result, flattened:
