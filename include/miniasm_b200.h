@@ -186,7 +186,7 @@ ma_ug_t *mab_export_ug(mab_ctx_t *ctx);
 float mab_coverage(const mab_ctx_t *ctx);
 /* The bytes of ma_ug_print(mab_export_ug(), mab_export_dict(), mab_export_sub(), fp) (asm.c:77-116) for a layout without
  * unitig sequences, formatted on the GPU and written with one fwrite: no host copies of the tables.  Returns the number
- * of bytes written, -1 before mab_unitigs.  (Experimental in round 1: the CLI uses it only with MAB_GPU_GFA=1.) */
+ * of bytes written, -1 before mab_unitigs.  (The CLI's default writer; MAB_GPU_GFA=0 selects the host route.) */
 long mab_write_gfa(mab_ctx_t *ctx, FILE *fp);
 /* -f reads: ma_ug_seq (asm.c:236-290) + ma_ug_print on the GPU.  mab_reads_prefetch starts streaming the FASTA/FASTQ file (plain
  * or gzip, "-" = stdin) into HBM on a thread and stream of its own -- call it before mab_ingest and the copy hides behind the

@@ -11,11 +11,9 @@
 //   for each unitig i: S line (+ the two circularising L lines), then its `a` lines   -> records [0, n_utg + n_items)
 //   L lines of the unitig graph                                                        -> next n_arc records
 //   x lines                                                                            -> last n_utg records
-// Integer formats are the reference's: "%d" of the 32-bit value, "utg%.6d" zero-padded.  Unitig sequences (-f reads)
-// are not handled here: the S line carries "*" (callers with sequences use the host writer).
-//
-// Status: experimental (MAB_GPU_GFA=1 in the CLI / bench.py --gpu-gfa); the host writer stays the default until this
-// file has been through the GPU test tier (tests/test_switches_gpu.py, MAB_TEST_EXPERIMENTAL=1).
+// Integer formats are the reference's: "%d" of the 32-bit value, "utg%.6d" zero-padded.  Without unitig sequences the S line
+// carries "*"; with them (-f reads) it reserves `len` bytes, pre-filled with 'N', that ugseq_dev.cu fills in place.
+// This is the default writer of the CLI and of bench.py (MAB_GPU_GFA=0 / --host-gfa: host structs + ma_ug_print).
 #include "gfa_dev.cuh"
 #include <cub/cub.cuh>
 

@@ -1056,7 +1056,7 @@ __global__ void k_sg_arcs(const DHit *a, size_t n, uint32_t *seq, HitArcParams p
 }
 
 // ---------------------------------------------------------------------------------------------
-// ma_sg_gen without a device-wide sort (experimental, MAB_SG_SEGSORT=1; the default is the column sort above).
+// ma_sg_gen without a device-wide sort (the default; MAB_SG_SEGSORT=0 or a case it declines -> the column sort above).
 // Hits arrive grouped by query read, and an arc's source vertex is its hit's query, so asg.c's "append, then sort by
 // ul" only has to order each read's arcs by (direction, length), hit order on ties -- a per-read problem of ~100
 // elements.  Pass 1 classifies every hit (flag byte, group bounds, the deletion side effects of asm.c:27-33) and

@@ -11,12 +11,12 @@
 //   * every stored line yields a hit and, when bi_dir and query != target, the mirrored hit right after it;
 //   * hits sorted by (query id, query start).
 //
-// GPU shape: (1) line starts by a flagged select over the bytes, (2) one thread per line parses and hashes the
-// two names, (3) names go through an open-addressing table keyed by a 64-bit hash, value = smallest
-// occurrence number (atomicMin), every occurrence is then verified byte-for-byte against the table's
-// representative (a true hash collision triggers a re-run with another seed: ids are exact, never
-// probabilistic), (4) distinct names ranked by first occurrence = ids, (5) hits emitted at scanned offsets,
-// (6) radix sort (hit_dev.cu).
+// GPU shape: (1) line starts (newline count per tile, scan, positions), (2) one thread per line parses it, applies the store
+// filter and enters both names into an exact open-addressing dictionary (slot word = hash fragment + byte offset of a witness
+// occurrence: an occurrence with the same fragment compares its bytes with the witness's; value = smallest occurrence number,
+// atomicMin) -- all in ONE pass that leaves a 32-byte record per line, (3) distinct names ranked by first occurrence = ids,
+// (4) hits emitted at scanned offsets, (5) radix sort (hit_dev.cu).  ingest_paf_stream runs (1)-(2) chunk by chunk while the next
+// chunks of the text are still crossing PCIe.
 #include "ingest_dev.cuh"
 #include "shard_comm.cuh"
 #include <cub/cub.cuh>
@@ -147,11 +147,6 @@ __global__ void k_nl_advance(unsigned long long *nl_state, const uint64_t *base,
 	rng[1] = hi;
 	rng[2] = last ? known_starts : ~0ull;
 }
-
-struct IsLineStart {
-	const char *text;
-	__device__ __forceinline__ bool operator()(uint64_t p) const { return p == 0 || text[p - 1] == '\n'; }
-};
 
 // strtol(field, 0, 10) narrowed to uint32, on the byte range [p, e).  Up to 18 significant digits cannot
 // overflow a long, so the common path is one multiply-add per digit; only longer digit strings take the clamping
@@ -1003,22 +998,6 @@ __global__ void __launch_bounds__(PUSH_LINES) k_push_emit(const PRec *ln, uint64
 	__threadfence_system();                            // the stores to peer memory are out before the grid reports completion
 	mx = __reduce_max_sync(0xffffffffu, mx);
 	if (lane == 0 && mx) atomicMax(max_qs, mx);
-}
-
-// bucket sizes from the SORTED destination keys: bucket g = [lower_bound(g), lower_bound(g+1)); one thread per rank
-// (a per-element atomicAdd on `world` counters serialised 100 M atomics on two addresses: 85 ms at N=2)
-__global__ void k_dest_bounds(const uint32_t *sorted_dest, uint64_t n, uint32_t world, unsigned long long *cnt)
-{
-	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-	if (g >= world) return;
-	uint64_t lo[2];
-	for (int k = 0; k < 2; ++k) {
-		uint64_t a = 0, b = n;
-		const uint32_t key = g + k;
-		while (a < b) { const uint64_t m = (a + b) >> 1; if (sorted_dest[m] < key) a = m + 1; else b = m; }
-		lo[k] = a;
-	}
-	cnt[g] = lo[1] - lo[0];
 }
 
 __global__ void k_gather_hits(const DHit *a, const uint32_t *pos, uint64_t n, DHit *out)
