@@ -64,3 +64,30 @@ def test_tie_order_audit(ref, port, paf_dir):
     for name in ("jitter30", "chaos"):
         paf = synth.generate(name, f"{paf_dir}/{name}.paf")
         assert Pipeline(ref, paf).run_all() == Pipeline(port, paf).run_all()
+
+
+def _reduce_tied(lib, w2_first):
+    from tests.tied_graph import FUZZ, tied_graph
+    arcs, seq, idx = tied_graph(w2_first)
+    g = lib.make_graph(arcs, seq, is_srt=True)
+    g.contents.idx = capi.c_malloc_copy(idx)
+    n = lib.asg_arc_del_trans(g, FUZZ)
+    out = lib.read_graph(g)
+    lib.asg_destroy(g)
+    return n, out
+
+
+def test_tied_arcs_decide_the_counter_not_the_graph(ref, port):
+    """two arcs tied on (source, length) whose targets overlap each other.  Which one the reference explores first
+    changes how many arcs asg_arc_del_trans itself reduces (asg.c:164-171); asg_symm inside the call (asg.c:188-191) takes the
+    one-sided survivor, so the graph that comes out is the same.  The port follows the reference for either slab order."""
+    res = {}
+    for w2_first in (False, True):
+        nr, gr = _reduce_tied(ref, w2_first)
+        n_p, gp = _reduce_tied(port, w2_first)
+        assert nr == n_p
+        assert np.array_equal(gr[0], gp[0]) and np.array_equal(gr[1], gp[1]) and np.array_equal(gr[2], gp[2]) and gr[3:] == gp[3:]
+        res[w2_first] = (nr, gr)
+    assert res[True][0] == res[False][0] + 1                     # v -> x is reduced by the pass itself only when w2 comes first
+    assert np.array_equal(canon_arcs(res[True][1][0]), canon_arcs(res[False][1][0]))
+    assert len(res[True][1][0]) == 6                             # v -> w1 -> w2 -> x and the complement chain remain
