@@ -322,3 +322,22 @@ def test_degenerate_inputs(content, paf_dir):
     same([path])
     same(["-S", "2", "-p", "paf", path], exact=False)
     same(["-p", "sg", path], exact=False)
+
+
+def test_long_read_names(built, paf_dir, tmp_path):
+    """Read names beyond 65535 bytes (the round-1 parser kept 16-bit name lengths and gave up; the reference takes
+    any length, paf.c / kseq getuntil).  Two of the names differ only in their last byte, which the dictionary's witness comparison
+    has to reach."""
+    src = synth.generate("tiny_exact", f"{paf_dir}/tiny_exact.paf")
+    long_a, long_b = "L" * 70000 + "a", "L" * 70000 + "b"
+    ren = {"r206": long_a, "r27": long_b, "r172": "M" * 66000}
+    dst = str(tmp_path / "long.paf")
+    with open(src) as f, open(dst, "w") as g:
+        for line in f:
+            c = line.split("\t")
+            c[0], c[5] = ren.get(c[0], c[0]), ren.get(c[5], c[5])
+            g.write("\t".join(c))
+    same([dst])
+    bed = same(["-S", "2", "-p", "bed", dst])
+    assert long_a.encode() + b"\t" in bed and long_b.encode() + b"\t" in bed and b"M" * 66000 + b"\t" in bed
+    same(["-R", dst])
