@@ -43,3 +43,40 @@ __host__ __device__ __forceinline__ int mab_hit2arc(const DHit &h, int ql, int t
 	arc->ol_del = ((uint32_t)ql - l) & 0x7fffffffu;
 	return (int)l;
 }
+
+// ---------------------------------------------------------------------------------------------
+// ma_hit_cut (hit.c:162-193).  The reference computes in `int` locals from uint32 operands and compares
+// against a 31-bit field (signed after promotion) or a uint32 field (unsigned); restated with explicit types.
+// ---------------------------------------------------------------------------------------------
+// clips hit p to the kept intervals rq (query read) / rt (target read); true if both spans stay >= min_span
+__host__ __device__ __forceinline__ bool mab_cut_hit(DHit &p, const DSub rq, const DSub rt, int min_span)
+{
+	{
+		if ((rq.s_del | rt.s_del) & MAB_DEL_BIT) return false;
+		const uint32_t rqs = rq.s_del, rts = rt.s_del, rqe = rq.e, rte = rt.e; // del bits are clear here
+		const uint32_t pqs = (uint32_t)p.qns;
+		uint32_t uqs, uqe, uts, ute;
+		if (p.ml_rev >> 31) {
+			uqs = p.te < rte ? pqs : pqs + (p.te - rte);
+			uqe = p.ts > rts ? p.qe : p.qe - (rts - p.ts);
+			uts = p.qe < rqe ? p.ts : p.ts + (p.qe - rqe);
+			ute = pqs > rqs ? p.te : p.te - (rqs - pqs);
+		} else {
+			uqs = p.ts > rts ? pqs : pqs + (rts - p.ts);
+			uqe = p.te < rte ? p.qe : p.qe - (p.te - rte);
+			uts = pqs > rqs ? p.ts : p.ts + (rqs - pqs);
+			ute = p.qe < rqe ? p.te : p.te - (p.qe - rqe);
+		}
+		int qs = (int)uqs, qe = (int)uqe, ts = (int)uts, te = (int)ute;
+		qs = (qs > (int)rqs ? qs : (int)rqs) - (int)rqs;                      // signed compare (31-bit field promotes to int)
+		qe = (int)(((uint32_t)qe < rqe ? (uint32_t)qe : rqe) - rqs);          // unsigned compare (uint32 field)
+		ts = (ts > (int)rts ? ts : (int)rts) - (int)rts;
+		te = (int)(((uint32_t)te < rte ? (uint32_t)te : rte) - rts);
+		bool keep = qe - qs >= min_span && te - ts >= min_span;
+		if (keep) {
+			p.qns = (p.qns >> 32 << 32) | (uint64_t)(int64_t)qs;
+			p.qe = (uint32_t)qe, p.ts = (uint32_t)ts, p.te = (uint32_t)te;
+		}
+		return keep;
+	}
+}

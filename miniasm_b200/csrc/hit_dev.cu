@@ -686,48 +686,13 @@ static uint64_t dh_sub_global(MabDev &d, const DHits &h, int min_dp, float min_i
 	return n_remained;
 }
 
-// ---------------------------------------------------------------------------------------------
-// ma_hit_cut (hit.c:162-193).  The reference computes in `int` locals from uint32 operands and compares
-// against a 31-bit field (signed after promotion) or a uint32 field (unsigned); restated with explicit types.
-// ---------------------------------------------------------------------------------------------
-// clips hit p to the kept intervals rq (query read) / rt (target read); true if both spans stay >= min_span
-__device__ __forceinline__ bool cut_hit(DHit &p, const DSub rq, const DSub rt, int min_span)
-{
-	{
-		if ((rq.s_del | rt.s_del) & MAB_DEL_BIT) return false;
-		const uint32_t rqs = rq.s_del, rts = rt.s_del, rqe = rq.e, rte = rt.e; // del bits are clear here
-		const uint32_t pqs = (uint32_t)p.qns;
-		uint32_t uqs, uqe, uts, ute;
-		if (p.ml_rev >> 31) {
-			uqs = p.te < rte ? pqs : pqs + (p.te - rte);
-			uqe = p.ts > rts ? p.qe : p.qe - (rts - p.ts);
-			uts = p.qe < rqe ? p.ts : p.ts + (p.qe - rqe);
-			ute = pqs > rqs ? p.te : p.te - (rqs - pqs);
-		} else {
-			uqs = p.ts > rts ? pqs : pqs + (rts - p.ts);
-			uqe = p.te < rte ? p.qe : p.qe - (p.te - rte);
-			uts = pqs > rqs ? p.ts : p.ts + (rqs - pqs);
-			ute = p.qe < rqe ? p.te : p.te - (p.qe - rqe);
-		}
-		int qs = (int)uqs, qe = (int)uqe, ts = (int)uts, te = (int)ute;
-		qs = (qs > (int)rqs ? qs : (int)rqs) - (int)rqs;                      // signed compare (31-bit field promotes to int)
-		qe = (int)(((uint32_t)qe < rqe ? (uint32_t)qe : rqe) - rqs);          // unsigned compare (uint32 field)
-		ts = (ts > (int)rts ? ts : (int)rts) - (int)rts;
-		te = (int)(((uint32_t)te < rte ? (uint32_t)te : rte) - rts);
-		bool keep = qe - qs >= min_span && te - ts >= min_span;
-		if (keep) {
-			p.qns = (p.qns >> 32 << 32) | (uint64_t)(int64_t)qs;
-			p.qe = (uint32_t)qe, p.ts = (uint32_t)ts, p.te = (uint32_t)te;
-		}
-		return keep;
-	}
-}
-
+// ma_hit_cut (hit.c:162-193): the clipping rule itself is mab_cut_hit in hit2arc.cuh (shared with the CPU-tier check of the
+// conversion rules, tests/hostsim/hit_host.cpp)
 __global__ void k_cut(DHit *a, size_t n, const DSub *__restrict__ reg, int min_span, uint8_t *flag)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
 		DHit p = ld_hit_rw(a + i);
-		const bool keep = cut_hit(p, reg[p.qns >> 32], reg[p.tn], min_span);
+		const bool keep = mab_cut_hit(p, reg[p.qns >> 32], reg[p.tn], min_span);
 		if (keep) st_hit(a + i, p);
 		flag[i] = keep;
 	}
@@ -742,7 +707,7 @@ __global__ void k_cut_flt(DHit *a, size_t n, const DSub *__restrict__ sub, int m
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
 		DHit p = ld_hit_rw(a + i);
 		const DSub sq = sub[p.qns >> 32], st = sub[p.tn];
-		bool keep = cut_hit(p, sq, st, min_span);
+		bool keep = mab_cut_hit(p, sq, st, min_span);
 		if (keep) {
 			++cut;
 			DArc t;
@@ -771,7 +736,7 @@ __global__ void k_cut_cont_mark(DHit *a, size_t n, const DSub *__restrict__ sub2
 		DHit p = ld_hit_rw(a + i);
 		const uint32_t q = (uint32_t)(p.qns >> 32), t = p.tn;
 		const DSub rq = sub2[q], rt = sub2[t];
-		const bool keep = cut_hit(p, rq, rt, min_span);
+		const bool keep = mab_cut_hit(p, rq, rt, min_span);
 		if (keep) {
 			++cut;
 			st_hit(a + i, p);
