@@ -1,5 +1,7 @@
-"""CPU tier, world_size 2 over gloo: the launcher-side logic of the sharded run (byte-range split at line ends,
-ownership, hand-over of the communicator id) and the rank aggregation bench.py uses."""
+"""CPU tier, world_size 2 (and 3) over gloo: the launcher-side logic of the sharded run (byte-range split at line ends,
+ownership, hand-over of the communicator id), the rank aggregation bench.py uses, and a model of the sharding scheme itself
+(global ids from per-rank dictionaries, hits to the owner of the query read, interval tables completed by all-reduce) with the
+unmodified reference as every rank's compute, checked against a single-rank run."""
 import os
 import socket
 
@@ -70,3 +72,118 @@ def test_split_ranges_edge_cases(world):
         assert all(e == len(data) or e == b or data[e - 1:e] == b"\n" for b, e in rs)
         assert b"".join(data[b:e] for b, e in rs) == data
     assert [sharded.owner(i, 4) for i in range(6)] == [0, 1, 2, 3, 0, 1]
+
+
+# ---- the sharding scheme itself, modelled with the reference as every rank's compute -------------------------------------------------
+def _model_worker(rank, world, port, paf, q):
+    """DESIGN.md section 8 steps 1-2 as a model: every rank parses its byte range with the UNMODIFIED reference (local ids), the ranks
+    agree on global ids (first appearance in rank order = file order), hits travel to the owner of their query read (id mod world)
+    keeping per-source order, the owner runs the reference's ma_hit_sub on what it received, the interval table is completed by an
+    all-reduce(sum), ma_hit_cut + ma_hit_flt run owner-local against the full table.  Every rank checks its share against a
+    single-rank run of the reference on the whole file."""
+    import ctypes as C
+    import tempfile
+
+    import numpy as np
+
+    from miniasm_b200 import capi
+    from miniasm_b200.capi import HIT_DT, SUB_DT
+    from miniasm_b200.pipeline import Pipeline
+    from oracle import loaders
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ref = loaders.load_reference()
+    ref.set_verbose(0)
+    data = open(paf, "rb").read()
+    b, e = sharded.split_ranges(data, world)[rank]
+    with tempfile.NamedTemporaryFile(suffix=".paf", delete=False) as tf:
+        tf.write(data[b:e])
+    mine = Pipeline(ref, tf.name).read()                     # local dictionary: ids = first appearance among MY stored lines
+    os.unlink(tf.name)
+    truth = Pipeline(ref, paf).read()                        # what one rank would have
+    o = truth.opt
+
+    # 1. global ids: walk the ranks in file order, a name keeps the id of its first appearance
+    names = [None] * world
+    dist.all_gather_object(names, mine.names())
+    gid = {}
+    for r in range(world):
+        for nm in names[r]:
+            gid.setdefault(nm, len(gid))
+    ok = [nm for nm, _ in sorted(gid.items(), key=lambda kv: kv[1])] == truth.names()
+    n_seq = len(gid)
+    l2g = np.array([gid[nm] for nm in mine.names()], dtype=np.uint64)
+
+    # 2. hits to the owner of the query read, per-source order kept; owner: concatenate in rank order, stable sort by (id, start)
+    h = mine.hits_np()
+    if len(h):
+        h["qns"] = (l2g[(h["qns"] >> np.uint64(32)).astype(np.int64)] << np.uint64(32)) | (h["qns"] & np.uint64(0xffffffff))
+        h["tn"] = l2g[h["tn"].astype(np.int64)].astype(np.uint32)
+    dest = ((h["qns"] >> np.uint64(32)) % np.uint64(world)).astype(np.int64)
+    box = [None] * world
+    dist.all_gather_object(box, [h[dest == r].tobytes() for r in range(world)])
+    got = np.concatenate([np.frombuffer(box[src][rank], dtype=HIT_DT) for src in range(world)])
+    got = got[np.argsort(got["qns"], kind="stable")].copy()
+    th = truth.hits_np()
+    owned = ((th["qns"] >> np.uint64(32)) % np.uint64(world)).astype(np.int64) == rank
+    key = ["qns", "qe", "tn", "ts", "te", "ml_rev"]        # (bl_del carries the del bit the reference never initialises)
+
+    def same_hits(a, b):
+        a, b = a.copy(), b.copy()
+        a["bl_del"] &= 0x7fffffff
+        b["bl_del"] &= 0x7fffffff
+        return len(a) == len(b) and np.array_equal(np.sort(a, order=key + ["bl_del"]), np.sort(b, order=key + ["bl_del"]))
+    ok = ok and same_hits(got, th[owned]) and np.array_equal(got["qns"], th[owned]["qns"])
+
+    # 3. ma_hit_sub on the owner, all-reduce(sum) completes the table; cut + flt owner-local against the full table
+    def sub_of(hits, clip):
+        p = ref.ma_hit_sub(o.min_dp, o.min_iden, clip, len(hits), hits.ctypes.data_as(C.c_void_p), n_seq)
+        t = capi.np_from_ptr(p, n_seq, SUB_DT)
+        capi.c_free(p)
+        rows = np.zeros(n_seq, dtype=bool)                     # rows of reads I do not own stay zero (calloc)
+        rows[np.arange(n_seq) % world == rank] = True
+        assert not t["s_del"][~rows].any() and not t["e"][~rows].any()
+        w = torch.from_numpy(t.view(np.uint32).astype(np.int64))
+        dist.all_reduce(w)
+        return w.numpy().astype(np.uint32).view(SUB_DT).reshape(-1)
+    sub = sub_of(got, 0)
+    truth.sub1()
+    ok = ok and np.array_equal(sub, truth.sub_np())
+    n = ref.ma_hit_cut(sub.ctypes.data_as(C.c_void_p), o.min_span, len(got), got.ctypes.data_as(C.c_void_p))
+    cov = C.c_float(0)
+    n = ref.ma_hit_flt(sub.ctypes.data_as(C.c_void_p), int(o.max_hang * 1.5), int(o.min_ovlp * .5), n, got.ctypes.data_as(C.c_void_p), C.byref(cov))
+    truth.cut().flt()
+    th = truth.hits_np()
+    owned = ((th["qns"] >> np.uint64(32)) % np.uint64(world)).astype(np.int64) == rank
+    ok = ok and same_hits(got[:n], th[owned])
+    tot = torch.tensor([n], dtype=torch.int64)
+    dist.all_reduce(tot)
+    ok = ok and tot.item() == truth.n_hits and n > 0
+    # second round: same exchange with the clip of main.c:131
+    sub2 = sub_of(got[:n].copy(), o.min_span // 2)
+    p2 = ref.ma_hit_sub(o.min_dp, o.min_iden, o.min_span // 2, truth.n_hits, truth.hits, n_seq)
+    ok = ok and np.array_equal(sub2, capi.np_from_ptr(p2, n_seq, SUB_DT))
+    capi.c_free(p2)
+    q.put((rank, bool(ok), int(n), int(n_seq)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharding_scheme_model(world, built, paf_dir):
+    from oracle import loaders
+    if not os.path.exists(loaders.REFERENCE_SO):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    paf = synth.generate("-n 3000 -s 78 -j 300 -l 8000 -L 12000", f"{paf_dir}/dist_model.paf")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_model_worker, args=(r, world, port, paf, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in ps)
+    for p in ps:
+        p.join(60)
+    assert [r for r, _, _, _ in res] == list(range(world))
+    assert all(ok for _, ok, _, _ in res), res
+    assert all(n > 0 for _, _, n, _ in res)
