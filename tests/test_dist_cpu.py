@@ -75,7 +75,7 @@ def test_split_ranges_edge_cases(world):
 
 
 # ---- the sharding scheme itself, modelled with the reference as every rank's compute -------------------------------------------------
-def _model_worker(rank, world, port, paf, q):
+def _model_body(rank, world, port, paf, q):
     """DESIGN.md section 8 steps 1-2 as a model: every rank parses its byte range with the UNMODIFIED reference (local ids), the ranks
     agree on global ids (first appearance in rank order = file order), hits travel to the owner of their query read (id mod world)
     keeping per-source order, the owner runs the reference's ma_hit_sub on what it received, the interval table is completed by an
@@ -164,9 +164,94 @@ def _model_worker(rank, world, port, paf, q):
     p2 = ref.ma_hit_sub(o.min_dp, o.min_iden, o.min_span // 2, truth.n_hits, truth.hits, n_seq)
     ok = ok and np.array_equal(sub2, capi.np_from_ptr(p2, n_seq, SUB_DT))
     capi.c_free(p2)
-    q.put((rank, bool(ok), int(n), int(n_seq)))
+
+    # 4. round-2 cut owner-local, merged table replicated (main.c:131-134)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = ref.ma_hit_cut(vp(sub2), o.min_span, n, vp(got))
+    merged = sub.copy()
+    ref.ma_sub_merge(n_seq, vp(merged), vp(sub2))
+    truth.cut(truth_sub2 := vp(sub2))
+    ref.ma_sub_merge(n_seq, truth.sub, truth_sub2)
+    th = truth.hits_np()
+    owned = ((th["qns"] >> np.uint64(32)) % np.uint64(world)).astype(np.int64) == rank
+    ok = ok and np.array_equal(merged, truth.sub_np()) and same_hits(got[:n], th[owned])
+
+    # 5. ma_hit_contained (hit.c:225-256): containment flags of the owner's hits OR-ed over the ranks (all-reduce max), "used" marks
+    #    likewise, renumbering replicated.  The local flags come from the reference itself: it runs on the owner's hits plus one
+    #    inert self hit per read (classified "internal", so every read counts as used and only flagged reads leave the dictionary).
+    gl_names = [nm for nm, _ in sorted(gid.items(), key=lambda kv: kv[1])]
+    lens_box = [None] * world
+    dist.all_gather_object(lens_box, dict(zip(mine.names(), mine.seq_lens().tolist())))
+    gl_len = [next(lens_box[r][nm] for r in range(world) if nm in lens_box[r]) for nm in gl_names]   # sdict.c:36: first appearance
+    ln = (merged["e"] - (merged["s_del"] & np.uint32(0x7fffffff))).astype(np.int64)
+    inert = np.zeros(n_seq, dtype=HIT_DT)
+    x = np.where(ln >= 2, 1, 0).astype(np.uint64)
+    inert["qns"] = (np.arange(n_seq, dtype=np.uint64) << np.uint64(32)) | x
+    inert["qe"] = inert["te"] = np.where(ln >= 2, 2, 0)
+    inert["ts"], inert["tn"], inert["bl_del"] = x.astype(np.uint32), np.arange(n_seq, dtype=np.uint32), 1
+    aug = np.concatenate([got[:n], inert])
+    dloc = ref.sd_init()
+    for nm, l in zip(gl_names, gl_len):
+        ref.sd_put(dloc, nm, l)
+    sub_copy = merged.copy()
+    ref.ma_hit_contained(C.byref(o), dloc, vp(sub_copy), len(aug), vp(aug))
+    left = {dloc.contents.seq[i].name for i in range(dloc.contents.n_seq)}
+    ref.sd_destroy(dloc)
+    flag = torch.tensor([nm not in left for nm in gl_names], dtype=torch.int32)
+    used = torch.zeros(n_seq, dtype=torch.int32)
+    used[torch.from_numpy((got[:n]["qns"] >> np.uint64(32)).astype(np.int64))] = 1
+    used[torch.from_numpy(got[:n]["tn"].astype(np.int64))] = 1
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    dist.all_reduce(used, op=dist.ReduceOp.MAX)
+    flag, used = flag.numpy().astype(bool), used.numpy().astype(bool)
+    ok = ok and not (used & (ln < 2)).any()                    # the inert hit of an empty interval may flag it: such reads are unused anyway
+    dead = flag | ~used
+    new_id = np.cumsum(~dead) - 1
+    old_of_new = np.flatnonzero(~dead)
+    loc = got[:n]
+    lq, lt = (loc["qns"] >> np.uint64(32)).astype(np.int64), loc["tn"].astype(np.int64)
+    loc = loc[~dead[lq] & ~dead[lt]].copy()
+    loc["qns"] = (new_id[(loc["qns"] >> np.uint64(32)).astype(np.int64)].astype(np.uint64) << np.uint64(32)) | (loc["qns"] & np.uint64(0xffffffff))
+    loc["tn"] = new_id[loc["tn"].astype(np.int64)].astype(np.uint32)
+    sub_new = merged[~dead].copy()
+    truth.contained()
+    th = truth.hits_np()
+    owned = old_of_new[(th["qns"] >> np.uint64(32)).astype(np.int64)] % world == rank     # ownership stays with the ORIGINAL id
+    ok = ok and [gl_names[i] for i in old_of_new] == truth.names() and np.array_equal(sub_new, truth.sub_np()) and same_hits(loc, th[owned])
+
+    # 6. ma_sg_gen (asm.c:9-39) on the owner; read flags OR-ed, arcs all-gathered and stably sorted by their key = the single-rank graph
+    dnew = ref.sd_init()
+    for i in old_of_new:
+        ref.sd_put(dnew, gl_names[i], gl_len[i])
+    g = ref.ma_sg_gen(C.byref(o), dnew, vp(sub_new), len(loc), vp(loc))
+    arcs, seq, _, _, _ = ref.read_graph(g)
+    ref.asg_destroy(g), ref.sd_destroy(dnew)
+    sdel = torch.from_numpy((seq >> 31).astype(np.int32))
+    dist.all_reduce(sdel, op=dist.ReduceOp.MAX)
+    seq = (seq & np.uint32(0x7fffffff)) | (sdel.numpy().astype(np.uint32) << np.uint32(31))
+    abox = [None] * world
+    dist.all_gather_object(abox, arcs.tobytes())
+    from miniasm_b200.capi import ARC_DT
+    from miniasm_b200.pipeline import canon_arcs
+    allarcs = np.concatenate([np.frombuffer(bts, dtype=ARC_DT) for bts in abox])
+    gone = (seq >> 31).astype(bool)
+    allarcs = allarcs[~gone[(allarcs["ul"] >> np.uint64(33)).astype(np.int64)] & ~gone[(allarcs["v"] >> 1).astype(np.int64)]]
+    allarcs = allarcs[np.argsort(allarcs["ul"], kind="stable")]
+    truth.sg_gen()
+    tarcs, tseq, _, _, _ = truth.graph_np()
+    ok = ok and np.array_equal(seq, tseq) and len(tarcs) > 0 and np.array_equal(allarcs["ul"], tarcs["ul"]) \
+        and np.array_equal(canon_arcs(allarcs), canon_arcs(tarcs))
+    q.put((rank, bool(ok), int(len(loc)), int(n_seq), int(flag.sum()), int(dead.sum()), int(len(tarcs))))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _model_worker(rank, world, port, paf, q):
+    try:
+        _model_body(rank, world, port, paf, q)
+    except BaseException as ex:  # noqa: BLE001 -- a rank that dies would leave the others waiting in a collective: report and let the parent stop them
+        import traceback
+        q.put((rank, False, traceback.format_exc()[-1500:] or repr(ex)))
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -181,9 +266,20 @@ def test_sharding_scheme_model(world, built, paf_dir):
     ps = [ctx.Process(target=_model_worker, args=(r, world, port, paf, q)) for r in range(world)]
     for p in ps:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in ps)
+    res = []
+    try:
+        for _ in ps:
+            res.append(q.get(timeout=300))
+            assert res[-1][1], res[-1]
+    finally:
+        if len(res) < world or not all(r[1] for r in res):
+            for p in ps:
+                p.terminate()
     for p in ps:
         p.join(60)
-    assert [r for r, _, _, _ in res] == list(range(world))
-    assert all(ok for _, ok, _, _ in res), res
-    assert all(n > 0 for _, _, n, _ in res)
+    res.sort()
+    assert [r[0] for r in res] == list(range(world))
+    assert all(r[1] for r in res), res
+    # the model has teeth: hits on every rank, contained reads flagged, a non-trivial graph
+    assert all(r[2] > 0 and r[4] > 100 and r[5] >= r[4] and r[6] > 100 for r in res), res
+    print(res)
