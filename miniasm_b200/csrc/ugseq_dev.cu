@@ -17,6 +17,7 @@
 // the caller falls back to the host reader (host/gfa.c ma_ug_seq), which walks the file like kseq does.
 #include "ugseq_dev.cuh"
 #include "ingest_dev.cuh"
+#include "basecomp.cuh"
 #include <cub/cub.cuh>
 
 enum { LT_EMPTY = 0, LT_HEADER = 1, LT_PLUS = 2, LT_SEQ = 3 };
@@ -126,22 +127,6 @@ __device__ __forceinline__ char seq_base(const SeqSrc &f, uint64_t l0, uint64_t 
 	return f.text[f.start[a] + (want - f.cum[a])];
 }
 
-__device__ __forceinline__ unsigned char comp_of(unsigned char c) // asm.c:224-233 comp_tab, bytes >= 128 -> 'N' (asm.c:281)
-{
-	if (c >= 128) return 'N';
-	if (c == 96) return 64;
-	const unsigned char u = c & 0xdf, lower = c & 0x20;          // letters only below
-	if (u < 'A' || u > 'Z') return c;
-	unsigned char r;
-	switch (u) {
-		case 'A': r = 'T'; break; case 'T': r = 'A'; break; case 'U': r = 'A'; break; case 'C': r = 'G'; break; case 'G': r = 'C'; break;
-		case 'B': r = 'V'; break; case 'V': r = 'B'; break; case 'D': r = 'H'; break; case 'H': r = 'D'; break;
-		case 'K': r = 'M'; break; case 'M': r = 'K'; break; case 'R': r = 'Y'; break; case 'Y': r = 'R'; break;
-		default: r = u;
-	}
-	return r | lower;
-}
-
 // one warp per layout item k = (read, strand, length); its bytes go to out + seq_pos[unitig] + offset of the item in the unitig
 __global__ void k_ugseq_gather(SeqSrc f, const DUtgMeta *meta, uint32_t n_utg, const uint64_t *items, const uint32_t *ioff, uint64_t n_items,
                                const unsigned long long *rec_of_read, const DSub *sub, const uint64_t *seq_pos, char *out, unsigned long long *n_short)
@@ -163,7 +148,7 @@ __global__ void k_ugseq_gather(SeqSrc f, const DUtgMeta *meta, uint32_t n_utg, c
 		const uint64_t s0 = sub ? (sub[id].s_del & 0x7fffffffu) : 0, e0 = sub ? sub[id].e : sl;
 		if (sub ? e0 > sl : ln > sl) { if (lane == 0) atomicAdd(n_short, 1ull); continue; } // asm.c:263 asserts it
 		for (uint32_t i = lane; i < ln; i += 32)
-			dst[i] = rev ? (char)comp_of((unsigned char)seq_base(f, l0, l1, e0 - 1 - i)) : seq_base(f, l0, l1, s0 + i);
+			dst[i] = rev ? (char)mab_comp_of((unsigned char)seq_base(f, l0, l1, e0 - 1 - i)) : seq_base(f, l0, l1, s0 + i);
 	}
 }
 

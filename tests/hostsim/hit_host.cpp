@@ -3,8 +3,9 @@
 // miniasm_b200/csrc/hit2arc.cuh, the very header the CUDA kernels are built from -- compiled for the host and put behind the
 // loops of ma_hit_cut / ma_hit_flt / ma_sg_gen, so that the CPU tier can fuzz them against the unmodified reference with inputs
 // no synthetic PAF produces (hits reaching outside the kept intervals, wrapped spans, empty intervals, self hits):
-// tests/test_hitrules_cpu.py.
+// tests/test_hitrules_cpu.py.  Also here: mab_comp_of (basecomp.cuh), the reverse-strand complement of `-f reads`, all 256 byte values.
 #include "../../miniasm_b200/csrc/hit2arc.cuh"
+#include "../../miniasm_b200/csrc/basecomp.cuh"
 
 extern "C" {
 
@@ -58,6 +59,9 @@ size_t hs_sg_arcs(int max_hang, float int_frac, int min_ovlp, size_t n, const DH
 	}
 	return m;
 }
+
+// the complement of a sequence byte as the gather kernel of `-f reads` applies it (asm.c:224-233,281)
+unsigned char hs_comp(unsigned char c) { return mab_comp_of(c); }
 
 // the classification alone, for a histogram of what the fuzz reached
 int hs_hit2arc(const DHit *h, int ql, int tl, int max_hang, float int_frac, int min_ovlp, DArc *t) { return mab_hit2arc(*h, ql, tl, max_hang, int_frac, min_ovlp, t); }

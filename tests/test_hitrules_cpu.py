@@ -20,7 +20,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(loaders.REFERENCE_SO), reason
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SIM_SRC = os.path.join(ROOT, "tests", "hostsim", "hit_host.cpp")
 SIM_SO = os.path.join(ROOT, "tests", "hostsim", "libhit_host.so")
-HDRS = [os.path.join(ROOT, "miniasm_b200", "csrc", h) for h in ("hit2arc.cuh", "mab_common.cuh")]
+HDRS = [os.path.join(ROOT, "miniasm_b200", "csrc", h) for h in ("hit2arc.cuh", "mab_common.cuh", "basecomp.cuh")]
 CUDA_INC = "/usr/local/cuda/include"
 
 
@@ -35,6 +35,7 @@ def sim(built):
     dll.hs_hit_flt.restype, dll.hs_hit_flt.argtypes = C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_ulonglong)]
     dll.hs_sg_arcs.restype = C.c_size_t
     dll.hs_sg_arcs.argtypes = [C.c_int, C.c_float, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    dll.hs_comp.restype, dll.hs_comp.argtypes = C.c_ubyte, [C.c_ubyte]
     dll.hs_hit2arc.restype = C.c_int
     dll.hs_hit2arc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
     return dll
@@ -193,3 +194,41 @@ def test_fuzz_reaches_every_class(sim):
             seen[key] = seen.get(key, 0) + 1
     for cls in (-1, -2, -3, -4, ("arc", 0, 0), ("arc", 0, 1), ("arc", 1, 0), ("arc", 1, 1)):
         assert seen.get(cls, 0) > 0, (cls, seen)
+
+
+def test_complement_of_every_byte(ref, sim, tmp_path):
+    """The reverse-strand copy of ma_ug_seq (asm.c:277-282): complement through comp_tab (asm.c:224-233), bytes >= 128 become N.  The
+    gather kernel of `-f reads` computes it arithmetically (basecomp.cuh); all byte values a FASTA line can carry are compared with
+    what the reference's own ma_ug_seq writes for a one-read unitig on the reverse strand."""
+    vals = [c for c in range(1, 256) if c not in (10, 13)]          # NUL, LF, CR cannot be sequence bytes of a FASTA line
+    seq = bytes(vals) + b"ACGTacgtNn"
+    fa = tmp_path / "all_bytes.fa"
+    fa.write_bytes(b">r0\n" + seq + b"\n")
+    d = ref.sd_init()
+    ref.sd_put(d, b"r0", len(seq))
+    item = np.array([(0 << 33) | (1 << 32) | len(seq)], dtype=np.uint64)       # read 0, reverse strand, whole length
+    utg = (capi.MaUtg * 1)()
+    utg[0].len_circ, utg[0].start, utg[0].end, utg[0].n, utg[0].m = len(seq), 1, 0, 1, 1
+    utg[0].a, utg[0].s = item.ctypes.data_as(C.POINTER(C.c_uint64)), None
+    ug = capi.MaUg()
+    ug.n = ug.m = 1
+    ug.a, ug.g = C.cast(utg, C.POINTER(capi.MaUtg)), None
+    assert ref.ma_ug_seq(C.pointer(ug), d, None, str(fa).encode()) == 0
+    got = C.string_at(C.cast(utg[0].s, C.c_void_p), len(seq))        # the unitig as the reference filled it
+    want = bytes(sim.hs_comp(c) for c in reversed(seq))
+    assert got == want
+    assert got != bytes(reversed(seq))                               # (it is not the identity)
+    ref.sd_destroy(d)
+    # the host reader of the drop-in level (host/gfa.c ma_ug_seq, also the fallback for multi-line FASTQ) on the same file
+    prod = capi.load_product(strict=False)
+    d2 = prod.sd_init()
+    prod.sd_put(d2, b"r0", len(seq))
+    utg2 = (capi.MaUtg * 1)()
+    utg2[0].len_circ, utg2[0].start, utg2[0].end, utg2[0].n, utg2[0].m = len(seq), 1, 0, 1, 1
+    utg2[0].a, utg2[0].s = item.ctypes.data_as(C.POINTER(C.c_uint64)), None
+    ug2 = capi.MaUg()
+    ug2.n = ug2.m = 1
+    ug2.a, ug2.g = C.cast(utg2, C.POINTER(capi.MaUtg)), None
+    assert prod.ma_ug_seq(C.pointer(ug2), d2, None, str(fa).encode()) == 0
+    assert C.string_at(C.cast(utg2[0].s, C.c_void_p), len(seq)) == want
+    prod.sd_destroy(d2)
