@@ -24,6 +24,7 @@ file order (rank r generates and holds part r), read ids are hash-sharded (owner
 * cli    : the drop-in command line, cold process, PAF in /dev/shm, GFA to /dev/null (cli_wall_s).
 * noisy  : a 600 K-read set with jittered ends (tips, thousands of bubbles) through the same legs, next to the
            reference's time on the same file.
+* host_affinity : every rank runs on the host cores NVML names for its GPU (bound before the pinned buffers are allocated).
 --impl reference prints the same line for the reference's own CPU implementation (rank 0 only).
 """
 import argparse
@@ -197,6 +198,28 @@ def reference_full_size(name, shm, model, cores):
     return d
 
 
+def bind_near_gpu(torch, ordinal):
+    """Run this process on the host cores next to its GPU (NVML's CPU affinity of the device), before any pinned buffer exists: the
+    buffers then live on that NUMA node and the H2D copies of several ranks do not cross the socket link.  Best effort: any
+    failure leaves the affinity as it was.  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(ordinal)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08X}:{pr.pci_bus_id:02X}:{pr.pci_device_id:02X}.0")
+        except Exception:  # noqa: BLE001 -- older torch without the PCI fields: NVML order = CUDA order unless CUDA_VISIBLE_DEVICES reorders
+            h = pynvml.nvmlDeviceGetHandleByIndex(ordinal)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if word >> b & 1} & os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "why": "NVML affinity mask does not meet the allowed CPUs"}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "cpus": len(cpus), "source": "NVML CPU affinity of the GPU"}
+    except Exception as ex:  # noqa: BLE001
+        return {"bound": False, "why": f"{type(ex).__name__}: {ex}"[:120]}
+
+
 def host_cpu():
     model = "unknown"
     try:
@@ -278,6 +301,7 @@ def main():
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device; the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    affinity = bind_near_gpu(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = capi.load_product()
@@ -525,7 +549,7 @@ def main():
                          "peak_source": peak_src, "kernel": "k_del_trans_warp", "algorithmic_bytes": alg_bytes, "formula": "16*n_arc + 16*inner_iters + 1*n_arc + 12*n_vtx"},
             "roofline_phases": phases,
             "cpu_baseline": cpu, "cpu_full_size": full, "cli": cli, "noisy": noisy,
-            "clocks": clocks, "wall_s_timed_region": res["wall_dev"], "wall_ms_per_step": res["wall_dev"] / a.steps * 1e3,
+            "clocks": clocks, "host_affinity": affinity, "wall_s_timed_region": res["wall_dev"], "wall_ms_per_step": res["wall_dev"] / a.steps * 1e3,
         }
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
