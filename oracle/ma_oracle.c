@@ -127,6 +127,34 @@ static void msort64(size_t n, void *base, size_t width, size_t key_off)
 static int cmp_u32(const void *x, const void *y) { uint32_t a = *(const uint32_t*)x, b = *(const uint32_t*)y; return a < b ? -1 : a > b; }
 
 /* ------------------------------------------------------------------ PAF reading + hit loading: paf.c:34-67, hit.c:70-107 */
+typedef struct { char *qn, *tn; uint32_t ql, qs, qe, tl, ts, te, ml, bl, rev; } oline_t;
+
+/* one PAF line (terminated in place) -> fields; 0 if it has fewer than 10 columns (paf.c:34-56).  *stale_bl carries the 11th
+ * column of the last line that had one: a 10-column line keeps it */
+static int paf_fields(char *line, ssize_t len, oline_t *r, uint32_t *stale_bl)
+{
+	char *f[12], *p = line;
+	int nf = 0;
+	if (len && line[len - 1] == '\n') line[--len] = 0;
+	if (len > 1 && line[len - 1] == '\r') line[--len] = 0;       /* kseq.h:143 */
+	for (f[nf++] = p; *p && nf < 12; ++p) if (*p == '\t') { *p = 0; f[nf++] = p + 1; }
+	if (nf < 10) return 0;                                       /* paf.c:54 */
+	r->qn = f[0], r->tn = f[5];
+	r->ql = (uint32_t)strtol(f[1], 0, 10); r->qs = (uint32_t)strtol(f[2], 0, 10); r->qe = (uint32_t)strtol(f[3], 0, 10);
+	r->rev = f[4][0] == '-';
+	r->tl = (uint32_t)strtol(f[6], 0, 10); r->ts = (uint32_t)strtol(f[7], 0, 10); r->te = (uint32_t)strtol(f[8], 0, 10);
+	r->ml = (uint32_t)strtol(f[9], 0, 10) & 0x7fffffffu;
+	if (nf >= 11) { char *e = strchr(f[10], '\t'); if (e) *e = 0; *stale_bl = (uint32_t)strtol(f[10], 0, 10); }
+	r->bl = *stale_bl;
+	return 1;
+}
+
+/* the filter both passes over the PAF apply before anything else (hit.c:57 and hit.c:85): unsigned spans, signed match count */
+static int too_small(const oline_t *r, int min_span, int min_match)
+{
+	return r->qe - r->qs < (uint32_t)min_span || r->te - r->ts < (uint32_t)min_span || (int)r->ml < min_match;
+}
+
 ma_hit_t *ma_hit_read(const char *fn, int min_span, int min_match, sdict_t *d, size_t *n, int bi_dir, const sdict_t *excl)
 {
 	FILE *fp = fopen(fn, "rb");
@@ -137,31 +165,20 @@ ma_hit_t *ma_hit_read(const char *fn, int min_span, int min_match, sdict_t *d, s
 	uint32_t stale_bl = 0;
 	if (!fp) { fprintf(stderr, "[E::%s] could not open PAF file %s\n", __func__, fn); exit(1); }
 	while ((len = getline(&line, &cap, fp)) >= 0) {
-		char *f[12], *p = line;
-		int nf = 0;
-		uint32_t ql, qs, qe, tl, ts, te, ml, bl, rev;
-		if (len && line[len - 1] == '\n') line[--len] = 0;
-		if (len > 1 && line[len - 1] == '\r') line[--len] = 0;   /* kseq.h:143 */
-		for (f[nf++] = p; *p && nf < 12; ++p) if (*p == '\t') { *p = 0; f[nf++] = p + 1; }
-		if (nf < 10) continue;                                   /* paf.c:54 */
-		ql = (uint32_t)strtol(f[1], 0, 10); qs = (uint32_t)strtol(f[2], 0, 10); qe = (uint32_t)strtol(f[3], 0, 10);
-		rev = f[4][0] == '-';
-		tl = (uint32_t)strtol(f[6], 0, 10); ts = (uint32_t)strtol(f[7], 0, 10); te = (uint32_t)strtol(f[8], 0, 10);
-		ml = (uint32_t)strtol(f[9], 0, 10) & 0x7fffffffu;
-		if (nf >= 11) { char *e = strchr(f[10], '\t'); if (e) *e = 0; stale_bl = (uint32_t)strtol(f[10], 0, 10); }
-		bl = stale_bl;                                           /* a 10-field line keeps the previous bl */
-		if (qe - qs < (uint32_t)min_span || te - ts < (uint32_t)min_span || (int)ml < min_match) continue; /* hit.c:85 */
-		if (excl && (sd_get(excl, f[0]) >= 0 || sd_get(excl, f[5]) >= 0)) continue;
+		oline_t r;
+		if (!paf_fields(line, len, &r, &stale_bl)) continue;
+		if (too_small(&r, min_span, min_match)) continue;        /* hit.c:85 */
+		if (excl && (sd_get(excl, r.qn) >= 0 || sd_get(excl, r.tn) >= 0)) continue;
 		if (n_a + 2 > m_a) { m_a = m_a ? m_a * 2 : 256; a = (ma_hit_t*)realloc(a, m_a * sizeof(ma_hit_t)); }
 		{
-			uint32_t qid = (uint32_t)sd_put(d, f[0], ql), tid = (uint32_t)sd_put(d, f[5], tl);
+			uint32_t qid = (uint32_t)sd_put(d, r.qn, r.ql), tid = (uint32_t)sd_put(d, r.tn, r.tl);
 			ma_hit_t *h = &a[n_a++];
 			memset(h, 0, sizeof(*h));
-			h->qns = (uint64_t)qid << 32 | qs; h->qe = qe; h->tn = tid; h->ts = ts; h->te = te; h->rev = rev; h->ml = ml; h->bl = bl;
+			h->qns = (uint64_t)qid << 32 | r.qs; h->qe = r.qe; h->tn = tid; h->ts = r.ts; h->te = r.te; h->rev = r.rev; h->ml = r.ml; h->bl = r.bl;
 			if (bi_dir && qid != tid) {                          /* mirrored hit, hit.c:92-98 */
 				h = &a[n_a++];
 				memset(h, 0, sizeof(*h));
-				h->qns = (uint64_t)tid << 32 | ts; h->qe = te; h->tn = qid; h->ts = qs; h->te = qe; h->rev = rev; h->ml = ml; h->bl = bl;
+				h->qns = (uint64_t)tid << 32 | r.ts; h->qe = r.te; h->tn = qid; h->ts = r.qs; h->te = r.qe; h->rev = r.rev; h->ml = r.ml; h->bl = r.bl;
 			}
 		}
 	}
@@ -169,6 +186,38 @@ ma_hit_t *ma_hit_read(const char *fn, int min_span, int min_match, sdict_t *d, s
 	msort64(n_a, a, sizeof(ma_hit_t), 0);                        /* ma_hit_sort, hit.c:19-22 */
 	*n = n_a;
 	return a;
+}
+
+/* ------------------------------------------------------------------ -R prefilter: hit.c:38-68
+ * A first pass over the PAF that names the reads to leave out: a read lying, with short overhangs, well inside a read more
+ * than twice its length.  The result is the `excl` dictionary of ma_hit_read. */
+sdict_t *ma_hit_no_cont(const char *fn, int min_span, int min_match, int max_hang, float int_frac)
+{
+	FILE *fp = fopen(fn, "rb");
+	char *line = 0;
+	size_t cap = 0;
+	ssize_t len;
+	uint32_t stale_bl = 0;
+	sdict_t *d;
+	const int near = max_hang >> 2, far = max_hang << 1;
+	if (!fp) { fprintf(stderr, "[E::%s] could not open PAF file %s\n", __func__, fn); exit(1); }
+	d = sd_init();
+	while ((len = getline(&line, &cap, fp)) >= 0) {
+		oline_t r;
+		int t5, t3;                                              /* target bases beyond the match, at the query's 5' / 3' side */
+		if (!paf_fields(line, len, &r, &stale_bl) || too_small(&r, min_span, min_match)) continue;
+		t5 = (int)(r.rev ? r.tl - r.te : r.ts), t3 = (int)(r.rev ? r.ts : r.tl - r.te);
+		if (r.ql >> 1 > r.tl) {                                  /* long query, short target: hit.c:60-63 */
+			if (t5 > near || t3 > near || (float)(r.te - r.ts) < (float)r.tl * int_frac) continue;
+			if ((int)r.qs - t5 > far && (int)(r.ql - r.qe) - t3 > far) sd_put(d, r.tn, r.tl);
+		} else if (r.ql < r.tl >> 1) {                           /* the mirror case: hit.c:64-67 (unsigned compares on the query side) */
+			if (r.qs > (uint32_t)near || r.ql - r.qe > (uint32_t)near || (float)(r.qe - r.qs) < (float)r.ql * int_frac) continue;
+			if (t5 - (int)r.qs > far && t3 - (int)(r.ql - r.qe) > far) sd_put(d, r.qn, r.ql);
+		}
+	}
+	free(line); fclose(fp);
+	if (ma_verbose >= 3) fprintf(stderr, "[M::%s] dropped %d contained reads\n", __func__, d->n_seq);
+	return d;
 }
 
 /* ------------------------------------------------------------------ the classifier: miniasm.h:86-104 */
@@ -680,6 +729,131 @@ void ma_ug_destroy(ma_ug_t *ug)
 	if (!ug) return;
 	for (i = 0; i < ug->u.n; ++i) { free(ug->u.a[i].a); free(ug->u.a[i].s); }
 	free(ug->u.a); asg_destroy(ug->g); free(ug);
+}
+
+/* ------------------------------------------------------------------ unitig sequences: asm.c:212-290, kseq.h:163-211
+ * The reads file (FASTA or FASTQ, plain or gzip, "-" = stdin) is walked record by record the way kseq_read does:
+ *   header   : '>' or '@', name = bytes up to the first white space, rest of the line ignored;
+ *   sequence : following lines joined, until a line STARTS with '>', '@' or '+'; empty lines skipped; after every line one
+ *              trailing CR is dropped from what has been collected so far (if more than one byte has);
+ *   '+'      : rest of that line skipped, then quality lines (same CR rule) until they are at least as long as the
+ *              sequence; a different length ends the whole scan (kseq_read returns -2, asm.c:261 stops);
+ *   after a FASTQ record the next header is hunted for byte by byte (any '>' or '@'), after a FASTA record it is the
+ *   byte that ended the sequence. */
+#include <zlib.h>
+#include <ctype.h>
+
+typedef struct { gzFile f; unsigned char buf[1 << 16]; int n, at; } rd_t;
+typedef struct { size_t l, m; char *s; } ostr_t;
+
+static int rd_byte(rd_t *r)
+{
+	if (r->at >= r->n) {
+		r->n = gzread(r->f, r->buf, sizeof(r->buf)), r->at = 0;
+		if (r->n <= 0) { r->n = 0; return -1; }
+	}
+	return r->buf[r->at++];
+}
+static int rd_more(rd_t *r) { int c = rd_byte(r); if (c >= 0) --r->at; return c >= 0; }
+static void ostr_push(ostr_t *s, int c) { if (s->l + 2 > s->m) { s->m = s->m ? s->m * 2 : 256; s->s = (char*)realloc(s->s, s->m); } s->s[s->l++] = (char)c; s->s[s->l] = 0; }
+/* rest of the current line appended to s, CR rule applied; -1 if the input was already exhausted */
+static int rd_rest_of_line(rd_t *r, ostr_t *s)
+{
+	int c;
+	if (!rd_more(r)) return -1;
+	while ((c = rd_byte(r)) >= 0 && c != '\n') ostr_push(s, c);
+	if (s->l > 1 && s->s[s->l - 1] == '\r') s->s[--s->l] = 0;
+	return 0;
+}
+
+/* next record: >= 0 length of the sequence, -1 end of input, -2 broken quality.  *head = the header byte already consumed (0: hunt) */
+static int next_record(rd_t *r, int *head, ostr_t *name, ostr_t *seq, ostr_t *qual)
+{
+	int c;
+	if (*head == 0) {
+		while ((c = rd_byte(r)) >= 0 && c != '>' && c != '@');
+		if (c < 0) return -1;
+		*head = c;
+	}
+	name->l = seq->l = qual->l = 0;
+	if (!rd_more(r)) return -1;
+	while ((c = rd_byte(r)) >= 0 && !isspace(c)) ostr_push(name, c);
+	if (name->l == 0) ostr_push(name, 0), name->l = 0;           /* keep name->s a valid empty string */
+	if (c >= 0 && c != '\n') while ((c = rd_byte(r)) >= 0 && c != '\n');
+	while ((c = rd_byte(r)) >= 0 && c != '>' && c != '+' && c != '@') {
+		if (c == '\n') continue;
+		ostr_push(seq, c);
+		rd_rest_of_line(r, seq);                                 /* (at the end of the input nothing is appended and no CR is dropped) */
+	}
+	if (c == '>' || c == '@') *head = c;
+	if (c != '+') return (int)seq->l;
+	while ((c = rd_byte(r)) >= 0 && c != '\n');
+	if (c < 0) return -2;
+	while (rd_rest_of_line(r, qual) >= 0 && qual->l < seq->l);
+	*head = 0;
+	return seq->l == qual->l ? (int)seq->l : -2;
+}
+
+static unsigned char comp_of[128];
+static void comp_init(void)                                     /* asm.c:224-233 as a rule: IUPAC pairs swap, U -> A, the rest stays */
+{
+	static const char pair[] = "ATCGMKRYVBHD";
+	int i;
+	for (i = 0; i < 128; ++i) comp_of[i] = (unsigned char)i;
+	for (i = 0; pair[i]; i += 2) {
+		comp_of[(int)pair[i]] = pair[i + 1], comp_of[(int)pair[i + 1]] = pair[i];
+		comp_of[pair[i] | 32] = pair[i + 1] | 32, comp_of[pair[i + 1] | 32] = pair[i] | 32;
+	}
+	comp_of['U'] = 'A', comp_of['u'] = 'a';
+	comp_of[96] = 64;                                            /* the table's row of lower-case letters starts with '@' (asm.c:231) */
+}
+
+int ma_ug_seq(ma_ug_t *ug, const sdict_t *d, const ma_sub_t *sub, const char *fn)
+{
+	typedef struct { uint32_t utg:31, rev:1, at, len; } place_t;  /* where a read goes: asm.c:246-257 */
+	rd_t *r;
+	place_t *pl;
+	ostr_t name = {0,0,0}, seq = {0,0,0}, qual = {0,0,0};
+	int head = 0, l;
+	size_t i, j;
+	gzFile f = fn && strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(fileno(stdin), "r");
+	if (f == 0) return -1;
+	comp_init();
+	r = (rd_t*)calloc(1, sizeof(rd_t));
+	r->f = f;
+	pl = (place_t*)calloc(d->n_seq ? d->n_seq : 1, sizeof(place_t));
+	for (i = 0; i < ug->u.n; ++i) {
+		ma_utg_t *u = &ug->u.a[i];
+		uint32_t at = 0;
+		u->s = (char*)calloc(1, (size_t)u->len + 1);
+		memset(u->s, 'N', u->len);                               /* reads missing from the file stay N (asm.c:249) */
+		for (j = 0; j < u->n; ++j) {
+			place_t *p = &pl[u->a[j] >> 33];
+			assert(p->len == 0);                                 /* a read sits in one place only (asm.c:252) */
+			p->utg = (uint32_t)i, p->rev = u->a[j] >> 32 & 1, p->at = at, p->len = (uint32_t)u->a[j];
+			at += p->len;
+		}
+	}
+	while ((l = next_record(r, &head, &name, &seq, &qual)) >= 0) {
+		int32_t id = sd_get(d, name.s);
+		const place_t *p;
+		const char *b = seq.s;
+		size_t bl = seq.l;
+		char *dst;
+		uint32_t k;
+		if (id < 0 || pl[id].len == 0) continue;
+		p = &pl[id];
+		if (sub) {                                               /* only the kept interval of the read counts (asm.c:262-266) */
+			assert(sub[id].e - sub[id].s <= bl);
+			b += sub[id].s, bl = sub[id].e - sub[id].s;
+		}
+		dst = ug->u.a[p->utg].s + p->at;
+		if (!p->rev) memcpy(dst, b, p->len);
+		else for (k = 0; k < p->len; ++k) { unsigned char c = (unsigned char)b[bl - 1 - k]; dst[k] = c >= 128 ? 'N' : (char)comp_of[c]; }
+	}
+	free(name.s); free(seq.s); free(qual.s); free(pl);
+	gzclose(f); free(r);
+	return 0;
 }
 
 /* ------------------------------------------------------------------ writers: asm.c:41-55,77-116 */

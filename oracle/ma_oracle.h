@@ -28,6 +28,7 @@ void sd_destroy(sdict_t *d);
 int32_t sd_get(const sdict_t *d, const char *name);
 int32_t sd_put(sdict_t *d, const char *name, uint32_t len);
 int32_t *sd_squeeze(sdict_t *d);
+sdict_t *ma_hit_no_cont(const char *fn, int min_span, int min_match, int max_hang, float int_frac);
 ma_hit_t *ma_hit_read(const char *fn, int min_span, int min_match, sdict_t *d, size_t *n, int bi_dir, const sdict_t *excl);
 ma_sub_t *ma_hit_sub(int min_dp, float min_iden, int end_clip, size_t n, const ma_hit_t *a, size_t n_sub);
 size_t ma_hit_cut(const ma_sub_t *reg, int min_span, size_t n, ma_hit_t *a);
@@ -52,6 +53,7 @@ int asg_cut_internal(asg_t *g, int max_ext);
 int asg_cut_biloop(asg_t *g, int max_ext);
 int asg_pop_bubble(asg_t *g, int max_dist);
 ma_ug_t *ma_ug_gen(asg_t *g);
+int ma_ug_seq(ma_ug_t *ug, const sdict_t *d, const ma_sub_t *sub, const char *fn);
 void ma_ug_destroy(ma_ug_t *ug);
 void ma_sg_print(const asg_t *g, const sdict_t *d, const ma_sub_t *sub, FILE *fp);
 void ma_ug_print(const ma_ug_t *ug, const sdict_t *d, const ma_sub_t *sub, FILE *fp);

@@ -1,5 +1,6 @@
 """CPU tier: the oracle port step by step against the unmodified reference (oracle/_ref/libminiasm_ref.so) --
 this is what pins the restatement, since the reference has no tests of its own."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -91,3 +92,48 @@ def test_tied_arcs_decide_the_counter_not_the_graph(ref, port):
     assert res[True][0] == res[False][0] + 1                     # v -> x is reduced by the pass itself only when w2 comes first
     assert np.array_equal(canon_arcs(res[True][1][0]), canon_arcs(res[False][1][0]))
     assert len(res[True][1][0]) == 6                             # v -> w1 -> w2 -> x and the complement chain remain
+
+
+@pytest.mark.parametrize("args", ["-n 4000 -l 2000 -L 30000 -c 30 -j 100 -s 41", "-n 6000 -l 1500 -L 40000 -c 40 -j 300 -s 42 -d 20000"])
+@pytest.mark.parametrize("hang,frac", [(1000, 0.8), (200, 0.5), (4000, 0.95)])
+def test_port_no_cont(args, hang, frac, ref, port, paf_dir):
+    """-R: ma_hit_no_cont (hit.c:38-68) and ma_hit_read with its exclusion list (hit.c:86) -- read lengths
+    spread over a factor of 20, so many reads lie clearly inside a read twice as long."""
+    paf = synth.generate(args, f"{paf_dir}/nocont_{len(args)}.paf").encode()
+    dr, dp = ref.ma_hit_no_cont(paf, 2000, 100, hang, frac), port.ma_hit_no_cont(paf, 2000, 100, hang, frac)
+    names = lambda d: [(d.contents.seq[i].name, d.contents.seq[i].len) for i in range(d.contents.n_seq)]
+    assert names(dr) == names(dp) and (len(names(dr)) > 20 or hang == 4000)
+    out = []
+    for lib, excl in ((ref, dr), (port, dp)):
+        d, n = lib.sd_init(), C.c_size_t(0)
+        h = lib.ma_hit_read(paf, 2000, 100, d, C.byref(n), 1, excl)
+        a = mask(capi.np_from_ptr(h, n.value, capi.HIT_DT))
+        out.append((names(d), np.sort(a, order=list(capi.HIT_DT.names))))
+        capi.c_free(h), lib.sd_destroy(d)
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+    gone = {nm for nm, _ in names(dr)}
+    assert gone and not gone & {nm for nm, _ in out[0][0]}
+    ref.sd_destroy(dr), port.sd_destroy(dp)
+
+
+@pytest.mark.parametrize("style,ext", [("fa_wrap", "fa"), ("fa_one_crlf", "fa"), ("fa_var_gaps_extra_dups_missing", "fa"), ("fa_wrap", "fa.gz"),
+                                       ("fq", "fq"), ("fq_crlf_extra_dups", "fq"), ("fq_missing", "fq.gz"), ("fq_multi", "fq")])
+def test_port_ug_seq(style, ext, ref, port, paf_dir):
+    """-f reads: ma_ug_seq (asm.c:236-290 over kseq.h:163-211) -- FASTA / FASTQ, wrapped, CRLF, gzip, empty
+    lines, multi-line FASTQ, records missing / foreign / repeated; the port fills the unitigs the reference built."""
+    from tests.test_cli_gpu import _reads_file
+    paf = synth.generate("chaos_small", f"{paf_dir}/chaos_small.paf")
+    reads = _reads_file(paf, f"{paf_dir}/port_{style}.{ext}", style).encode()
+    r = Pipeline(ref, paf).read().select().sg_gen().clean().ug_gen()
+    want = r.gfa(reads.decode())                                  # reference fills r.ug and prints it
+    ug2 = ref.ma_ug_gen(r.sg)                                    # a second, empty layout of the same graph for the port
+    dp = port.sd_init()                                          # (a dictionary's index is private to the library that made it)
+    for i in range(r.d.contents.n_seq):
+        port.sd_put(dp, r.d.contents.seq[i].name, r.d.contents.seq[i].len)
+    assert port.ma_ug_seq(ug2, dp, r.sub, reads) == 0
+    got = ref.print_to_string("ma_ug_print", ug2, r.d, r.sub)
+    ref.ma_ug_destroy(ug2)
+    assert got == want and b"\t*\tLN" not in want and want.count(b"S\t") > 0
+    assert port.ma_ug_seq(ref.ma_ug_gen(r.sg), dp, r.sub, b"/nonexistent/reads.fa") == -1      # asm.c:243
+    port.sd_destroy(dp)
+    r.free()
