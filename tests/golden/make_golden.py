@@ -67,7 +67,38 @@ def main():
             with gzip.GzipFile(os.path.join(HERE, name + ".gfa.gz"), "wb", mtime=0) as f:
                 f.write(gfa)
         print(name, rec["paf_lines"], "lines", len(gfa), "GFA bytes")
+    next_rows(tmp)
+
+
+NEXT_R = "-n 4000 -l 2000 -L 30000 -c 30 -j 100 -s 41"          # read lengths spread over a factor of 15: -R has something to drop
+NEXT_F = ["fa_var_gaps_extra_dups_missing.fa", "fq_crlf_extra_dups.fq", "fq_multi.fq"]
+
+
+def next_rows(tmp):
+    """`-R` on a length-skewed set, `-f reads` on three layouts of the reads file (written by the
+    generator the tests use, tests/test_cli_gpu.py::_reads_file; the files are identified by their sha256)."""
+    from tests.test_cli_gpu import _reads_file
+    rec = {"R": {}, "f": {}}
+    paf = synth.generate(NEXT_R, os.path.join(tmp, "next_R.paf"))
+    gfa, err = run(["-R", paf])
+    rec["R"] = {"pafgen_args": NEXT_R, "paf_sha256": synth.sha256(paf), "gfa_sha256": hashlib.sha256(gfa).hexdigest(),
+                "dropped": [ln.partition("] ")[2] for ln in err.splitlines() if "dropped" in ln],
+                "stderr_counts": [c for c in counts(err) if not c.startswith("main:")]}
+    paf = synth.generate("chaos_small", os.path.join(tmp, "chaos_small.paf"))
+    for fn in NEXT_F:
+        style, ext = fn.rsplit(".", 1)
+        reads = _reads_file(paf, os.path.join(tmp, "next_" + fn), style)
+        gfa, _ = run(["-f", reads, paf])
+        rec["f"][fn] = {"reads_sha256": hashlib.sha256(open(reads, "rb").read()).hexdigest(), "gfa_sha256": hashlib.sha256(gfa).hexdigest(),
+                        "gfa_bytes": len(gfa)}
+    with open(os.path.join(HERE, "next_rows.json"), "w") as f:
+        json.dump(rec, f, indent=1, sort_keys=True)
+    print("next rows:", rec["R"]["dropped"], {k: v["gfa_bytes"] for k, v in rec["f"].items()})
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["next"]:
+        os.makedirs("/tmp/mab_golden", exist_ok=True)
+        next_rows("/tmp/mab_golden")
+    else:
+        main()

@@ -109,3 +109,33 @@ def test_golden_files_are_current(name, pafs):
     import subprocess
     out = subprocess.run([os.path.join(capi.ROOT, "oracle", "_ref", "miniasm_ref"), pafs[name]], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
     assert hashlib.sha256(out).hexdigest() == gold(name)["gfa_sha256"]
+
+
+def test_oracle_port_next_rows(port, paf_dir):
+    """SURVEY.md 8f rows 2 and 3 against vectors the reference binary produced (tests/golden/next_rows.json, make_golden.py next):
+    `-R` (ma_hit_no_cont + ma_hit_read with its exclusion list) and `-f reads` (ma_ug_seq) through the port."""
+    import ctypes as C
+
+    from tests.golden.make_golden import NEXT_F
+    from tests.test_cli_gpu import _reads_file
+    g = json.load(open(os.path.join(GOLD, "next_rows.json")))
+    paf = synth.generate(g["R"]["pafgen_args"], f"{paf_dir}/next_R.paf")
+    assert synth.sha256(paf) == g["R"]["paf_sha256"]
+    p = Pipeline(port, paf)
+    o = p.opt
+    excl = port.ma_hit_no_cont(p.paf, o.min_span, o.min_match, o.max_hang, o.int_frac)
+    assert f"dropped {excl.contents.n_seq} contained reads" == g["R"]["dropped"][0]
+    p.d, n = port.sd_init(), C.c_size_t(0)
+    p.hits = port.ma_hit_read(p.paf, o.min_span, o.min_match, p.d, C.byref(n), 1, excl)
+    p.n_hits = n.value
+    assert f"stored {p.n_hits} hits and {p.d.contents.n_seq} sequences" in g["R"]["stderr_counts"][0]
+    text = p.select().sg_gen().clean().ug_gen().gfa()
+    assert hashlib.sha256(text).hexdigest() == g["R"]["gfa_sha256"]
+    p.free(), port.sd_destroy(excl)
+    paf = synth.generate("chaos_small", f"{paf_dir}/chaos_small.paf")
+    for fn in NEXT_F:
+        style, ext = fn.rsplit(".", 1)
+        reads = _reads_file(paf, f"{paf_dir}/next_{fn}", style)
+        assert hashlib.sha256(open(reads, "rb").read()).hexdigest() == g["f"][fn]["reads_sha256"]
+        text = Pipeline(port, paf).run_all(reads)
+        assert len(text) == g["f"][fn]["gfa_bytes"] and hashlib.sha256(text).hexdigest() == g["f"][fn]["gfa_sha256"], fn
